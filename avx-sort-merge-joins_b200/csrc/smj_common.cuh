@@ -1,0 +1,139 @@
+// smj_common.cuh -- shared helpers for the sm_100a kernels (internal, not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef unsigned long long u64;
+typedef unsigned int       u32;
+
+// ---------------------------------------------------------------------------------------
+// runtime context (smj_runtime.cu)
+// ---------------------------------------------------------------------------------------
+struct SmjCtx {
+    int          device;
+    int          sm_count;
+    cudaStream_t stream;      // stream all kernels are launched on
+    cudaStream_t own_stream;  // the library's own stream (used when the caller sets none)
+    u64          launches;    // kernels launched so far
+    bool         ready;
+};
+SmjCtx *smj_ctx();                 // initialises lazily; nullptr on failure
+int     smj_fail(cudaError_t e, const char *what, const char *file, int line);
+int     smj_fail_msg(const char *msg);
+
+#define SMJ_CHECK(expr)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (expr);                                              \
+        if (e__ != cudaSuccess) return smj_fail(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// every kernel launch goes through this so that gpu_launches is a real count
+#define SMJ_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+    do {                                                                       \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+        (ctx)->launches++;                                                     \
+        cudaError_t e__ = cudaGetLastError();                                  \
+        if (e__ != cudaSuccess) return smj_fail(e__, #kernel, __FILE__, __LINE__); \
+    } while (0)
+
+// stream-ordered scratch allocation with automatic release at scope exit
+struct SmjScratch {
+    SmjCtx *ctx;
+    void   *ptrs[32];
+    int     n;
+    u64     bytes;
+    explicit SmjScratch(SmjCtx *c) : ctx(c), n(0), bytes(0) {}
+    ~SmjScratch() { release(); }
+    void *get(size_t nbytes) {
+        if (n >= 32) return nullptr;
+        void *p = nullptr;
+        if (nbytes == 0) nbytes = 16;
+        if (cudaMallocAsync(&p, nbytes, ctx->stream) != cudaSuccess) return nullptr;
+        ptrs[n++] = p;
+        bytes += nbytes;
+        return p;
+    }
+    void release() {
+        for (int i = 0; i < n; i++) cudaFreeAsync(ptrs[i], ctx->stream);
+        n = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#define SMJ_FULL_MASK 0xffffffffu
+
+// bucket(x) = ((x - sub) >> shift) & mask.  sub = 1<<32 turns key into key-1 without touching
+// the payload half (reference HASH_BIT_MODULO, src/partition/partition.c:29).
+struct DigitFn {
+    u64 sub;
+    u32 shift;
+    u32 mask;
+    __host__ __device__ __forceinline__ u32 operator()(u64 x) const {
+        return (u32)((x - sub) >> shift) & mask;
+    }
+    __host__ __device__ __forceinline__ u32 last_bin() const { return mask; }
+};
+
+// destination of an item under range partitioning: number of splitters <= key (at most 32 parts)
+struct SplitFn {
+    u32 nparts;
+    u32 sp[31];
+    __host__ __device__ __forceinline__ u32 operator()(u64 x) const {
+        const u32 k = (u32)(x >> 32);
+        u32       d = 0;
+#pragma unroll
+        for (int i = 0; i < 31; i++)
+            if (i + 1 < (int)nparts) d += (sp[i] <= k) ? 1u : 0u;
+        return d;
+    }
+    __host__ __device__ __forceinline__ u32 last_bin() const { return nparts - 1; }
+};
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// streaming (read-once) loads/stores: keep L1 clean, let L2 do the write combining
+__device__ __forceinline__ u64 ld_stream(const u64 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(u64 *p, u64 v) { __stcs(p, v); }
+
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ u64 warp_reduce_add(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SMJ_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ u64 warp_reduce_or(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(SMJ_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ u64 warp_reduce_and(u64 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v &= __shfl_xor_sync(SMJ_FULL_MASK, v, o);
+    return v;
+}
+
+static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// The join checksum (DESIGN.md / SURVEY.md 8d): sum over matched pairs of A(r)*B(s) mod 2^64.
+__host__ __device__ __forceinline__ u64 smj_cks_a(u64 r) {
+    return (r >> 32) * 0x9E3779B97F4A7C15ull + (r & 0xffffffffull) * 0xC2B2AE3D27D4EB4Full + 1ull;
+}
+__host__ __device__ __forceinline__ u64 smj_cks_b(u64 s) {
+    return (s >> 32) * 0x165667B19E3779F9ull + (s & 0xffffffffull) * 0x27D4EB2F165667C5ull + 1ull;
+}

@@ -1,0 +1,217 @@
+// smj_merge.cu -- merge-path 2-way merge and batched k-way merge of sorted runs.
+//
+// B200 restatement of
+//   * src/merge/merge.c:28-235 (scalar_merge_*, avx_merge_*) and the bitonic merge kernels
+//     merge{4,8,16}_{eqlen,varlen} of src/avxsort/avxsort_core.h:111-1211
+//   * src/merge/avx_multiwaymerge.c:199-338 avx_multiway_merge (binary tree of cache resident
+//     FIFOs)  ->  ceil(log2 k) rounds of pairwise merges, every pair of a round in ONE launch.
+//
+// Instead of a sequential two-cursor loop (CPU) the output is cut into fixed tiles along the
+// merge path: k_mp_partition binary-searches where each tile starts in A and B, k_mp_merge loads
+// the two pieces into shared memory, every thread finds its own 8-item slice by a second
+// (shared-memory) search and merges it serially; the tile is written back coalesced.
+//
+// HBM traffic: 16 B per item per round (+ 2 binary searches per 4096-item tile).
+#include "smj_common.cuh"
+#include "../../include/smj_device.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+constexpr int MP_THREADS = 512;
+constexpr int MP_IPT     = 8;
+constexpr int MP_TILE    = MP_THREADS * MP_IPT;  // 4096 items = 32 KB of shared memory
+
+struct MergeJob {
+    const u64 *a;
+    const u64 *b;
+    u64       *out;
+    u64        na, nb;
+    u64        tile_begin;  // index of this job's first tile in the launch
+};
+
+// mode 0: whole-word compare (AVX kernels, src/avxsort/avxcommon.h:186), A first on ties
+// mode 1: key-only compare, B first on ties (scalar_merge_tuples, src/merge/merge.c:78-87)
+template <int MODE>
+__device__ __forceinline__ bool a_goes_first(u64 a, u64 b) {
+    if (MODE == 0) return a <= b;
+    return (a >> 32) < (b >> 32);
+}
+
+// number of A items among the first `diag` items of the merged sequence
+template <int MODE, typename PA, typename PB>
+__device__ __forceinline__ u64 merge_path(PA a, u64 na, PB b, u64 nb, u64 diag) {
+    u64 lo = diag > nb ? diag - nb : 0;
+    u64 hi = diag < na ? diag : na;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (a_goes_first<MODE>(a[mid], b[diag - 1 - mid]))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ u32 find_job(const MergeJob *jobs, u32 njobs, u64 tile) {
+    u32 lo = 0, hi = njobs;  // last job with tile_begin <= tile
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (jobs[mid].tile_begin <= tile)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_mp_partition(const MergeJob *__restrict__ jobs, u32 njobs,
+                                                      u64 total_tiles, u64 *__restrict__ diag_a) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_tiles) return;
+    const MergeJob j    = jobs[find_job(jobs, njobs, t)];
+    u64            diag = (t - j.tile_begin) * MP_TILE;
+    diag_a[t]           = merge_path<MODE>(j.a, j.na, j.b, j.nb, diag);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restrict__ jobs,
+                                                         u32 njobs, u64 total_tiles,
+                                                         const u64 *__restrict__ diag_a) {
+    __shared__ u64 s_in[MP_TILE];
+    const u64      t  = blockIdx.x;
+    const u32      ji = find_job(jobs, njobs, t);
+    const MergeJob j  = jobs[ji];
+    const u64 local   = t - j.tile_begin;
+    const u64 total   = j.na + j.nb;
+    const u64 d0      = local * MP_TILE;
+    const u64 d1      = min(d0 + (u64)MP_TILE, total);
+    const bool last   = (ji + 1 < njobs) ? (t + 1 == jobs[ji + 1].tile_begin) : (t + 1 == total_tiles);
+    const u64 a0 = diag_a[t], a1 = last ? j.na : diag_a[t + 1];
+    const u64 b0 = d0 - a0, b1 = d1 - a1;
+    const u32 la = (u32)(a1 - a0), lb = (u32)(b1 - b0), cnt = la + lb;
+
+    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS)
+        s_in[i] = (i < la) ? ld_stream(j.a + a0 + i) : ld_stream(j.b + b0 + (i - la));
+    __syncthreads();
+
+    const u64 *sa = s_in, *sb = s_in + la;
+    const u32  d  = min((u32)(threadIdx.x * MP_IPT), cnt);
+    u32        ai = (u32)merge_path<MODE>(sa, (u64)la, sb, (u64)lb, (u64)d);
+    u32        bi = d - ai;
+    u64        r[MP_IPT];
+#pragma unroll
+    for (int k = 0; k < MP_IPT; k++) {
+        r[k] = 0;
+        if (d + k < cnt) {
+            bool take_a = (bi >= lb) || (ai < la && a_goes_first<MODE>(sa[ai], sb[bi]));
+            r[k]        = take_a ? sa[ai++] : sb[bi++];
+        }
+    }
+    __syncthreads();  // everyone is done reading the inputs: reuse the buffer for the output
+#pragma unroll
+    for (int k = 0; k < MP_IPT; k++)
+        if (d + k < cnt) s_in[d + k] = r[k];
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[i]);
+}
+
+int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
+    u64                   total_tiles = 0;
+    std::vector<MergeJob> jobs;
+    for (MergeJob j : jobs_h) {
+        if (j.na + j.nb == 0) continue;
+        j.tile_begin = total_tiles;
+        total_tiles += div_up(j.na + j.nb, MP_TILE);
+        jobs.push_back(j);
+    }
+    if (jobs.empty()) return 0;
+    SmjScratch sc(ctx);
+    MergeJob  *d_jobs = (MergeJob *)sc.get(jobs.size() * sizeof(MergeJob));
+    u64       *d_diag = (u64 *)sc.get((total_tiles + 1) * 8);
+    if (!d_jobs || !d_diag) return smj_fail_msg("merge: scratch allocation failed");
+    SMJ_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(MergeJob),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    const u32 nj = (u32)jobs.size();
+    const unsigned pgrid = (unsigned)div_up(total_tiles, 256);
+    if (mode == 0) {
+        SMJ_LAUNCH(ctx, k_mp_partition<0>, pgrid, 256, 0, d_jobs, nj, total_tiles, d_diag);
+        SMJ_LAUNCH(ctx, k_mp_merge<0>, (unsigned)total_tiles, MP_THREADS, 0, d_jobs, nj,
+                   total_tiles, d_diag);
+    } else {
+        SMJ_LAUNCH(ctx, k_mp_partition<1>, pgrid, 256, 0, d_jobs, nj, total_tiles, d_diag);
+        SMJ_LAUNCH(ctx, k_mp_merge<1>, (unsigned)total_tiles, MP_THREADS, 0, d_jobs, nj,
+                   total_tiles, d_diag);
+    }
+    // jobs_h lives in pageable memory: the async copy above has already staged it
+    return 0;
+}
+
+}  // namespace
+
+int smj_merge2(SmjCtx *ctx, const u64 *a, u64 na, const u64 *b, u64 nb, u64 *out, int mode) {
+    std::vector<MergeJob> jobs(1);
+    jobs[0] = {a, b, out, na, nb, 0};
+    return run_jobs(ctx, jobs, mode);
+}
+
+// runs[i] / lens[i]: host arrays of device pointers.  Result in out.
+int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, const u64 *lens,
+                       u32 nruns, int mode) {
+    struct Run {
+        const u64 *p;
+        u64        n;
+    };
+    std::vector<Run> cur;
+    for (u32 i = 0; i < nruns; i++)
+        if (lens[i]) cur.push_back({runs[i], lens[i]});
+    if (cur.empty()) return 0;
+    int rounds = 0;
+    while ((1ull << rounds) < cur.size()) rounds++;
+    if (rounds == 0) rounds = 1;  // a single run is copied by a merge with an empty partner
+    for (int r = 1; r <= rounds; r++) {
+        u64 *dst = ((rounds - r) % 2 == 0) ? out : tmp;
+        std::vector<MergeJob> jobs;
+        std::vector<Run>      next;
+        u64                   off = 0;
+        for (size_t i = 0; i < cur.size(); i += 2) {
+            MergeJob j;
+            j.a   = cur[i].p;
+            j.na  = cur[i].n;
+            j.b   = (i + 1 < cur.size()) ? cur[i + 1].p : nullptr;
+            j.nb  = (i + 1 < cur.size()) ? cur[i + 1].n : 0;
+            j.out = dst + off;
+            j.tile_begin = 0;
+            jobs.push_back(j);
+            next.push_back({dst + off, j.na + j.nb});
+            off += j.na + j.nb;
+        }
+        int rc = run_jobs(ctx, jobs, mode);
+        if (rc) return rc;
+        cur.swap(next);
+    }
+    return 0;
+}
+
+extern "C" int smjdev_merge(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb,
+                            uint64_t *out, int mode) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    return smj_merge2(ctx, (const u64 *)a, na, (const u64 *)b, nb, (u64 *)out, mode);
+}
+
+extern "C" int smjdev_multiway_merge(uint64_t *out, uint64_t *tmp, const uint64_t *const *runs,
+                                     const uint64_t *lens, uint32_t nruns, int mode) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    std::vector<const u64 *> r(nruns);
+    std::vector<u64>         l(nruns);
+    for (u32 i = 0; i < nruns; i++) {
+        r[i] = (const u64 *)runs[i];
+        l[i] = lens[i];
+    }
+    return smj_multiway_merge(ctx, (u64 *)out, (u64 *)tmp, r.data(), l.data(), nruns, mode);
+}

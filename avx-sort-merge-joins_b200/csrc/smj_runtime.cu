@@ -1,0 +1,204 @@
+// smj_runtime.cu -- device selection, stream, memory and timing entry points of smj_device.h.
+#include "smj_common.cuh"
+#include "../../include/smj_device.h"
+
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false};
+static std::mutex          g_mu;
+static thread_local char   g_err[512] = "";
+
+int smj_fail(cudaError_t e, const char *what, const char *file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d in `%s`", (int)e,
+             cudaGetErrorString(e), file, line, what);
+    if (getenv("SMJ_VERBOSE")) fprintf(stderr, "[smj_b200] %s\n", g_err);
+    return -(int)e - 1000;
+}
+int smj_fail_msg(const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    if (getenv("SMJ_VERBOSE")) fprintf(stderr, "[smj_b200] %s\n", g_err);
+    return -1;
+}
+
+static int ctx_init_locked(int device) {
+    if (g_ctx.ready && (device < 0 || device == g_ctx.device)) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return smj_fail_msg("no CUDA device available: the sort-merge join kernels need a GPU "
+                            "(there is no CPU fallback)");
+    }
+    if (device < 0) {
+        const char *env = getenv("SMJ_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        device = env ? atoi(env) : 0;
+        if (device < 0 || device >= ndev) device = device % ndev;
+    }
+    if (device >= ndev) return smj_fail_msg("smjdev_init: device index out of range");
+    SMJ_CHECK(cudaSetDevice(device));
+    if (g_ctx.ready && g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+    cudaDeviceProp prop;
+    SMJ_CHECK(cudaGetDeviceProperties(&prop, device));
+    g_ctx.device   = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
+    g_ctx.stream = g_ctx.own_stream;
+    // keep freed scratch in the pool: cudaMallocAsync then costs microseconds, not a driver call
+    cudaMemPool_t pool;
+    SMJ_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thresh = ~0ull;
+    SMJ_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    g_ctx.ready = true;
+    return 0;
+}
+
+SmjCtx *smj_ctx() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready && ctx_init_locked(-1) != 0) return nullptr;
+    // the caller may have switched devices (torch does); kernels must go to ours
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ctx.device) cudaSetDevice(g_ctx.device);
+    return &g_ctx;
+}
+
+extern "C" {
+
+int smjdev_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int smjdev_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return ctx_init_locked(device);
+}
+int smjdev_current_device(void) {
+    SmjCtx *c = smj_ctx();
+    return c ? c->device : -1;
+}
+int smjdev_set_stream(void *s) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+void *smjdev_get_stream(void) {
+    SmjCtx *c = smj_ctx();
+    return c ? (void *)c->stream : nullptr;
+}
+int smjdev_sync(void) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    SMJ_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+const char *smjdev_last_error(void) { return g_err; }
+uint64_t    smjdev_launch_count(void) { return g_ctx.launches; }
+int         smjdev_sm_count(void) {
+    SmjCtx *c = smj_ctx();
+    return c ? c->sm_count : 0;
+}
+
+void *smjdev_malloc(size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return nullptr;
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    if (e != cudaSuccess) {
+        smj_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+        return nullptr;
+    }
+    return p;
+}
+int smjdev_free(void *p) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (p) SMJ_CHECK(cudaFreeAsync(p, c->stream));
+    return 0;
+}
+void *smjdev_host_alloc(size_t bytes) {
+    if (!smj_ctx()) return nullptr;
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
+        smj_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+        return nullptr;
+    }
+    return p;
+}
+int smjdev_host_free(void *p) {
+    if (p) SMJ_CHECK(cudaFreeHost(p));
+    return 0;
+}
+int smjdev_memcpy_h2d(void *dst, const void *src, size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (bytes) SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+int smjdev_memcpy_d2h(void *dst, const void *src, size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (bytes) SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+int smjdev_memcpy_d2d(void *dst, const void *src, size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (bytes) SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int smjdev_memset(void *dst, int value, size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (bytes) SMJ_CHECK(cudaMemsetAsync(dst, value, bytes, c->stream));
+    return 0;
+}
+int smjdev_pointer_kind(const void *p) {
+    if (!smj_ctx()) return -1;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    switch (attr.type) {
+        case cudaMemoryTypeHost: return 1;
+        case cudaMemoryTypeDevice: return 2;
+        case cudaMemoryTypeManaged: return 3;
+        default: return 0;
+    }
+}
+
+int smjdev_event_create(void **ev) {
+    if (!smj_ctx()) return -1;
+    cudaEvent_t e;
+    SMJ_CHECK(cudaEventCreate(&e));
+    *ev = (void *)e;
+    return 0;
+}
+int smjdev_event_record(void *ev) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    SMJ_CHECK(cudaEventRecord((cudaEvent_t)ev, c->stream));
+    return 0;
+}
+int smjdev_event_elapsed_ms(void *start, void *stop, float *ms) {
+    SMJ_CHECK(cudaEventSynchronize((cudaEvent_t)stop));
+    SMJ_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return 0;
+}
+int smjdev_event_destroy(void *ev) {
+    if (ev) SMJ_CHECK(cudaEventDestroy((cudaEvent_t)ev));
+    return 0;
+}
+
+}  // extern "C"

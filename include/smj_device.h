@@ -1,0 +1,144 @@
+/**
+ * smj_device.h -- the thin C-ABI layer over the hand-written sm_100a kernels.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types appear in any signature (a CUDA
+ * stream is passed as void*).  The reference-facing entry points of smj_b200.h are written in
+ * C on top of this layer.  Every function returns 0 on success and a negative value on
+ * failure (message via smjdev_last_error()); there is NO CPU fallback anywhere below this
+ * line: if no CUDA device is usable every call fails.
+ *
+ * "item" = one 8-byte tuple viewed as uint64 = key<<32 | (uint32)payload
+ * (reference src/types.h:51-54).  All `uint64_t *` data arguments below are DEVICE pointers
+ * unless the comment says "host".
+ */
+#ifndef SMJ_DEVICE_H
+#define SMJ_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ runtime ---------- */
+int         smjdev_device_count(void);
+int         smjdev_init(int device);          /* idempotent; device<0 -> $SMJ_DEVICE, $LOCAL_RANK or 0 */
+int         smjdev_current_device(void);
+int         smjdev_set_stream(void *cuda_stream); /* run on the caller's stream (NULL -> own stream) */
+void       *smjdev_get_stream(void);
+int         smjdev_sync(void);
+const char *smjdev_last_error(void);
+uint64_t    smjdev_launch_count(void);        /* kernels launched by this library so far */
+int         smjdev_sm_count(void);
+
+/* ------------------------------------------------------------------ memory ----------- */
+void *smjdev_malloc(size_t bytes);            /* HBM, stream-ordered pool */
+int   smjdev_free(void *dptr);
+void *smjdev_host_alloc(size_t bytes);        /* pinned host memory */
+int   smjdev_host_free(void *hptr);
+int   smjdev_memcpy_h2d(void *dst, const void *src, size_t bytes); /* async on the stream */
+int   smjdev_memcpy_d2h(void *dst, const void *src, size_t bytes); /* async on the stream */
+int   smjdev_memcpy_d2d(void *dst, const void *src, size_t bytes); /* async on the stream */
+int   smjdev_memset(void *dst, int value, size_t bytes);
+/* 0 = ordinary (pageable) host memory, 1 = pinned host, 2 = device, 3 = managed */
+int   smjdev_pointer_kind(const void *p);
+
+/* ------------------------------------------------------------------ timing ----------- */
+int smjdev_event_create(void **ev);
+int smjdev_event_record(void *ev);            /* on the library's stream */
+int smjdev_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on stop */
+int smjdev_event_destroy(void *ev);
+
+/* ------------------------------------------------------------------ sort ------------- */
+/* Ascending sort of n items (replaces src/avxsort/avxsort.c:128-209 avxsort_aligned and
+ * the in-partition sort of src/joins/sortmergejoin_multiway.c:388-460).
+ * buf and tmp are two n-item device buffers, both clobbered; *sorted is set to whichever
+ * of the two holds the result.  key_only != 0 orders by the key (upper 32 bits) only and
+ * keeps the input order among equal keys (stable) -- enough for the merge-join and cheaper.
+ * algo: 0 = auto, 1 = LSD one-sweep radix passes, 2 = MSD partition + in-shared-memory
+ * segment sort (falls back to 1 when a segment does not fit). */
+int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_only, int algo,
+                uint64_t **sorted);
+
+/* In-place ascending sort of n int32 values (src/scalarsort/scalarsort.c:91-99); `data` may be a
+ * host or a device pointer.  Implemented by widening to items and one key-only sort. */
+int smjdev_sort_int32(int32_t *data, uint64_t n);
+
+/* ------------------------------------------------------------------ partition -------- */
+/* Stable radix partition (replaces src/partition/partition.c:94-287).
+ * bucket(x) = ((key(x) - key_minus_one) >> shift) & (2^nbits - 1)     (partition.c:29)
+ * padded != 0: every partition starts at a multiple of 8 tuples (partition.c:183-187),
+ *              `out` must hold n + 8*2^nbits items; otherwise partitions are dense.
+ * tmp: n-item scratch, needed only when nbits > 8 (two stable passes); may be NULL else.
+ * hist: device array of 2^nbits uint64 that receives the partition sizes.
+ * offs: device array of 2^nbits uint64 that receives each partition's start (in items). */
+int smjdev_partition(const uint64_t *in, uint64_t *out, uint64_t *tmp, uint64_t n,
+                     uint32_t nbits, uint32_t shift, int key_minus_one, int padded,
+                     uint64_t *hist, uint64_t *offs);
+/* histogram only (first half of partition.c:388-420 baseline_histogram_memcpy) */
+int smjdev_histogram(const uint64_t *in, uint64_t n, uint32_t nbits, uint32_t shift,
+                     int key_minus_one, uint64_t *hist);
+
+/* ------------------------------------------------------------------ merge ------------ */
+/* 2-way merge-path merge (replaces src/merge/merge.c:28-235 and the mergeN_varlen kernels
+ * of src/avxsort/avxsort_core.h:390-902).  mode 0: compare whole 64-bit word (AVX
+ * semantics); mode 1: compare key only, take from B on ties (scalar_merge_tuples,
+ * merge.c:78-87).  Inputs are NOT modified. */
+int smjdev_merge(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb,
+                 uint64_t *out, int mode);
+/* k-way merge of sorted runs (replaces src/merge/avx_multiwaymerge.c:199-338):
+ * ceil(log2 k) rounds of batched pairwise merge-path merges, all pairs of a round in one
+ * launch.  runs/lens are HOST arrays (k device pointers / k lengths); out and tmp are
+ * device buffers of sum(lens) items; the result always lands in out. */
+int smjdev_multiway_merge(uint64_t *out, uint64_t *tmp, const uint64_t *const *runs,
+                          const uint64_t *lens, uint32_t nruns, int mode);
+
+/* ------------------------------------------------------------------ merge join ------- */
+/* Merge-join scan of two key-sorted device arrays (replaces src/joins/joincommon.c:239-312).
+ * count    = sum over keys of |run_R| * |run_S|
+ * checksum = sum over matched pairs of A(r)*B(s) mod 2^64 (DESIGN.md "checksum")
+ * Results are written to HOST variables; the call synchronises. */
+int smjdev_merge_join(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                      uint64_t *count, uint64_t *checksum);
+/* semi != 0: count the S tuples that have a partner in R (what joincommon.c:325-394
+ * merge_join_interpolation counts); the checksum is then undefined */
+int smjdev_merge_join_ex(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns, int semi,
+                         uint64_t *count, uint64_t *checksum);
+/* asynchronous variant: accumulates into a device pair acc[0]=count, acc[1]=checksum */
+int smjdev_merge_join_acc(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                          uint64_t *acc);
+
+/* ------------------------------------------------------------------ join pipelines --- */
+enum { SMJ_ALGO_MWAY = 0, SMJ_ALGO_MPASS = 1, SMJ_ALGO_MPSM = 2 };
+
+typedef struct smj_join_stats_t {
+    uint64_t matches;
+    uint64_t checksum;
+    float    ms_h2d;       /* host->device copies (0 when inputs were device resident) */
+    float    ms_partition; /* range partition passes                                    */
+    float    ms_sort;      /* in-partition / run sort                                   */
+    float    ms_merge;     /* run merging (m-pass, m-way with nruns>1)                  */
+    float    ms_join;      /* merge-join scan                                           */
+    float    ms_total;     /* first kernel -> result on host                            */
+    uint64_t launches;     /* kernels launched by this call                             */
+    uint64_t hbm_bytes;    /* peak scratch bytes allocated by this call                 */
+} smj_join_stats_t;
+
+/* Device-resident join: r/s are device arrays and are left unmodified.
+ * nruns: number of sorted runs per relation for m-pass / mpsm (>=1; m-way ignores it). */
+int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                int nruns, smj_join_stats_t *stats);
+
+/* Multi-GPU building blocks (one process per GPU; the exchange itself is done by the
+ * caller with NCCL).
+ * Range-partition n items into nparts (<= 32) destinations by splitters[0..nparts-2] (ascending
+ * keys, HOST array of uint32): dest(x) = number of splitters <= key(x).  Items of one
+ * destination are contiguous in out; counts (device, nparts uint64) receives the sizes. */
+int smjdev_range_partition(const uint64_t *in, uint64_t *out, uint64_t n,
+                           const uint32_t *splitters, uint32_t nparts, uint64_t *counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMJ_DEVICE_H */
