@@ -17,7 +17,12 @@ struct SmjCtx {
     cudaStream_t own_stream;  // the library's own stream (used when the caller sets none)
     u64          launches;    // kernels launched so far
     bool         ready;
+    bool         profiling;   // smjdev_profile_begin(): CUDA events around every launch
+    u64          next_items;  // items the next launch processes (annotation for the profile)
 };
+void smj_prof_before(SmjCtx *ctx, const char *kernel_name);
+void smj_prof_after(SmjCtx *ctx);
+#define SMJ_ITEMS(ctx, n) ((ctx)->next_items = (u64)(n))
 SmjCtx *smj_ctx();                 // initialises lazily; nullptr on failure
 int     smj_fail(cudaError_t e, const char *what, const char *file, int line);
 int     smj_fail_msg(const char *msg);
@@ -31,7 +36,10 @@ int     smj_fail_msg(const char *msg);
 // every kernel launch goes through this so that gpu_launches is a real count
 #define SMJ_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
     do {                                                                       \
+        if ((ctx)->profiling) smj_prof_before((ctx), #kernel);                 \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+        if ((ctx)->profiling) smj_prof_after((ctx));                           \
+        (ctx)->next_items = 0;                                                 \
         (ctx)->launches++;                                                     \
         cudaError_t e__ = cudaGetLastError();                                  \
         if (e__ != cudaSuccess) return smj_fail(e__, #kernel, __FILE__, __LINE__); \

@@ -306,6 +306,7 @@ int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, 
     if (!d_diag || !d_recs) return smj_fail_msg("merge_join: scratch allocation failed");
     SMJ_LAUNCH(ctx, k_mj_partition, (unsigned)div_up(tiles + 1, 256), 256, 0, r, nr, s, ns, tiles,
                d_diag);
+    SMJ_ITEMS(ctx, nr + ns);
     SMJ_LAUNCH(ctx, k_mj_tile, (unsigned)tiles, MJ_THREADS, MJ_SMEM, r, nr, s, ns, d_diag, d_recs,
                acc, semi);
     SMJ_LAUNCH(ctx, k_mj_fixup, 1, FX_THREADS, 0, d_recs, tiles * 2, acc, semi);

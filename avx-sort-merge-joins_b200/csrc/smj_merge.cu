@@ -120,10 +120,11 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
 }
 
 int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
-    u64                   total_tiles = 0;
+    u64                   total_tiles = 0, total_items = 0;
     std::vector<MergeJob> jobs;
     for (MergeJob j : jobs_h) {
         if (j.na + j.nb == 0) continue;
+        total_items += j.na + j.nb;
         j.tile_begin = total_tiles;
         total_tiles += div_up(j.na + j.nb, MP_TILE);
         jobs.push_back(j);
@@ -139,10 +140,12 @@ int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
     const unsigned pgrid = (unsigned)div_up(total_tiles, 256);
     if (mode == 0) {
         SMJ_LAUNCH(ctx, k_mp_partition<0>, pgrid, 256, 0, d_jobs, nj, total_tiles, d_diag);
+        SMJ_ITEMS(ctx, total_items);
         SMJ_LAUNCH(ctx, k_mp_merge<0>, (unsigned)total_tiles, MP_THREADS, 0, d_jobs, nj,
                    total_tiles, d_diag);
     } else {
         SMJ_LAUNCH(ctx, k_mp_partition<1>, pgrid, 256, 0, d_jobs, nj, total_tiles, d_diag);
+        SMJ_ITEMS(ctx, total_items);
         SMJ_LAUNCH(ctx, k_mp_merge<1>, (unsigned)total_tiles, MP_THREADS, 0, d_jobs, nj,
                    total_tiles, d_diag);
     }

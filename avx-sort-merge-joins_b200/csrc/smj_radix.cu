@@ -374,6 +374,7 @@ int launch_onesweep(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64
         attr_set = true;
     }
     const u64 tiles = div_up(n, OSCfg::TILE);
+    SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, (k_onesweep<OS_THREADS, OS_IPT, F>), (unsigned)tiles, OS_THREADS, OSCfg::SMEM,
                in, out, n, fn, bases, status, counter, fn_full, padshift);
     return 0;
@@ -419,6 +420,7 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     if (!d_bits) return smj_fail_msg("smj_lsd_sort: scratch allocation failed");
     const u64 init[2] = {0ull, ~0ull};
     SMJ_CHECK(cudaMemcpyAsync(d_bits, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, n, 256, 16), 256, 0, buf, n, d_bits);
     u64 h_bits[2];
     SMJ_CHECK(cudaMemcpyAsync(h_bits, d_bits, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -453,6 +455,7 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     SMJ_CHECK(cudaMemsetAsync(d_hist, 0, (size_t)plan.nd * RADIX_NB * 8, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_status, 0, sbytes * plan.nd, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_count, 0, sizeof(u32) * 8, ctx->stream));
+    SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, buf, n, plan, d_hist);
     SMJ_LAUNCH(ctx, k_bases_multi, plan.nd, RADIX_NB, 0, d_hist, d_bases);
 

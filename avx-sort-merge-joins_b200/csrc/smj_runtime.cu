@@ -2,11 +2,35 @@
 #include "smj_common.cuh"
 #include "../../include/smj_device.h"
 
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
-static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false};
+static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false, false, 0};
+
+// ---- optional per-kernel timing (bench.py's roofline numbers): CUDA events on the launch stream
+struct ProfRec {
+    const char *name;
+    cudaEvent_t start, stop;
+    u64         items;
+};
+static std::vector<ProfRec> g_prof;
+
+void smj_prof_before(SmjCtx *ctx, const char *kernel_name) {
+    ProfRec r;
+    r.name  = kernel_name;
+    r.items = ctx->next_items;
+    cudaEventCreate(&r.start);
+    cudaEventCreate(&r.stop);
+    cudaEventRecord(r.start, ctx->stream);
+    g_prof.push_back(r);
+}
+void smj_prof_after(SmjCtx *ctx) {
+    if (!g_prof.empty()) cudaEventRecord(g_prof.back().stop, ctx->stream);
+}
 static std::mutex          g_mu;
 static thread_local char   g_err[512] = "";
 
@@ -176,6 +200,57 @@ int smjdev_pointer_kind(const void *p) {
         case cudaMemoryTypeManaged: return 3;
         default: return 0;
     }
+}
+
+int smjdev_profile_begin(void) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    for (auto &r : g_prof) {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+    c->profiling = true;
+    return 0;
+}
+// writes one line per kernel: name;launches;total_ms;total_items
+int smjdev_profile_end(char *out, size_t cap) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    c->profiling = false;
+    SMJ_CHECK(cudaStreamSynchronize(c->stream));
+    struct Agg {
+        u64    n, items;
+        double ms;
+    };
+    std::map<std::string, Agg> agg;
+    std::vector<std::string>   order;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (!agg.count(r.name)) {
+            order.push_back(r.name);
+            agg[r.name] = {0, 0, 0.0};
+        }
+        Agg &a = agg[r.name];
+        a.n++;
+        a.items += r.items;
+        a.ms += ms;
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+    std::string txt;
+    for (auto &k : order) {
+        char line[512];
+        snprintf(line, sizeof(line), "%s;%llu;%.6f;%llu\n", k.c_str(), agg[k].n, agg[k].ms,
+                 agg[k].items);
+        txt += line;
+    }
+    if (out && cap) {
+        snprintf(out, cap, "%s", txt.c_str());
+    }
+    return 0;
 }
 
 int smjdev_event_create(void **ev) {

@@ -50,6 +50,12 @@ int smjdev_event_record(void *ev);            /* on the library's stream */
 int smjdev_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on stop */
 int smjdev_event_destroy(void *ev);
 
+/* Per-kernel timing for roofline reports: between begin and end every kernel launch of the
+ * library is bracketed by CUDA events on the launch stream.  end() writes one text line per
+ * kernel, "name;launches;total_ms;total_items", into out (NUL terminated, truncated to cap). */
+int smjdev_profile_begin(void);
+int smjdev_profile_end(char *out, size_t cap);
+
 /* ------------------------------------------------------------------ sort ------------- */
 /* Ascending sort of n items (replaces src/avxsort/avxsort.c:128-209 avxsort_aligned and
  * the in-partition sort of src/joins/sortmergejoin_multiway.c:388-460).
@@ -137,6 +143,15 @@ int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uin
  * destination are contiguous in out; counts (device, nparts uint64) receives the sizes. */
 int smjdev_range_partition(const uint64_t *in, uint64_t *out, uint64_t n,
                            const uint32_t *splitters, uint32_t nparts, uint64_t *counts);
+
+/* ------------------------------------------------------------------ data generators -- */
+/* Deterministic on-device relation generators (replace src/datagen/generator.c:83-93, 234-350
+ * and :458-488 for the benchmark workloads; the reference's own are seeded from time()).
+ * Rows [first, first+count) of the relation are written to out[0..count); payload = row index.
+ * unique: keys are a pseudo-random permutation of 1..n (Feistel network + cycle walking).
+ * fk:     keys are uniformly drawn from 1..maxkey. */
+int smjdev_gen_unique(uint64_t *out, uint64_t n, uint64_t first, uint64_t count, uint64_t seed);
+int smjdev_gen_fk(uint64_t *out, uint64_t first, uint64_t count, uint32_t maxkey, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,65 @@
+/*
+ * smj_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C) of the reference's sort-merge join path, used solely as the checker
+ * in tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  No
+ * product code links, imports or calls anything in this directory.
+ *
+ * Parity pinning: the reference ships no golden vectors.  This restatement is
+ * pinned against the reference itself, compiled unmodified from /root/reference by
+ * oracle/Makefile (`make ref` -> oracle/_ref/libsmj_ref.so), in tests/test_oracle_vs_ref.py, and
+ * against fixtures generated from that library (tests/golden/, tests/golden/make_golden.py).
+ *
+ * "item" = uint64 view of tuple_t {int32 payload; int32 key;} = key<<32 | (uint32)payload
+ * (reference src/types.h:51-54).
+ */
+#ifndef SMJ_ORACLE_H
+#define SMJ_ORACLE_H
+#include <stdint.h>
+
+/* sort: ascending on the 64-bit word (reference src/avxsort/avxsort.c:128-209 orders items as
+ * IEEE doubles, identical for key >= 0 without the NaN exponent pattern) */
+void orc_sort(uint64_t *items, uint64_t n);
+/* stable sort on the key (upper 32 bits) only */
+void orc_sort_key_stable(uint64_t *items, uint64_t n);
+/* which buffer the reference returns the result in: 0 = *inputptr's, 1 = *outputptr's */
+int orc_avxsort_placement(uint64_t n, int multiway);
+
+/* partition: reference src/partition/partition.c:94-287.  padded: partition starts rounded up to
+ * 8 tuples (:183-187).  hist/offs: 2^nbits entries.  Returns the number of output slots used. */
+uint64_t orc_partition(const uint64_t *in, uint64_t n, uint32_t nbits, uint32_t shift, int padded,
+                       uint64_t *out, uint64_t *hist, uint64_t *offs);
+
+/* merge: mode 0 whole-word compare (avx_merge_*, scalar_merge_int64), mode 1 key-only compare
+ * with B first on ties (scalar_merge_tuples, reference src/merge/merge.c:66-103) */
+uint64_t orc_merge(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint64_t *out,
+                   int mode);
+/* k-way merge by pairwise merging (reference src/merge/avx_multiwaymerge.c:199-338: binary tree) */
+uint64_t orc_multiway_merge(const uint64_t *const *runs, const uint64_t *lens, uint32_t nruns,
+                            uint64_t *out);
+
+/* merge join: reference src/joins/joincommon.c:239-312 restated literally (one match at a time);
+ * the checksum is sum A(r)*B(s) mod 2^64 over the matches. */
+void orc_merge_join(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                    uint64_t *count, uint64_t *checksum);
+/* same result computed run by run (count += |R run|*|S run|) so that skewed inputs finish */
+void orc_merge_join_runs(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                         uint64_t *count, uint64_t *checksum);
+/* reference src/joins/joincommon.c:325-394 without the interpolated start */
+uint64_t orc_merge_join_interpolation(const uint64_t *r, uint64_t nr, const uint64_t *s,
+                                      uint64_t ns);
+
+/* whole joins.  orc_join_bruteforce: sort both sides, merge join.
+ * orc_join_mway: the reference's 4-phase structure (sortmergejoin_multiway.c:129-599) executed by
+ * `nthreads` logical threads one after the other, fan-out `fanout`, with its bit-shift rule. */
+void orc_join_bruteforce(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                         uint64_t *count, uint64_t *checksum);
+int orc_join_mway(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns, int nthreads,
+                  int fanout, uint64_t *count, uint64_t *checksum);
+
+/* deterministic generators (the reference's are seeded from time(), generator.c:136-139) */
+void orc_gen_unique(uint64_t *out, uint64_t n, uint64_t seed);                  /* keys = perm of 1..n */
+void orc_gen_fk(uint64_t *out, uint64_t n, uint32_t maxkey, uint64_t seed);     /* keys in 1..maxkey  */
+uint64_t orc_cks_a(uint64_t r);
+uint64_t orc_cks_b(uint64_t s);
+#endif

@@ -1,0 +1,302 @@
+"""Parity of the CUDA path (through the C-ABI of libsmj_b200.so) with the CPU oracle on the same
+seeded inputs.  Bit-exact everywhere: this is integer work.  Needs a GPU (pytest -m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+SORT_SIZES = [1, 2, 15, 16, 100, 255, 256, 6143, 6144, 6145, 16383, 16384, 16385, 100003, 1000003]
+
+
+def _inputs(rng, n, kind):
+    if kind == "unique":
+        return ol.make_unique(rng, n)
+    if kind == "dups":
+        return ol.rand_items(rng, n, 7)
+    if kind == "equal":
+        return np.full(n, (5 << 32) | 9, dtype=np.uint64)
+    if kind == "presorted":
+        return np.sort(ol.rand_items(rng, n, 1 << 20))
+    if kind == "reverse":
+        return np.sort(ol.rand_items(rng, n, 1 << 20))[::-1].copy()
+    if kind == "wide":  # all 32 payload bits and 31 key bits in use
+        return ol.rand_items(rng, n, (1 << 31) - 1)
+    raise ValueError(kind)
+
+
+# ------------------------------------------------------------------------------------ sort
+@pytest.mark.parametrize("n", SORT_SIZES)
+@pytest.mark.parametrize("algo", [1, 0])
+def test_device_sort(smj, orc, n, algo):
+    rng = np.random.default_rng(n)
+    for kind in ("unique", "dups", "equal", "presorted", "reverse", "wide"):
+        items = _inputs(rng, n, kind)
+        buf, tmp = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+        res = C.c_void_p()
+        smj.check(smj.lib.smjdev_sort(buf.ptr, tmp.ptr, n, 0, algo, C.byref(res)), "sort")
+        smj.check(smj.lib.smjdev_sync())
+        assert res.value in (buf.ptr, tmp.ptr)
+        got = (buf if res.value == buf.ptr else tmp).to_host()
+        assert np.array_equal(got, orc.sort(items)), (kind, n)
+        # key-only variant: stable on the key
+        buf2, tmp2 = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+        smj.check(smj.lib.smjdev_sort(buf2.ptr, tmp2.ptr, n, 1, algo, C.byref(res)), "sort")
+        smj.check(smj.lib.smjdev_sync())
+        got = (buf2 if res.value == buf2.ptr else tmp2).to_host()
+        assert np.array_equal(got, orc.sort_key_stable(items)), (kind, n)
+        for b in (buf, tmp, buf2, tmp2):
+            b.free()
+
+
+@pytest.mark.parametrize("n", [0, 1, 100, 255, 16384, 32684, 81920, 1000003])
+def test_avxsort_tuples_host_api(smj, orc, n):
+    """avxsort_tuples with host buffers: sorted contents, pointer-swap contract and the buffer the
+    reference would have chosen (reference src/avxsort/avxsort.c:117-118, 212-226)."""
+    rng = np.random.default_rng(n + 1)
+    items = ol.rand_items(rng, n, 1 << 27)
+    for name, mw in (("avxsort_tuples", 0), ("avxsort_int64", 0), ("avxsortmultiway_tuples", 1)):
+        a, b = items.copy(), np.zeros(max(n, 1), dtype=np.uint64)
+        pa, pb = C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)
+        getattr(smj.lib, name)(C.byref(pa), C.byref(pb), n)
+        if n == 0:
+            assert (pa.value, pb.value) == (a.ctypes.data, b.ctypes.data)
+            continue
+        placement = orc.placement(n, mw)
+        assert pb.value == (b.ctypes.data if placement else a.ctypes.data), name
+        assert pa.value == (a.ctypes.data if placement else b.ctypes.data), name
+        res = b if placement else a
+        assert np.array_equal(res[:n], orc.sort(items)), name
+
+
+def test_scalarsort_host_api(smj, orc):
+    rng = np.random.default_rng(5)
+    n = 50001
+    items = ol.rand_items(rng, n, 1000)
+    a, b = items.copy(), np.zeros(n, dtype=np.uint64)
+    pa, pb = C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)
+    smj.lib.scalarsort_tuples(C.byref(pa), C.byref(pb), n)
+    assert pb.value == a.ctypes.data and pa.value == b.ctypes.data  # sorted in place, swapped
+    assert np.array_equal(a >> np.uint64(32), np.sort(items >> np.uint64(32)))
+    assert np.array_equal(np.sort(a), np.sort(items))
+    v = rng.integers(-2**31, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+    w, z = v.copy(), np.zeros(n, dtype=np.int32)
+    pa, pb = C.c_void_p(w.ctypes.data), C.c_void_p(z.ctypes.data)
+    smj.lib.scalarsort_int32(C.byref(pa), C.byref(pb), n)
+    assert pb.value == w.ctypes.data
+    assert np.array_equal(w, np.sort(v))
+
+
+# ------------------------------------------------------------------------------------ partition
+@pytest.mark.parametrize("nbits,shift", [(2, 0), (4, 0), (7, 3), (8, 0), (9, 1), (11, 0), (14, 2),
+                                         (15, 0)])
+def test_partition_relation_host_api(smj, orc, nbits, shift):
+    """partition_relation / _optimized / _V2 vs the oracle: counts, starts (8-tuple aligned for the
+    optimized variants) and exact per-partition contents, i.e. the scatter is stable
+    (reference tests/check_partitioning.c:73-90)."""
+    rng = np.random.default_rng(nbits * 100 + shift)
+    n = 200003
+    items = ol.rand_items(rng, n, 1 << 22)
+    fan = 1 << nbits
+    for name, padded in (("partition_relation", False), ("partition_relation_optimized", True),
+                         ("partition_relation_optimized_V2", True)):
+        out = np.zeros(n + 8 * fan + 8, dtype=np.uint64)
+        parts = (smj.relation_t * fan)()
+        pp = (C.POINTER(smj.relation_t) * fan)(*[C.pointer(parts[i]) for i in range(fan)])
+        rin, rout = smj.rel(items), smj.relation_t(out.ctypes.data, n)
+        getattr(smj.lib, name)(pp, C.byref(rin), C.byref(rout), nbits, shift)
+        eout, ehist, eoffs, _ = orc.partition(items, nbits, shift, padded)
+        hist = np.array([parts[i].num_tuples for i in range(fan)], dtype=np.uint64)
+        offs = np.array([(parts[i].tuples - out.ctypes.data) // 8 for i in range(fan)], dtype=np.uint64)
+        assert np.array_equal(hist, ehist), name
+        assert np.array_equal(offs, eoffs), name
+        if padded:
+            assert not np.any(offs % np.uint64(8)), name
+        for p in range(fan):
+            lo, c = int(offs[p]), int(hist[p])
+            assert np.array_equal(out[lo:lo + c], eout[lo:lo + c]), (name, p)
+
+
+def test_radix_cluster_and_histogram(smj, orc):
+    rng = np.random.default_rng(11)
+    n = 70001
+    items = ol.rand_items(rng, n, 1 << 20)
+    out = np.zeros(n, dtype=np.uint64)
+    hist = np.zeros(64, dtype=np.int32)
+    rin, rout = smj.rel(items), smj.relation_t(out.ctypes.data, n)
+    smj.lib.radix_cluster(C.byref(rout), C.byref(rin), hist.ctypes.data_as(C.POINTER(C.c_int32)), 2, 6)
+    eout, ehist, _, _ = orc.partition(items, 6, 2, False)
+    assert np.array_equal(hist.astype(np.uint64), ehist)
+    assert np.array_equal(out, eout[:n])
+    out2 = np.zeros(n, dtype=np.uint64)
+    rout2 = smj.relation_t(out2.ctypes.data, n)
+    smj.lib.histogram_memcpy_bench(None, C.byref(rin), C.byref(rout2), 10)
+    assert np.array_equal(out2, items)
+
+
+def test_partition_empty_and_tiny(smj, orc):
+    for n in (0, 1, 7):
+        items = ol.rand_items(np.random.default_rng(n), n, 100)
+        fan = 16
+        out = np.zeros(n + 8 * fan + 8, dtype=np.uint64)
+        parts = (smj.relation_t * fan)()
+        pp = (C.POINTER(smj.relation_t) * fan)(*[C.pointer(parts[i]) for i in range(fan)])
+        rin, rout = smj.relation_t(items.ctypes.data if n else None, n), smj.relation_t(out.ctypes.data, n)
+        smj.lib.partition_relation_optimized(pp, C.byref(rin), C.byref(rout), 4, 0)
+        _, ehist, eoffs, _ = orc.partition(items, 4, 0, True)
+        assert [parts[i].num_tuples for i in range(fan)] == list(ehist)
+
+
+# ------------------------------------------------------------------------------------ merge
+@pytest.mark.parametrize("na,nb", [(0, 5), (5, 0), (1, 1), (100, 37), (4096, 4096), (4095, 4097),
+                                   (100000, 333), (250000, 250001)])
+def test_merge_host_api(smj, orc, na, nb):
+    rng = np.random.default_rng(na * 31 + nb)
+    a = np.sort(ol.rand_items(rng, na, 50))
+    b = np.sort(ol.rand_items(rng, nb, 50))
+    out = np.zeros(na + nb, dtype=np.uint64)
+    for name in ("avx_merge_tuples", "avx_merge_int64", "scalar_merge_int64"):
+        out[:] = 0
+        k = getattr(smj.lib, name)(a.ctypes.data, b.ctypes.data, out.ctypes.data, na, nb)
+        assert k == na + nb
+        assert np.array_equal(out, orc.merge(a, b, 0)), name
+    ak, bk = orc.sort_key_stable(a), orc.sort_key_stable(b)
+    k = smj.lib.scalar_merge_tuples(ak.ctypes.data, bk.ctypes.data, out.ctypes.data, na, nb)
+    assert k == na + nb
+    assert np.array_equal(out, orc.merge(ak, bk, 1))
+
+
+@pytest.mark.parametrize("nruns", [1, 2, 3, 4, 8, 64, 100])
+def test_multiway_merge_host_api(smj, orc, nruns):
+    rng = np.random.default_rng(nruns)
+    runs = [np.sort(ol.rand_items(rng, int(rng.integers(0, 9000)), 1 << 16)) for _ in range(nruns)]
+    total = sum(r.size for r in runs)
+    out = np.zeros(total + 1, dtype=np.uint64)
+    rels = (smj.relation_t * nruns)(*[smj.relation_t(r.ctypes.data if r.size else None, r.size) for r in runs])
+    pp = (C.POINTER(smj.relation_t) * nruns)(*[C.pointer(rels[i]) for i in range(nruns)])
+    k = smj.lib.avx_multiway_merge(out.ctypes.data, pp, nruns, None, 0)
+    assert k == total
+    assert np.array_equal(out[:total], orc.multiway_merge(runs))
+    assert all(rels[i].num_tuples == 0 for i in range(nruns))  # inputs are consumed
+    # scalar twin: key-only order; the reference only guarantees key-sortedness + the multiset
+    rels = (smj.relation_t * nruns)(*[smj.relation_t(r.ctypes.data if r.size else None, r.size) for r in runs])
+    pp = (C.POINTER(smj.relation_t) * nruns)(*[C.pointer(rels[i]) for i in range(nruns)])
+    out[:] = 0
+    k = smj.lib.scalar_multiway_merge(out.ctypes.data, pp, nruns, None, 0)
+    assert k == total
+    assert np.all(np.diff((out[:total] >> np.uint64(32)).astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(out[:total]), orc.multiway_merge(runs))
+
+
+# ------------------------------------------------------------------------------------ merge join
+@pytest.mark.parametrize("nr,ns,kmax", [(1000, 1000, 1000), (5000, 20000, 300), (100, 100, 1),
+                                        (1, 1, 5), (3000, 10, 50), (200000, 300000, 150000),
+                                        (50000, 50000, 3), (4096, 4096, 1 << 30), (100000, 1, 7)])
+def test_merge_join(smj, orc, nr, ns, kmax):
+    rng = np.random.default_rng(nr + ns + kmax)
+    r = orc.sort(ol.rand_items(rng, nr, kmax))
+    s = orc.sort(ol.rand_items(rng, ns, kmax))
+    exp = orc.merge_join_runs(r, s)
+    if nr * ns <= 4_000_000:
+        assert orc.merge_join(r, s) == exp  # literal restatement agrees with the run formula
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    cnt, cks = C.c_uint64(), C.c_uint64()
+    smj.check(smj.lib.smjdev_merge_join(dr.ptr, nr, ds.ptr, ns, C.byref(cnt), C.byref(cks)))
+    assert (cnt.value, cks.value) == exp
+    assert smj.lib.merge_join(r.ctypes.data, s.ctypes.data, nr, ns, None) == exp[0]
+    dr.free()
+    ds.free()
+
+
+def test_merge_join_interpolation(smj, orc):
+    rng = np.random.default_rng(9)
+    r = orc.sort(ol.make_unique(rng, 40000))
+    s = orc.sort(ol.rand_items(rng, 90000, 40000))
+    assert smj.lib.merge_join_interpolation(r.ctypes.data, s.ctypes.data, r.size, s.size, None) == \
+        orc.merge_join_interpolation(r, s)
+    # duplicates in R: the reference then counts every matching S tuple once
+    r2 = orc.sort(ol.rand_items(rng, 40000, 1000))
+    s2 = orc.sort(ol.rand_items(rng, 50000, 2000))
+    assert smj.lib.merge_join_interpolation(r2.ctypes.data, s2.ctypes.data, r2.size, s2.size, None) == \
+        orc.merge_join_interpolation(r2, s2)
+
+
+# ------------------------------------------------------------------------------------ joins
+def _join_cases(orc):
+    rng = np.random.default_rng(2024)
+    n = 1 << 18
+    yield "unique", orc.gen_unique(n, 12345), orc.gen_unique(n, 54321)
+    yield "fk", orc.gen_unique(n // 4, 12345), orc.gen_fk(n, n // 4, 99)
+    yield "dups_both", ol.rand_items(rng, n, n // 8), ol.rand_items(rng, n, n // 8)
+    yield "all_equal", np.full(3000, (7 << 32) | 1, dtype=np.uint64), np.full(5000, (7 << 32) | 2, dtype=np.uint64)
+    yield "disjoint", ol.rand_items(rng, 10000, 1000), ol.rand_items(rng, 10000, 1000) + np.uint64(5000 << 32)
+    yield "ragged", orc.gen_unique(100003, 1), orc.gen_fk(7, 100003, 2)
+    zk = ol.zipf_keys(rng, n, n // 4, 1.0)
+    yield "zipf", orc.gen_unique(n // 4, 5), (zk << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    yield "empty_r", np.zeros(0, dtype=np.uint64), orc.gen_unique(1000, 3)
+    yield "empty_s", orc.gen_unique(1000, 3), np.zeros(0, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("algo", ["multiway", "multipass", "mpsm"])
+def test_join_host_api(smj, orc, algo):
+    """sortmergejoin_* called like src/main.c:603 with host relations: cardinality and checksum
+    equal to the oracle's (brute force == the reference's m-way pipeline restated)."""
+    for name, r, s in _join_cases(orc):
+        exp = orc.join_bruteforce(r, s)
+        r0, s0 = r.copy(), s.copy()
+        total, st = smj.join_host(algo, r, s, nthreads=4, fanout=128)
+        assert total == exp[0], (algo, name)
+        assert (st.matches, st.checksum) == exp, (algo, name)
+        assert np.array_equal(r, r0) and np.array_equal(s, s0), "inputs must stay unmodified"
+        if algo == "multiway" and name in ("unique", "fk", "dups_both"):
+            assert orc.join_mway(r, s, 4, 128) == exp
+
+
+def test_join_error_behaviour(smj, orc, capfd):
+    r, s = orc.gen_unique(1000, 1), orc.gen_unique(1000, 2)
+    total, _ = smj.join_host("multiway", r, s, nthreads=3)  # not a power of two
+    assert total is None
+    assert "power of 2" in capfd.readouterr().out
+
+
+def test_join_device_resident(smj, orc):
+    n = 1 << 20
+    r, s = orc.gen_unique(n, 12345), orc.gen_fk(2 * n, n, 7)
+    exp = orc.join_bruteforce(r, s)
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    for algo, nruns in ((smj.ALGO_MWAY, 1), (smj.ALGO_MPASS, 8), (smj.ALGO_MPASS, 5), (smj.ALGO_MPSM, 8)):
+        st = smj.device_join(algo, dr, ds, nruns)
+        assert (st.matches, st.checksum) == exp, algo
+        assert st.launches > 0
+    assert np.array_equal(dr.to_host(), r) and np.array_equal(ds.to_host(), s)
+
+
+# ------------------------------------------------------------------------------------ generators
+def test_generators_match_oracle(smj, orc):
+    for n in (1, 2, 1000, 100003, 1 << 20):
+        d = smj.DeviceBuffer(n)
+        smj.check(smj.lib.smjdev_gen_unique(d.ptr, n, 0, n, 12345))
+        got = d.to_host()
+        assert np.array_equal(got, orc.gen_unique(n, 12345))
+        assert np.array_equal(np.sort(got >> np.uint64(32)), np.arange(1, n + 1, dtype=np.uint64))
+        smj.check(smj.lib.smjdev_gen_fk(d.ptr, 0, n, max(n // 3, 1), 77))
+        assert np.array_equal(d.to_host(), orc.gen_fk(n, max(n // 3, 1), 77))
+        d.free()
+
+
+def test_range_partition(smj, orc):
+    rng = np.random.default_rng(4)
+    n = 300007
+    items = ol.rand_items(rng, n, 1 << 20)
+    for nparts in (1, 2, 8):
+        sp = np.array([(i + 1) * (1 << 20) // nparts for i in range(nparts - 1)], dtype=np.uint32)
+        d_in, d_out, d_cnt = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n), smj.DeviceBuffer(nparts)
+        smj.check(smj.lib.smjdev_range_partition(d_in.ptr, d_out.ptr, n,
+                                                 sp.ctypes.data_as(C.POINTER(C.c_uint32)), nparts, d_cnt.ptr))
+        cnt, out = d_cnt.to_host(), d_out.to_host()
+        dest = np.searchsorted(sp, (items >> np.uint64(32)).astype(np.uint32), side="right")
+        assert np.array_equal(cnt, np.bincount(dest, minlength=nparts).astype(np.uint64))
+        assert np.array_equal(out, items[np.argsort(dest, kind="stable")])  # stable

@@ -1,0 +1,126 @@
+"""Pins the C oracle (oracle/smj_oracle.c) against the UNMODIFIED reference compiled from
+/root/reference (oracle/_ref/libsmj_ref.so).  CPU only.  The reference has no golden vectors and
+its own tests use time() seeds, so this side-by-side run IS the pin; a frozen
+subset of it is committed under tests/golden/ (see test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+SIZES = [1, 2, 15, 16, 17, 100, 255, 256, 257, 1000, 4096, 16383, 16384, 16385, 32684, 81920,
+         100003]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_sort_matches_reference(orc, ref, n):
+    rng = np.random.default_rng(n)
+    for kind in ("unique", "dups", "equal", "presorted", "reverse"):
+        if kind == "unique":
+            items = ol.rand_items(rng, n, 1 << 27)
+        elif kind == "dups":
+            items = ol.rand_items(rng, n, 7)
+        elif kind == "equal":
+            items = np.full(n, (5 << 32) | 9, dtype=np.uint64)
+        elif kind == "presorted":
+            items = np.sort(ol.rand_items(rng, n, 1 << 20))
+        else:
+            items = np.sort(ol.rand_items(rng, n, 1 << 20))[::-1].copy()
+        got, placement = ref.sort(items)
+        assert np.array_equal(orc.sort(items), got), kind
+        assert np.array_equal(np.sort(items), got), kind  # == ascending uint64 order
+        assert orc.placement(n) == placement, kind
+
+
+@pytest.mark.parametrize("n", [5000, 2621440 + 17, 3 * 2621440 + 5, 4 * 2621440 + 100])
+def test_sortmultiway_matches_reference(orc, ref, n):
+    rng = np.random.default_rng(n)
+    items = ol.rand_items(rng, n, 1 << 27)
+    got, placement = ref.sort(items, "avxsortmultiway_tuples")
+    assert np.array_equal(np.sort(items), got)
+    assert orc.placement(n, 1) == placement
+
+
+def test_placement_sweep(orc, ref):
+    rng = np.random.default_rng(7)
+    sizes = list(range(1, 70)) + [int(x) for x in rng.integers(70, 600000, size=60)]
+    for n in sizes:
+        items = ol.rand_items(rng, n, 1 << 26)
+        _, placement = ref.sort(items)
+        assert orc.placement(n) == placement, n
+
+
+@pytest.mark.parametrize("na,nb", [(0, 5), (5, 0), (1, 1), (100, 37), (4096, 4096), (10000, 333)])
+def test_merge_matches_reference(orc, ref, na, nb):
+    rng = np.random.default_rng(na * 31 + nb)
+    a = np.sort(ol.rand_items(rng, na, 50))
+    b = np.sort(ol.rand_items(rng, nb, 50))
+    assert np.array_equal(orc.merge(a, b, 0), ref.merge(a, b, "avx_merge_tuples"))
+    # scalar variant: key-only compare, B first on ties -- compare on key-sorted inputs
+    ak, bk = orc.sort_key_stable(a), orc.sort_key_stable(b)
+    assert np.array_equal(orc.merge(ak, bk, 1), ref.merge(ak, bk, "scalar_merge_tuples"))
+
+
+@pytest.mark.parametrize("nruns", [4, 8, 64])
+def test_multiway_merge_matches_reference(orc, ref, nruns):
+    rng = np.random.default_rng(nruns)
+    runs = [np.sort(ol.rand_items(rng, int(rng.integers(0, 5000)), 1 << 16)) for _ in range(nruns)]
+    got, k = ref.multiway_merge(runs)
+    exp = orc.multiway_merge(runs)
+    assert k == exp.size
+    assert np.array_equal(exp, got)
+
+
+@pytest.mark.parametrize("nbits,shift", [(2, 0), (4, 0), (7, 3), (8, 0), (11, 0), (14, 2)])
+def test_partition_matches_reference(orc, ref, nbits, shift):
+    rng = np.random.default_rng(nbits * 100 + shift)
+    n = 50000
+    items = ol.rand_items(rng, n, 1 << 22)
+    for which, padded in (("partition_relation", False), ("partition_relation_optimized", True),
+                          ("partition_relation_optimized_V2", True)):
+        rout, rhist, roffs = ref.partition(items, nbits, shift, which)
+        out, hist, offs, used = orc.partition(items, nbits, shift, padded)
+        assert np.array_equal(hist, rhist), which
+        assert np.array_equal(offs, roffs), which
+        for p in range(1 << nbits):
+            lo, c = int(offs[p]), int(hist[p])
+            assert np.array_equal(out[lo:lo + c], rout[lo:lo + c]), (which, p)
+
+
+def test_merge_join_matches_reference(orc, ref):
+    rng = np.random.default_rng(3)
+    for (nr, ns, kmax) in [(1000, 1000, 1000), (5000, 20000, 300), (100, 100, 1), (1, 1, 5),
+                           (3000, 10, 50)]:
+        r = orc.sort(ol.rand_items(rng, nr, kmax))
+        s = orc.sort(ol.rand_items(rng, ns, kmax))
+        cnt = ref.merge_join(r, s)
+        assert orc.merge_join(r, s)[0] == cnt
+        assert orc.merge_join_runs(r, s) == orc.merge_join(r, s)
+    # interpolation variant assumes unique R keys that bracket S
+    r = orc.sort(ol.make_unique(rng, 4000))
+    s = orc.sort(ol.rand_items(rng, 9000, 4000))
+    assert orc.merge_join_interpolation(r, s) == ref.merge_join(r, s, "merge_join_interpolation")
+
+
+@pytest.mark.parametrize("nthreads,fanout", [(1, 16), (2, 128), (4, 128), (8, 32)])
+def test_join_matches_reference(orc, ref, nthreads, fanout):
+    rng = np.random.default_rng(nthreads)
+    n = 1 << 17
+    r = orc.gen_unique(n, 12345)
+    s = orc.gen_unique(n, 54321)
+    assert ref.join(r, s, "sortmergejoin_multiway", nthreads, fanout) == n
+    assert orc.join_mway(r, s, nthreads, fanout)[0] == n
+    assert orc.join_bruteforce(r, s) == orc.join_mway(r, s, nthreads, fanout)
+    # foreign keys with duplicates on the S side, both algorithms of the reference
+    s2 = orc.gen_fk(3 * n, n, 99)
+    exp = orc.join_bruteforce(r, s2)
+    assert exp[0] == 3 * n
+    assert ref.join(r, s2, "sortmergejoin_multiway", nthreads, fanout) == exp[0]
+    if nthreads > 1:  # the reference's m-pass frees interior pointers when run with one thread
+        assert ref.join(r, s2, "sortmergejoin_multipass", nthreads, fanout) == exp[0]
+    assert orc.join_mway(r, s2, nthreads, fanout) == exp
+    # duplicates on both sides
+    r3 = ol.rand_items(rng, n, n // 4)
+    s3 = ol.rand_items(rng, n, n // 4)
+    exp = orc.join_bruteforce(r3, s3)
+    assert ref.join(r3, s3, "sortmergejoin_multiway", nthreads, fanout) == exp[0]
+    assert orc.join_mway(r3, s3, nthreads, fanout) == exp
