@@ -85,6 +85,16 @@ struct DigitFn {
     __host__ __device__ __forceinline__ u32 last_bin() const { return mask; }
 };
 
+// plain bit-field digit (LSD sort passes): no key-1 adjustment, saves the 64-bit subtract
+struct FieldFn {
+    u32 shift;
+    u32 mask;
+    __host__ __device__ __forceinline__ u32 operator()(u64 x) const {
+        return (u32)(x >> shift) & mask;
+    }
+    __host__ __device__ __forceinline__ u32 last_bin() const { return mask; }
+};
+
 // destination of an item under range partitioning: number of splitters <= key (at most 32 parts)
 struct SplitFn {
     u32 nparts;

@@ -7,16 +7,16 @@
 //     (stubbed, sortmergejoin_mpsm.c:38-45) MPSM driver.
 //
 // Scan design: the merged order of R and S (by key, R first on ties) is cut into tiles of 4096
-// items (k_mj_partition, merge path).  A CTA loads its two pieces into shared memory, builds one
-// prefix-sum array of the checksum terms, and every thread that owns the FIRST S item of a key
-// run finds the matching R run with a shared-memory binary search:
+// items (k_mj_partition, merge path).  A CTA loads its two pieces into shared memory; every thread
+// walks its own 8-item slice of the tile's merge path, and the thread that meets the FIRST S item
+// of a key run combines it with the R run that ends at its R cursor:
 //     count    += |run_R| * |run_S|                       (what the reference counts one by one)
 //     checksum += (sum A(r)) * (sum B(s))                 (bilinear, so no pair enumeration)
 // Key runs that may continue in a neighbouring tile (the tile's first and last key) are not
 // multiplied in the tile; their partial sums go to a record array that k_mj_fixup stitches.
 // Work per key run is O(log tile), so Zipf-skewed inputs cost the same as uniform ones.
 //
-// HBM traffic: 8 B per input tuple (read only) + 80 B of records per 4096 tuples.
+// HBM traffic: 8 B per input tuple (read only); boundary records only where a run really crosses.
 #include "smj_common.cuh"
 #include "../../include/smj_device.h"
 
@@ -30,10 +30,9 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
 
 namespace {
 
-constexpr int MJ_THREADS = 512;
-constexpr int MJ_IPT     = 8;
+constexpr int MJ_THREADS = 256;
+constexpr int MJ_IPT     = 16;
 constexpr int MJ_TILE    = MJ_THREADS * MJ_IPT;                 // 4096 merged items per CTA
-constexpr size_t MJ_SMEM = (size_t)MJ_TILE * 8 + (size_t)(MJ_TILE + 2) * 8;
 
 struct MjRec {
     u64 key;
@@ -85,16 +84,17 @@ __global__ void __launch_bounds__(256) k_mj_partition(const u64 *__restrict__ r,
     diag_r[t] = lo;
 }
 
+// One tile of the merged order.  Every thread finds its 8-item slice of the merge path and walks
+// it with two cursors; when it meets the FIRST S item of a key run it multiplies the sizes (and
+// checksum sums) of the R run ending at its R cursor and of the S run starting there.
 __global__ void __launch_bounds__(MJ_THREADS) k_mj_tile(const u64 *__restrict__ r, u64 nr,
                                                         const u64 *__restrict__ s, u64 ns,
                                                         const u64 *__restrict__ diag_r,
                                                         MjRec *__restrict__ recs,
+                                                        unsigned char *__restrict__ rec_valid,
                                                         u64 *__restrict__ acc, int semi) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_it = (u64 *)smem_raw;   // [MJ_TILE]  R piece followed by S piece
-    u64 *s_pf = s_it + MJ_TILE;    // [MJ_TILE+1] exclusive prefix sums of A(r) ... B(s)
-    __shared__ u64 s_wsum[MJ_THREADS / 32];
-    __shared__ u64 s_red[2][MJ_THREADS / 32];
+    __shared__ u64 s_it[MJ_TILE];  // R piece followed by S piece
+    __shared__ u64 s_red[10][MJ_THREADS / 32];
 
     const u64 t  = blockIdx.x;
     const u64 d0 = t * (u64)MJ_TILE;
@@ -109,102 +109,149 @@ __global__ void __launch_bounds__(MJ_THREADS) k_mj_tile(const u64 *__restrict__ 
     __syncthreads();
     const u64 *sR = s_it, *sS = s_it + la;
 
-    // ---- one exclusive scan over [A(r_0..la-1), B(s_0..lb-1)]
-    {
-        u64       v[MJ_IPT];
-        u64       ts   = 0;
-        const u32 base = threadIdx.x * MJ_IPT;
-#pragma unroll
-        for (int k = 0; k < MJ_IPT; k++) {
-            u32 idx = base + k;
-            v[k]    = (idx < la) ? smj_cks_a(s_it[idx]) : (idx < cnt ? smj_cks_b(s_it[idx]) : 0ull);
-            ts += v[k];
-        }
-        u64 incl = ts;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u64 x = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
-            if (lane >= (u32)o) incl += x;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        u64 run = incl - ts;
-        for (u32 w = 0; w < warp; w++) run += s_wsum[w];
-#pragma unroll
-        for (int k = 0; k < MJ_IPT; k++) {
-            s_pf[base + k] = run;
-            run += v[k];
-        }
-        if (threadIdx.x == MJ_THREADS - 1) s_pf[MJ_TILE] = run;
-    }
-    __syncthreads();
-
-    // ---- keys that may continue in a neighbouring tile
+    // ---- the tile's first / last key: their runs may continue in the neighbouring tiles
     const u32 kf = min(la ? key_of(sR[0]) : 0xffffffffu, lb ? key_of(sS[0]) : 0xffffffffu);
     const u32 kl = max(la ? key_of(sR[la - 1]) : 0u, lb ? key_of(sS[lb - 1]) : 0u);
+    const bool first_open = (r0 > 0 && key_of(r[r0 - 1]) == kf) || (s0 > 0 && key_of(s[s0 - 1]) == kf);
+    const bool last_open  = (r1 < nr && key_of(r[r1]) == kl) || (s1 < ns && key_of(s[s1]) == kl);
+    // a key whose run is not complete inside this tile is left to k_mj_fixup
+    const bool ex_f = first_open || (kf == kl && last_open);
+    const bool ex_l = (kl != kf) && last_open;
 
     u64 my_cnt = 0, my_cks = 0;
-    for (u32 j = threadIdx.x; j < lb; j += MJ_THREADS) {
-        const u32 k = key_of(sS[j]);
-        if (j > 0 && key_of(sS[j - 1]) == k) continue;  // not the head of its S run
-        if (k == kf || k == kl) continue;               // stitched by k_mj_fixup
-        u32 lo = lower_key(sR, 0, la, k);
-        if (lo >= la || key_of(sR[lo]) != k) continue;  // no partner in R
-        u32 hi = lo + 1;
-        if (hi < la && key_of(sR[hi]) == k) hi = upper_key(sR, hi, la, k);
-        u32 j2 = j + 1;
-        if (j2 < lb && key_of(sS[j2]) == k) j2 = upper_key(sS, j2, lb, k);
-        my_cnt += semi ? (u64)(j2 - j) : (u64)(hi - lo) * (u64)(j2 - j);
-        my_cks += (s_pf[hi] - s_pf[lo]) * (s_pf[la + j2] - s_pf[la + j]);
-    }
+    u64 f_cr = 0, f_cs = 0, f_sa = 0, f_sb = 0, l_cr = 0, l_cs = 0, l_sa = 0, l_sb = 0;
 
-    if (threadIdx.x == 0) {
-        u32   hr = upper_key(sR, 0, la, kf), hs = upper_key(sS, 0, lb, kf);
-        MjRec rec;
-        rec.key = kf;
-        rec.cr  = hr;
-        rec.cs  = hs;
-        rec.sa  = s_pf[hr] - s_pf[0];
-        rec.sb  = s_pf[la + hs] - s_pf[la];
-        recs[2 * t] = rec;
-    }
-    if (threadIdx.x == 32) {
-        MjRec rec;
-        rec.key = kl;
-        if (kl != kf) {
-            u32 lr = lower_key(sR, 0, la, kl), ls = lower_key(sS, 0, lb, kl);
-            rec.cr = la - lr;
-            rec.cs = lb - ls;
-            rec.sa = s_pf[la] - s_pf[lr];
-            rec.sb = s_pf[la + lb] - s_pf[la + ls];
-        } else {
-            rec.cr = rec.cs = rec.sa = rec.sb = 0;
+    const u32 d = min((u32)(threadIdx.x * MJ_IPT), cnt);
+    u32       ai, bi;
+    {  // merge path on keys inside the tile, R before S on ties
+        u32 lo = d > lb ? d - lb : 0, hi = d < la ? d : la;
+        while (lo < hi) {
+            u32 mid = (lo + hi) >> 1;
+            if (key_of(sR[mid]) <= key_of(sS[d - 1 - mid]))
+                lo = mid + 1;
+            else
+                hi = mid;
         }
-        recs[2 * t + 1] = rec;
+        ai = lo;
+        bi = d - lo;
+    }
+    // Heads of the two pieces and the last items passed are kept in registers: one shared-memory
+    // load per step (the classic serial merge), everything else is register compares.
+    u64  a_it = (ai < la) ? sR[ai] : 0ull, b_it = (bi < lb) ? sS[bi] : 0ull;
+    u64  last_r      = (ai > 0) ? sR[ai - 1] : 0ull;       // last R item before the cursor
+    bool has_last_r  = ai > 0;
+    u32  last_r2_key = (ai > 1) ? key_of(sR[ai - 2]) : 0u;  // and the one before it
+    bool has_last_r2 = ai > 1;
+    u32  prev_s_key  = (bi > 0) ? key_of(sS[bi - 1]) : 0u;
+    bool has_prev_s  = bi > 0;
+#pragma unroll 1
+    for (int step = 0; step < MJ_IPT; step++) {
+        if (d + step >= cnt) break;
+        // The body is written with selects instead of an R branch and an S branch: the lanes of
+        // a warp disagree on take_r at almost every step and would otherwise run both sides.
+        const bool take_r = (bi >= lb) || (ai < la && key_of(a_it) <= key_of(b_it));
+        const u64  x      = take_r ? a_it : b_it;
+        const u32  k      = key_of(x);
+        bool       open   = false;
+        if (ex_f | ex_l) {  // block-uniform and rare: a run crosses the tile boundary
+            if (ex_f && k == kf) {
+                open = true;
+                if (take_r) {
+                    f_cr++;
+                    f_sa += smj_cks_a(x);
+                } else {
+                    f_cs++;
+                    f_sb += smj_cks_b(x);
+                }
+            } else if (ex_l && k == kl) {
+                open = true;
+                if (take_r) {
+                    l_cr++;
+                    l_sa += smj_cks_a(x);
+                } else {
+                    l_cs++;
+                    l_sb += smj_cks_b(x);
+                }
+            }
+        }
+        // advance the cursor that was taken and load its next head (one shared-memory load)
+        const u32 nidx = take_r ? ai + 1 : la + bi + 1;
+        const u32 nend = take_r ? la : cnt;
+        const u64 nxt  = (nidx < nend) ? s_it[nidx] : 0ull;
+        // an S item that starts an S run and whose key equals the last R item passed
+        const bool head = !take_r && !open && !(has_prev_s && prev_s_key == k) && has_last_r &&
+                          key_of(last_r) == k;
+        if (head) {
+            const bool multi = (has_last_r2 && last_r2_key == k) || (bi + 1 < lb && key_of(nxt) == k);
+            if (!multi) {
+                my_cnt += 1;
+                my_cks += smj_cks_a(last_r) * smj_cks_b(x);
+            } else {  // duplicates: the R run is [lo, ai), the S run [bi, j2)
+                u32 lo = ai - 1;
+                if (has_last_r2 && last_r2_key == k) lo = lower_key(sR, 0, lo, k);
+                u32 j2 = bi + 1;
+                if (j2 < lb && key_of(nxt) == k) j2 = upper_key(sS, j2, lb, k);
+                const u32 cr = ai - lo, cs = j2 - bi;
+                my_cnt += semi ? (u64)cs : (u64)cr * (u64)cs;
+                u64 sa = 0, sb = 0;
+                for (u32 i = lo; i < ai; i++) sa += smj_cks_a(sR[i]);
+                for (u32 j = bi; j < j2; j++) sb += smj_cks_b(sS[j]);
+                my_cks += sa * sb;
+            }
+        }
+        if (take_r) {
+            last_r2_key = key_of(last_r);
+            has_last_r2 = has_last_r;
+            last_r      = x;
+            has_last_r  = true;
+            ai++;
+            a_it = nxt;
+        } else {
+            prev_s_key = k;
+            has_prev_s = true;
+            bi++;
+            b_it = nxt;
+        }
     }
 
-    my_cnt = warp_reduce_add(my_cnt);
-    my_cks = warp_reduce_add(my_cks);
-    if (lane == 0) {
-        s_red[0][warp] = my_cnt;
-        s_red[1][warp] = my_cks;
+    // ---- block reduction: count / checksum always, the boundary partial sums only when needed
+    const int nred  = (ex_f | ex_l) ? 10 : 2;
+    u64       v[10] = {my_cnt, my_cks, f_cr, f_cs, f_sa, f_sb, l_cr, l_cs, l_sa, l_sb};
+#pragma unroll
+    for (int q = 0; q < 10; q++) {
+        if (q < nred) {
+            u64 x = warp_reduce_add(v[q]);
+            if (lane == 0) s_red[q][warp] = x;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        u64 c = 0, x = 0;
-        for (int w = 0; w < MJ_THREADS / 32; w++) {
-            c += s_red[0][w];
-            x += s_red[1][w];
+        u64 tot[10];
+        for (int q = 0; q < 10; q++) {
+            tot[q] = 0;
+            if (q < nred)
+                for (int w = 0; w < MJ_THREADS / 32; w++) tot[q] += s_red[q][w];
         }
-        if (c) atomicAdd(acc, c);
-        if (x) atomicAdd(acc + 1, x);
+        if (tot[0]) atomicAdd(acc, tot[0]);
+        if (tot[1]) atomicAdd(acc + 1, tot[1]);
+        rec_valid[2 * t]     = ex_f ? 1 : 0;
+        rec_valid[2 * t + 1] = ex_l ? 1 : 0;
+        if (ex_f) {
+            MjRec rec = {kf, tot[2], tot[3], tot[4], tot[5]};
+            recs[2 * t] = rec;
+        }
+        if (ex_l) {
+            MjRec rec = {kl, tot[6], tot[7], tot[8], tot[9]};
+            recs[2 * t + 1] = rec;
+        }
     }
 }
 
-// Stitch the per-tile boundary records: consecutive records with the same key form one run.
+// Stitch the per-tile boundary records: consecutive valid records with the same key form one run.
 constexpr int FX_THREADS = 512;
-__global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict__ recs, u64 nrec,
-                                                         u64 *__restrict__ acc, int semi) {
+__global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict__ recs,
+                                                         const unsigned char *__restrict__ rec_valid,
+                                                         u64 nrec, u64 *__restrict__ acc, int semi) {
     __shared__ MjRec         s_open[2 * FX_THREADS];
     __shared__ unsigned char s_valid[2 * FX_THREADS];
     __shared__ u64           s_red[2][FX_THREADS / 32];
@@ -214,17 +261,21 @@ __global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict
     u64       my_cnt = 0, my_cks = 0;
     s_valid[2 * threadIdx.x]     = 0;
     s_valid[2 * threadIdx.x + 1] = 0;
-    if (lo < hi) {
-        MjRec cur         = recs[lo];
-        bool  first_saved = false;
-        for (u64 i = lo + 1; i < hi; i++) {
-            MjRec x = recs[i];
-            if (x.key == cur.key) {
+    {
+        MjRec cur;
+        bool  have = false, first_saved = false;
+        cur.key = cur.cr = cur.cs = cur.sa = cur.sb = 0;
+        for (u64 i = lo; i < hi; i++) {
+            if (!rec_valid[i]) continue;
+            const MjRec x = recs[i];
+            if (have && x.key == cur.key) {
                 cur.cr += x.cr;
                 cur.cs += x.cs;
                 cur.sa += x.sa;
                 cur.sb += x.sb;
-            } else {
+                continue;
+            }
+            if (have) {
                 if (!first_saved) {  // may continue a run of the previous chunk
                     s_open[2 * threadIdx.x]  = cur;
                     s_valid[2 * threadIdx.x] = 1;
@@ -233,12 +284,15 @@ __global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict
                     my_cnt += semi ? (cur.cr ? cur.cs : 0ull) : cur.cr * cur.cs;
                     my_cks += cur.sa * cur.sb;
                 }
-                cur = x;
             }
+            cur  = x;
+            have = true;
         }
-        const int slot = first_saved ? 1 : 0;  // may continue in the next chunk
-        s_open[2 * threadIdx.x + slot]  = cur;
-        s_valid[2 * threadIdx.x + slot] = 1;
+        if (have) {  // may continue in the next chunk
+            const int slot                  = first_saved ? 1 : 0;
+            s_open[2 * threadIdx.x + slot]  = cur;
+            s_valid[2 * threadIdx.x + slot] = 1;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -293,23 +347,18 @@ __global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict
 int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc,
                        int semi = 0) {
     if (nr == 0 || ns == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_mj_tile, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)MJ_SMEM));
-        attr_set = true;
-    }
     const u64  tiles = div_up(nr + ns, MJ_TILE);
     SmjScratch sc(ctx);
-    u64   *d_diag = (u64 *)sc.get((tiles + 1) * 8);
-    MjRec *d_recs = (MjRec *)sc.get(tiles * 2 * sizeof(MjRec));
-    if (!d_diag || !d_recs) return smj_fail_msg("merge_join: scratch allocation failed");
+    u64           *d_diag  = (u64 *)sc.get((tiles + 1) * 8);
+    MjRec         *d_recs  = (MjRec *)sc.get(tiles * 2 * sizeof(MjRec));
+    unsigned char *d_valid = (unsigned char *)sc.get(tiles * 2);
+    if (!d_diag || !d_recs || !d_valid) return smj_fail_msg("merge_join: scratch allocation failed");
     SMJ_LAUNCH(ctx, k_mj_partition, (unsigned)div_up(tiles + 1, 256), 256, 0, r, nr, s, ns, tiles,
                d_diag);
     SMJ_ITEMS(ctx, nr + ns);
-    SMJ_LAUNCH(ctx, k_mj_tile, (unsigned)tiles, MJ_THREADS, MJ_SMEM, r, nr, s, ns, d_diag, d_recs,
-               acc, semi);
-    SMJ_LAUNCH(ctx, k_mj_fixup, 1, FX_THREADS, 0, d_recs, tiles * 2, acc, semi);
+    SMJ_LAUNCH(ctx, k_mj_tile, (unsigned)tiles, MJ_THREADS, 0, r, nr, s, ns, d_diag, d_recs,
+               d_valid, acc, semi);
+    SMJ_LAUNCH(ctx, k_mj_fixup, 1, FX_THREADS, 0, d_recs, d_valid, tiles * 2, acc, semi);
     return 0;
 }
 

@@ -15,11 +15,12 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
 
-constexpr int RADIX_NB = 256;  // bins per pass (8-bit digits)
+constexpr int RADIX_NB = 512;  // stride of every per-digit table; a pass uses 2^8 or 2^9 bins
 
 // ---------------------------------------------------------------------------------------
 // OR / AND of all items: tells which bit positions vary at all (constant bits need no pass)
@@ -212,83 +213,96 @@ constexpr u64 ST_AGG    = 1ull << 62;  // tile-local count published
 constexpr u64 ST_PREFIX = 2ull << 62;  // inclusive prefix over tiles 0..t published
 constexpr u64 ST_VAL    = (1ull << 62) - 1;
 
-template <int THREADS, int IPT>
+template <int THREADS, int IPT, int BITS>
 struct OneSweepCfg {
+    static constexpr int    NB    = 1 << BITS;
     static constexpr int    WARPS = THREADS / 32;
     static constexpr int    TILE  = THREADS * IPT;
-    static constexpr size_t SMEM =
-        (size_t)TILE * 8 + (size_t)WARPS * RADIX_NB * 4 + RADIX_NB * 4 + RADIX_NB * 8;
+    static constexpr int    BPT   = (NB + THREADS - 1) / THREADS;  // bins owned by a thread
+    static constexpr size_t SMEM  = (size_t)TILE * 8 + (size_t)WARPS * NB * 4 + NB * 8;
 };
 
-template <int THREADS, int IPT, class F>
-__global__ void __launch_bounds__(THREADS, 2)
-    k_onesweep(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, F fn,
-               const u64 *__restrict__ bases,  // [256] global start of every bin
-               u64 *status,                    // [tiles][256] look-back state, zeroed
-               u32 *tile_counter,              // zeroed
-               DigitFn fn_full, const u64 *__restrict__ padshift) {
-    using Cfg = OneSweepCfg<THREADS, IPT>;
-    static_assert(THREADS >= RADIX_NB, "need one thread per bin");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_items     = (u64 *)smem_raw;                        // TILE staged items
-    u32 *s_whist     = (u32 *)(s_items + Cfg::TILE);           // [WARPS][256]
-    u32 *s_tile_base = s_whist + Cfg::WARPS * RADIX_NB;        // [256] exclusive scan of the tile
-    u64 *s_goff      = (u64 *)(s_tile_base + RADIX_NB);        // [256] global offset - tile_base
-    __shared__ u32 s_tile;
-    __shared__ u32 s_wsum[32];
-
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < Cfg::WARPS * RADIX_NB; i += THREADS) s_whist[i] = 0;
-    __syncthreads();
-
-    const u32 tile       = s_tile;
+// Ranks are computed with warp votes: one ballot per digit bit gives every lane the mask of the
+// lanes that hold the same digit ("peers").  match.any would do the same in one instruction but
+// executes on the XU pipe once per DISTINCT value in the warp (~28 for random 8-bit digits): the
+// first version of this kernel was XU-bound at 24 % of the HBM roofline because of it
+// (profiles/r01_onesweep_matchany.txt).
+// One tile of a stable partitioning pass:
+//   1. load the tile (warp-striped: position order == memory order)
+//   2. count: per-warp histogram with shared-memory atomics                -> publish the tile's
+//      per-bin counts for the look-back of later tiles as early as possible
+//   3. scan: counts -> position of every (warp, bin) group inside the tile
+//   4. rank: position of every item = group position + number of equal-digit items before it.
+//      RANK 0 finds the equal-digit lanes ("peers") with one ballot per digit bit, RANK 1 through a
+//      per-warp bitmask in shared memory (atomicOr of the lane bit into mask[digit]); the mask
+//      array aliases the staging buffer, which is idle until step 5.  match.any would do it in
+//      one instruction but runs on the XU pipe once per DISTINCT value in the warp: the first
+//      version of this kernel was bound by it (profiles/r01_onesweep.md).
+//   5. stage the tile in bin order in shared memory, finish the look-back (global position of the
+//      tile's first item of every bin), write runs of consecutive addresses.
+template <int THREADS, int IPT, int BITS, class F, bool FULL, int RANK>
+__device__ __forceinline__ void onesweep_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                              const F &fn, const u64 *__restrict__ bases,
+                                              u64 *status, const DigitFn &fn_full,
+                                              const u64 *__restrict__ padshift, u32 tile,
+                                              u32 valid, u64 *s_items, u32 *s_whist,
+                                              u64 *s_goff, u32 *s_wsum) {
+    using Cfg = OneSweepCfg<THREADS, IPT, BITS>;
+    constexpr int NB  = Cfg::NB;
+    constexpr int BPT = Cfg::BPT;
     const u64 tile_start = (u64)tile * Cfg::TILE;
-    const u64 remain     = n - tile_start;
-    const u32 valid      = remain < (u64)Cfg::TILE ? (u32)remain : (u32)Cfg::TILE;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 last_bin   = fn.last_bin();  // bins in use: 0..last_bin (<= 255)
+    const u32 last_bin   = fn.last_bin();  // bins in use: 0..last_bin (< NB)
     const u32 lt         = lanemask_lt();
 
-    // ---- load (warp-striped so that rank order == memory order) and rank
+    // ---- 1. load
     u64       item[IPT];
-    u32       rank[IPT];
     const u32 wbase = warp * 32 * IPT;
+    const u64 *src  = in + tile_start + wbase + lane;
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        item[j] = (FULL || wbase + j * 32 + lane < valid) ? ld_stream(src + j * 32) : ~0ull;
+
+    // ---- 2. count
+    u32 *wh = s_whist + warp * NB;
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
-        u32 idx = wbase + j * 32 + lane;
-        item[j] = (idx < valid) ? ld_stream(in + tile_start + idx) : ~0ull;
-    }
-    u32 *wh = s_whist + warp * RADIX_NB;
-#pragma unroll
-    for (int j = 0; j < IPT; j++) {
-        u32 idx    = wbase + j * 32 + lane;
-        u32 d      = (idx < valid) ? fn(item[j]) : last_bin;
-        u32 m      = __match_any_sync(SMJ_FULL_MASK, d);
-        u32 leader = __ffs(m) - 1;
-        u32 prev   = 0;
-        if (lane == leader) {
-            prev  = wh[d];
-            wh[d] = prev + __popc(m);
-        }
-        __syncwarp();
-        prev    = __shfl_sync(SMJ_FULL_MASK, prev, leader);
-        rank[j] = prev + __popc(m & lt);
+        const u32 d = (FULL || wbase + j * 32 + lane < valid) ? fn(item[j]) : last_bin;
+        atomicAdd(&wh[d], 1u);
     }
     __syncthreads();
 
-    // ---- per bin: exclusive scan over warps, then exclusive scan over bins
-    u32 tile_cnt = 0;
-    if (threadIdx.x < RADIX_NB) {
-        u32 run = 0;
+    // ---- 3. scan: every thread owns BPT consecutive bins
+    u32 cntb[BPT], tsum = 0;
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS; w++) {
-            u32 t                                = s_whist[w * RADIX_NB + threadIdx.x];
-            s_whist[w * RADIX_NB + threadIdx.x] = run;
-            run += t;
+    for (int q = 0; q < BPT; q++) {
+        const u32 b = threadIdx.x * BPT + q;
+        u32       c = 0;
+        if (b < NB) {
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS; w++) c += s_whist[w * NB + b];
         }
-        tile_cnt = run;
+        cntb[q] = c;
+        tsum += c;
     }
-    u32 incl = tile_cnt;
+    // publish the counts now: later tiles can add them up while this one is still ranking
+    u64 first_prev[BPT];  // state of the previous tile, fetched early and looked at in step 5
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const u32 b   = threadIdx.x * BPT + q;
+        first_prev[q] = 0;
+        if (b <= last_bin) {
+            // padding items of a partial tile were counted in the last bin; they are not data
+            const u64 cnt = (u64)cntb[q] - ((b == last_bin) ? (u64)(Cfg::TILE - valid) : 0ull);
+            if (tile == 0) {
+                st_relaxed(status + b, ST_PREFIX | cnt);
+            } else {
+                st_relaxed(status + (u64)tile * NB + b, ST_AGG | cnt);
+                first_prev[q] = ld_relaxed(status + (u64)(tile - 1) * NB + b);
+            }
+        }
+    }
+    u32 incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         u32 t = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
@@ -296,54 +310,106 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    u32 excl = 0;
-    if (threadIdx.x < RADIX_NB) {
-        u32 woff = 0;
-        for (u32 w = 0; w < warp; w++) woff += s_wsum[w];
-        excl                     = woff + incl - tile_cnt;
-        s_tile_base[threadIdx.x] = excl;
-    }
-
-    // ---- decoupled look-back: global rank of this tile's first item in every bin
-    if (threadIdx.x <= last_bin) {
-        const u32 b = threadIdx.x;
-        // padding items of a partial tile were counted in the last bin; they are not data
-        const u64 cnt  = (u64)tile_cnt - ((b == last_bin) ? (u64)(Cfg::TILE - valid) : 0ull);
-        u64      *st   = status + (u64)tile * RADIX_NB + b;
-        u64       prev = 0;
-        if (tile == 0) {
-            st_relaxed(st, ST_PREFIX | cnt);
-        } else {
-            st_relaxed(st, ST_AGG | cnt);
-            long long t = (long long)tile - 1;
-            while (true) {
-                u64 s;
-                do {
-                    s = ld_relaxed(status + (u64)t * RADIX_NB + b);
-                } while ((s >> 62) == 0);
-                prev += s & ST_VAL;
-                if ((s >> 62) == 2) break;
-                t--;
-            }
-            st_relaxed(st, ST_PREFIX | (prev + cnt));
-        }
-        s_goff[b] = bases[b] + prev - (u64)excl;
-    }
-    __syncthreads();  // s_tile_base, s_whist (warp bases) and s_goff visible
-
-    // ---- stage the tile in bin order, then write runs of consecutive addresses
+    u32 excl = incl - tsum;
+    for (u32 w = 0; w < warp; w++) excl += s_wsum[w];
+    u32 excl_b[BPT];
 #pragma unroll
-    for (int j = 0; j < IPT; j++) {
-        u32 idx = wbase + j * 32 + lane;
-        u32 d   = (idx < valid) ? fn(item[j]) : last_bin;
-        u32 pos = s_tile_base[d] + wh[d] + rank[j];
-        s_items[pos] = item[j];
+    for (int q = 0; q < BPT; q++) {
+        const u32 b = threadIdx.x * BPT + q;
+        excl_b[q]   = excl;
+        if (b < NB) {
+            u32 run = excl;
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS; w++) {
+                const u32 t         = s_whist[w * NB + b];
+                s_whist[w * NB + b] = run;  // tile position of warp w's first item of bin b
+                run += t;
+            }
+        }
+        excl += cntb[q];
     }
     __syncthreads();
+
+    // ---- 4. rank: tile position of every item (two 16-bit positions per register)
+    u32  pos2[IPT / 2];
+    u32 *wm = (u32 *)s_items + warp * NB;  // RANK 1 only; zeroed by the kernel prologue
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        const u32 d = (FULL || wbase + j * 32 + lane < valid) ? fn(item[j]) : last_bin;
+        u32       peers, base;
+        if (RANK == 0) {
+            peers = SMJ_FULL_MASK;
+#pragma unroll
+            for (int b = 0; b < BITS; b++) {
+                const bool bit = (d >> b) & 1u;
+                const u32  v   = __ballot_sync(SMJ_FULL_MASK, bit);
+                peers &= bit ? v : ~v;
+            }
+            base = wh[d];  // the same word for all peers: a broadcast
+            __syncwarp();
+            if ((peers >> lane) == 1u) wh[d] = base + __popc(peers);  // highest peer bumps it
+            __syncwarp();
+        } else {
+            atomicOr(&wm[d], 1u << lane);
+            __syncwarp();
+            peers = wm[d];
+            base  = wh[d];
+            __syncwarp();
+            if ((peers >> lane) == 1u) {
+                wh[d] = base + __popc(peers);
+                wm[d] = 0;
+            }
+            __syncwarp();
+        }
+        const u32 p = base + __popc(peers & lt);  // peers in lower lanes come earlier in memory
+        if (j & 1)
+            pos2[j / 2] |= p << 16;
+        else
+            pos2[j / 2] = p;
+    }
+    if (RANK == 1) __syncthreads();  // the mask arrays alias the staging buffer
+
+    // ---- 5. stage in bin order
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        s_items[(j & 1) ? (pos2[j / 2] >> 16) : (pos2[j / 2] & 0xffffu)] = item[j];
+
+    // finish the decoupled look-back: global rank of this tile's first item in every bin
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const u32 b = threadIdx.x * BPT + q;
+        if (b <= last_bin) {
+            u64 prev = 0;
+            if (tile != 0) {
+                const u64 cnt = (u64)cntb[q] - ((b == last_bin) ? (u64)(Cfg::TILE - valid) : 0ull);
+                long long t   = (long long)tile - 1;
+                u64       sv  = first_prev[q];
+                while (true) {
+                    while ((sv >> 62) == 0) sv = ld_relaxed(status + (u64)t * NB + b);
+                    prev += sv & ST_VAL;
+                    if ((sv >> 62) == 2) break;
+                    t--;
+                    sv = ld_relaxed(status + (u64)t * NB + b);
+                }
+                st_relaxed(status + (u64)tile * NB + b, ST_PREFIX | (prev + cnt));
+            }
+            s_goff[b] = bases[b] + prev - (u64)excl_b[q];
+        }
+    }
+    __syncthreads();  // staged items and s_goff visible
+
     if (padshift == nullptr) {
-        for (u32 i = threadIdx.x; i < valid; i += THREADS) {
-            u64 x = s_items[i];
-            st_stream(out + s_goff[fn(x)] + i, x);
+        if (FULL) {
+#pragma unroll 4
+            for (u32 i = threadIdx.x; i < (u32)Cfg::TILE; i += THREADS) {
+                u64 x = s_items[i];
+                st_stream(out + s_goff[fn(x)] + i, x);
+            }
+        } else {
+            for (u32 i = threadIdx.x; i < valid; i += THREADS) {
+                u64 x = s_items[i];
+                st_stream(out + s_goff[fn(x)] + i, x);
+            }
         }
     } else {
         for (u32 i = threadIdx.x; i < valid; i += THREADS) {
@@ -353,31 +419,122 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
 }
 
-// tuning point: 384 threads x 16 items = 6144 items (48 KB) per tile, 2 CTAs / SM
-constexpr int OS_THREADS = 384;
-constexpr int OS_IPT     = 16;
-using OSCfg              = OneSweepCfg<OS_THREADS, OS_IPT>;
+template <int THREADS, int IPT, int BITS, class F, int RANK, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    k_onesweep(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, F fn,
+               const u64 *__restrict__ bases,  // [NB] global start of every bin
+               u64 *status,                    // [tiles][NB] look-back state, zeroed
+               u32 *tile_counter,              // zeroed
+               DigitFn fn_full, const u64 *__restrict__ padshift) {
+    using Cfg = OneSweepCfg<THREADS, IPT, BITS>;
+    constexpr int NB = Cfg::NB;
+    static_assert(IPT % 2 == 0, "positions are packed in pairs");
+    static_assert(Cfg::TILE <= 65536, "positions are 16 bit");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_items = (u64 *)smem_raw;                       // TILE staged items
+    u32 *s_whist = (u32 *)(s_items + Cfg::TILE);          // [WARPS][NB]
+    u64 *s_goff  = (u64 *)(s_whist + Cfg::WARPS * NB);    // [NB] global offset - tile position
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wsum[32];
 
-struct PassState {
-    u64 *status;
-    u32 *counter;
-};
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < Cfg::WARPS * NB; i += THREADS) s_whist[i] = 0;
+    if (RANK == 1) {
+        static_assert(Cfg::WARPS * NB * 4 <= Cfg::TILE * 8, "mask array must fit the staging area");
+        for (int i = threadIdx.x; i < Cfg::WARPS * NB; i += THREADS) ((u32 *)s_items)[i] = 0;
+    }
+    __syncthreads();
+    const u32 tile   = s_tile;
+    const u64 remain = n - (u64)tile * Cfg::TILE;
+    if (remain >= (u64)Cfg::TILE)
+        onesweep_tile<THREADS, IPT, BITS, F, true, RANK>(in, out, fn, bases, status, fn_full,
+                                                         padshift, tile, (u32)Cfg::TILE, s_items,
+                                                         s_whist, s_goff, s_wsum);
+    else
+        onesweep_tile<THREADS, IPT, BITS, F, false, RANK>(in, out, fn, bases, status, fn_full,
+                                                          padshift, tile, (u32)remain, s_items,
+                                                          s_whist, s_goff, s_wsum);
+}
+
+// Tile shapes (SMJ_OS_CFG selects one; default 1).  Wide digits want big tiles: with 512 bins a
+// 4096-item tile has only 8 items per bin to amortise the per-bin scan and look-back over.
+//   0: 256 threads x 16 items, 4 CTAs/SM    1: 512 x 16, 2 CTAs/SM
+//   2: 256 x 24, 3 CTAs/SM                  3: 384 x 16, 2 CTAs/SM
+constexpr int OS_MIN_TILE = 4096;
+
+inline size_t status_bytes(u64 n) {
+    // sized for the smallest tile and the largest bin count: fits every configuration
+    return (size_t)div_up(n, OS_MIN_TILE) * RADIX_NB * 8;
+}
+
+template <int THREADS, int IPT, int BITS, class F, int RANK, int MINB>
+int launch_onesweep_cfg(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64 *bases,
+                        u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
+    using Cfg = OneSweepCfg<THREADS, IPT, BITS>;
+    static_assert(Cfg::TILE >= OS_MIN_TILE, "status_bytes assumes tiles of at least OS_MIN_TILE");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const u64 tiles = div_up(n, Cfg::TILE);
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, (k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>), (unsigned)tiles, THREADS,
+               Cfg::SMEM, in, out, n, fn, bases, status, counter, fn_full, padshift);
+    return 0;
+}
+
+inline int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// SMJ_RANK_MODE=0 selects the ballot ranking, 1 (default) the shared-memory bitmask ranking
+inline int rank_mode() {
+    static int mode = env_int("SMJ_RANK_MODE", 1);
+    return mode;
+}
+inline int os_cfg() {
+    static int cfg = env_int("SMJ_OS_CFG", 1);
+    return cfg;
+}
+
+template <int BITS, int RANK, class F>
+int launch_onesweep_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64 *bases,
+                          u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
+    switch (os_cfg()) {
+        case 0:
+            return launch_onesweep_cfg<256, 16, BITS, F, RANK, 4>(ctx, in, out, n, fn, bases, status,
+                                                                  counter, fn_full, padshift);
+        case 2:
+            return launch_onesweep_cfg<256, 24, BITS, F, RANK, 3>(ctx, in, out, n, fn, bases, status,
+                                                                  counter, fn_full, padshift);
+        case 3:
+            return launch_onesweep_cfg<384, 16, BITS, F, RANK, 2>(ctx, in, out, n, fn, bases, status,
+                                                                  counter, fn_full, padshift);
+        default:
+            return launch_onesweep_cfg<512, 16, BITS, F, RANK, 2>(ctx, in, out, n, fn, bases, status,
+                                                                  counter, fn_full, padshift);
+    }
+}
 
 template <class F>
 int launch_onesweep(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64 *bases,
                     u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep<OS_THREADS, OS_IPT, F>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)OSCfg::SMEM));
-        attr_set = true;
+    const bool wide = fn.last_bin() >= 256;
+    if (rank_mode() == 0) {
+        if (wide)
+            return launch_onesweep_shape<9, 0, F>(ctx, in, out, n, fn, bases, status, counter,
+                                                  fn_full, padshift);
+        return launch_onesweep_shape<8, 0, F>(ctx, in, out, n, fn, bases, status, counter, fn_full,
+                                              padshift);
     }
-    const u64 tiles = div_up(n, OSCfg::TILE);
-    SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, (k_onesweep<OS_THREADS, OS_IPT, F>), (unsigned)tiles, OS_THREADS, OSCfg::SMEM,
-               in, out, n, fn, bases, status, counter, fn_full, padshift);
-    return 0;
+    if (wide)
+        return launch_onesweep_shape<9, 1, F>(ctx, in, out, n, fn, bases, status, counter, fn_full,
+                                              padshift);
+    return launch_onesweep_shape<8, 1, F>(ctx, in, out, n, fn, bases, status, counter, fn_full,
+                                          padshift);
 }
 
 // histogram of one bucket function with <= 256 bins
@@ -394,8 +551,6 @@ __global__ void __launch_bounds__(512) k_hist_fn(const u64 *__restrict__ in, u64
     for (int i = threadIdx.x; i < RADIX_NB; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
 }
-
-inline size_t status_bytes(u64 n) { return (size_t)div_up(n, OSCfg::TILE) * RADIX_NB * 8; }
 
 int hist_grid(SmjCtx *ctx, u64 n, int threads, int per_thread) {
     u64 want = div_up(n, (u64)threads * per_thread);
@@ -428,20 +583,34 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     u64 varying = h_bits[0] & ~h_bits[1];
     if (key_only) varying &= 0xffffffff00000000ull;
 
-    // plan: cover the varying bits, least significant first, with windows of <= 8 bits
+    // plan: cover the varying bits, least significant first.  Bits that are closer than 9
+    // positions form a group; a group of span s takes ceil(s/9) passes of equal width (27 key
+    // bits -> 9+9+9, 30 bits -> 8+8+7+7), each window trimmed to the bits that really vary.
     DigitPlan plan;
     plan.nd = 0;
     u64 v   = varying;
-    while (v) {
-        int lo   = __builtin_ctzll(v);
-        int bits = std::min(8, 64 - lo);
-        u64 win  = (v >> lo) & ((1ull << bits) - 1);
-        bits     = 64 - __builtin_clzll(win);  // trim constant bits at the top of the window
-        plan.d[plan.nd].sub   = 0;
-        plan.d[plan.nd].shift = (u32)lo;
-        plan.d[plan.nd].mask  = (u32)((1ull << bits) - 1);
-        plan.nd++;
-        v &= ~(((1ull << bits) - 1) << lo);
+    while (v && plan.nd < 8) {
+        const int lo  = __builtin_ctzll(v);
+        int       end = lo + 1;  // one past the highest bit of the group
+        for (int b = lo + 1; b < 64 && b < end + 9; b++)
+            if ((v >> b) & 1) end = b + 1;
+        const int span   = end - lo;
+        const int passes = (span + 8) / 9;
+        const int width  = (span + passes - 1) / passes;
+        for (int p = 0; p < passes && plan.nd < 8; p++) {
+            const int wlo = lo + p * width;
+            int       w   = std::min(width, end - wlo);
+            u64       win = (varying >> wlo) & ((1ull << w) - 1);
+            if (win == 0) continue;  // nothing varies inside this window
+            const int skip = __builtin_ctzll(win);
+            win >>= skip;
+            w                     = 64 - __builtin_clzll(win);
+            plan.d[plan.nd].sub   = 0;
+            plan.d[plan.nd].shift = (u32)(wlo + skip);
+            plan.d[plan.nd].mask  = (u32)((1ull << w) - 1);
+            plan.nd++;
+        }
+        v = (end >= 64) ? 0 : (v >> end) << end;
     }
     if (plan.nd == 0) return 0;  // all items equal (on the compared bits): already sorted
 
@@ -462,9 +631,10 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     const u64 *cur = in;
     for (int k = 0; k < plan.nd; k++) {
         u64 *dst = (k & 1) ? b : a;
-        int  rc  = launch_onesweep(ctx, cur, dst, n, plan.d[k], d_bases + (size_t)k * RADIX_NB,
-                                   (u64 *)((char *)d_status + sbytes * k), d_count + k, plan.d[k],
-                                   nullptr);
+        FieldFn f  = {plan.d[k].shift, plan.d[k].mask};
+        int     rc = launch_onesweep(ctx, cur, dst, n, f, d_bases + (size_t)k * RADIX_NB,
+                                     (u64 *)((char *)d_status + sbytes * k), d_count + k, plan.d[k],
+                                     nullptr);
         if (rc) return rc;
         cur = dst;
     }
@@ -517,7 +687,7 @@ extern "C" int smjdev_partition(const uint64_t *in_, uint64_t *out_, uint64_t *t
     int rc = run_hist_wide(ctx, in, n, full, nbins, hist);
     if (rc) return rc;
     SmjScratch sc(ctx);
-    const bool two_pass = nbits > 8;
+    const bool two_pass = nbits > 9;
     u64 *d_padshift = (padded && two_pass) ? (u64 *)sc.get((size_t)nbins * 8) : nullptr;
     if (padded && two_pass && !d_padshift) return smj_fail_msg("smjdev_partition: scratch");
     SMJ_LAUNCH(ctx, k_bases_wide, 1, 1024, 0, hist, nbins, padded, offs, d_padshift);
