@@ -440,7 +440,7 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
     for (int i = 0; i < runs; i++) {
         u64  len    = off[i + 1] - off[i];
         u64 *sorted = nullptr;
-        int  rc = smj_lsd_sort(ctx, in + off[i], a + off[i], b + off[i], len, 1, &sorted);
+        int  rc = smj_lsd_sort(ctx, in + off[i], a + off[i], b + off[i], len, 2, &sorted);
         if (rc) return rc;
         ptrs.push_back(sorted);
         lens.push_back(len);
@@ -480,8 +480,8 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             // (the reference's nthreads == 1 path, sortmergejoin_multiway.c:476-489)
             u64 *sr = nullptr, *ss = nullptr;
             t_part = tm.mark();
-            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 1, &sr))) return rc;
-            if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 1, &ss))) return rc;
+            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
+            if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
             t_sort = t_merge = tm.mark();
             if ((rc = smj_merge_join_acc(ctx, sr, nr, ss, ns, acc))) return rc;
             t_join = tm.mark();
@@ -510,7 +510,7 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             std::vector<const u64 *> ps;
             std::vector<u64>         ls;
             t_part = tm.mark();
-            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 1, &sr))) return rc;
+            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
             if ((rc = sort_runs(ctx, s, aS, bS, ns, nruns, ps, ls))) return rc;
             t_sort = t_merge = tm.mark();
             for (size_t i = 0; i < ps.size(); i++)

@@ -213,6 +213,31 @@ constexpr u64 ST_AGG    = 1ull << 62;  // tile-local count published
 constexpr u64 ST_PREFIX = 2ull << 62;  // inclusive prefix over tiles 0..t published
 constexpr u64 ST_VAL    = (1ull << 62) - 1;
 
+// Decoupled look-back for one bin: sum of the bin's counts over all earlier tiles.  The states of
+// LB predecessors are fetched with independent loads, so one L2 round trip covers LB tiles; with
+// one predecessor per round trip the whole pass is limited to about 2*depth tiles per L2 latency
+// (45 % of the warp time of the first versions was spent here, profiles/r01_onesweep.md).
+template <int NB>
+__device__ __forceinline__ u64 lookback_sum(const u64 *status, u32 tile, u32 b) {
+    constexpr int LB   = 8;
+    u64           prev = 0;
+    long long     t    = (long long)tile - 1;
+    while (true) {
+        u64 sv[LB];
+#pragma unroll
+        for (int i = 0; i < LB; i++)
+            sv[i] = (t - i >= 0) ? ld_relaxed(status + (u64)(t - i) * NB + b) : ST_PREFIX;
+#pragma unroll
+        for (int i = 0; i < LB; i++) {
+            u64 x = sv[i];
+            while ((x >> 62) == 0) x = ld_relaxed(status + (u64)(t - i) * NB + b);
+            prev += x & ST_VAL;
+            if ((x >> 62) == 2) return prev;
+        }
+        t -= LB;
+    }
+}
+
 template <int THREADS, int IPT, int BITS>
 struct OneSweepCfg {
     static constexpr int    NB    = 1 << BITS;
@@ -286,11 +311,9 @@ __device__ __forceinline__ void onesweep_tile(const u64 *__restrict__ in, u64 *_
         tsum += c;
     }
     // publish the counts now: later tiles can add them up while this one is still ranking
-    u64 first_prev[BPT];  // state of the previous tile, fetched early and looked at in step 5
 #pragma unroll
     for (int q = 0; q < BPT; q++) {
         const u32 b   = threadIdx.x * BPT + q;
-        first_prev[q] = 0;
         if (b <= last_bin) {
             // padding items of a partial tile were counted in the last bin; they are not data
             const u64 cnt = (u64)cntb[q] - ((b == last_bin) ? (u64)(Cfg::TILE - valid) : 0ull);
@@ -298,7 +321,6 @@ __device__ __forceinline__ void onesweep_tile(const u64 *__restrict__ in, u64 *_
                 st_relaxed(status + b, ST_PREFIX | cnt);
             } else {
                 st_relaxed(status + (u64)tile * NB + b, ST_AGG | cnt);
-                first_prev[q] = ld_relaxed(status + (u64)(tile - 1) * NB + b);
             }
         }
     }
@@ -382,15 +404,7 @@ __device__ __forceinline__ void onesweep_tile(const u64 *__restrict__ in, u64 *_
             u64 prev = 0;
             if (tile != 0) {
                 const u64 cnt = (u64)cntb[q] - ((b == last_bin) ? (u64)(Cfg::TILE - valid) : 0ull);
-                long long t   = (long long)tile - 1;
-                u64       sv  = first_prev[q];
-                while (true) {
-                    while ((sv >> 62) == 0) sv = ld_relaxed(status + (u64)t * NB + b);
-                    prev += sv & ST_VAL;
-                    if ((sv >> 62) == 2) break;
-                    t--;
-                    sv = ld_relaxed(status + (u64)t * NB + b);
-                }
+                prev = lookback_sum<NB>(status, tile, b);
                 st_relaxed(status + (u64)tile * NB + b, ST_PREFIX | (prev + cnt));
             }
             s_goff[b] = bases[b] + prev - (u64)excl_b[q];
@@ -454,6 +468,136 @@ __global__ void __launch_bounds__(THREADS, MINB)
         onesweep_tile<THREADS, IPT, BITS, F, false, RANK>(in, out, fn, bases, status, fn_full,
                                                           padshift, tile, (u32)remain, s_items,
                                                           s_whist, s_goff, s_wsum);
+}
+
+// ---------------------------------------------------------------------------------------
+// UNSTABLE partitioning pass: same contract as k_onesweep except that items of one bin keep no
+// particular order inside a tile.  Good enough for the first pass of a key-only sort (nothing to
+// preserve yet) and for MSD passes; much cheaper, because the rank of an item is simply the value
+// a shared-memory atomicAdd on the bin counter returns: no per-warp histograms, no peer search.
+// ---------------------------------------------------------------------------------------
+template <int THREADS, int IPT, int BITS, class F, bool FULL>
+__device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                              const F &fn, u64 *cursors, u32 tile, u32 valid,
+                                              u64 *s_items, u32 *s_cnt, u64 *s_goff, u32 *s_wsum) {
+    constexpr int NB   = 1 << BITS;
+    constexpr int TILE = THREADS * IPT;
+    constexpr int BPT  = (NB + THREADS - 1) / THREADS;
+    const u64 tile_start = (u64)tile * TILE;
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 last_bin = fn.last_bin();
+
+    u64       item[IPT];
+    u32       pos2[IPT / 2];
+    const u64 *src = in + tile_start + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        item[j] = (FULL || j * THREADS + threadIdx.x < valid) ? ld_stream(src + j * THREADS) : ~0ull;
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        u32 r = 0;  // rank inside the tile's bin; items past the end of the input take no part
+        if (FULL || j * THREADS + threadIdx.x < valid) r = atomicAdd(&s_cnt[fn(item[j])], 1u);
+        if (j & 1)
+            pos2[j / 2] |= r << 16;
+        else
+            pos2[j / 2] = r;
+    }
+    __syncthreads();
+
+    // Order between tiles does not matter either, so there is no look-back chain: the tile
+    // reserves its slice of every bin with one atomicAdd on the bin's global cursor.
+    u32 cntb[BPT], tsum = 0;
+    u64 gbase[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const u32 b = threadIdx.x * BPT + q;
+        cntb[q]     = (b < NB) ? s_cnt[b] : 0u;
+        gbase[q]    = 0;
+        tsum += cntb[q];
+        if (b <= last_bin && cntb[q]) gbase[q] = atomicAdd(&cursors[b], (u64)cntb[q]);
+    }
+    u32 incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    u32 excl = incl - tsum;
+    for (u32 w = 0; w < warp; w++) excl += s_wsum[w];
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const u32 b = threadIdx.x * BPT + q;
+        if (b < NB) {
+            s_cnt[b]  = excl;  // tile position of the bin's first item
+            s_goff[b] = gbase[q] - (u64)excl;
+        }
+        excl += cntb[q];
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+        if (FULL || j * THREADS + threadIdx.x < valid) {
+            const u32 r = (j & 1) ? (pos2[j / 2] >> 16) : (pos2[j / 2] & 0xffffu);
+            s_items[s_cnt[fn(item[j])] + r] = item[j];
+        }
+    }
+    __syncthreads();
+    if (FULL) {
+#pragma unroll 4
+        for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
+            u64 x = s_items[i];
+            st_stream(out + s_goff[fn(x)] + i, x);
+        }
+    } else {
+        for (u32 i = threadIdx.x; i < valid; i += THREADS) {
+            u64 x = s_items[i];
+            st_stream(out + s_goff[fn(x)] + i, x);
+        }
+    }
+}
+
+template <int THREADS, int IPT, int BITS, class F>
+__global__ void __launch_bounds__(THREADS, 2)
+    k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, F fn,
+                        u64 *cursors /* [NB], initialised to the start of every bin */) {
+    constexpr int NB   = 1 << BITS;
+    constexpr int TILE = THREADS * IPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_items = (u64 *)smem_raw;           // TILE staged items
+    u32 *s_cnt   = (u32 *)(s_items + TILE);   // [NB]
+    u64 *s_goff  = (u64 *)(s_cnt + NB);       // [NB]
+    __shared__ u32 s_wsum[32];
+    for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const u32 tile   = blockIdx.x;
+    const u64 remain = n - (u64)tile * TILE;
+    if (remain >= (u64)TILE)
+        unstable_tile<THREADS, IPT, BITS, F, true>(in, out, fn, cursors, tile, (u32)TILE, s_items,
+                                                   s_cnt, s_goff, s_wsum);
+    else
+        unstable_tile<THREADS, IPT, BITS, F, false>(in, out, fn, cursors, tile, (u32)remain,
+                                                    s_items, s_cnt, s_goff, s_wsum);
+}
+
+// bases: [NB] start of every bin; it is used as the cursor array and is CONSUMED (on return
+// bases[b] is the end of bin b)
+template <int BITS, class F>
+int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases) {
+    constexpr int    THREADS = 512, IPT = 16, NB = 1 << BITS, TILE = THREADS * IPT;
+    constexpr size_t SMEM    = (size_t)TILE * 8 + NB * 4 + NB * 8;
+    static bool      attr_set = false;
+    if (!attr_set) {
+        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_set = true;
+    }
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F>), (unsigned)div_up(n, TILE), THREADS,
+               SMEM, in, out, n, fn, bases);
+    return 0;
 }
 
 // Tile shapes (SMJ_OS_CFG selects one; default 1).  Wide digits want big tiles: with 512 bins a
@@ -563,6 +707,8 @@ int hist_grid(SmjCtx *ctx, u64 n, int threads, int per_thread) {
 // ---------------------------------------------------------------------------------------
 // LSD radix sort over the varying bits (internal entry used by smjdev_sort and the joins)
 // ---------------------------------------------------------------------------------------
+// key_only: 0 = order by the whole 64-bit word, 1 = by the key, stable, 2 = by the key with an
+// unspecified order among equal keys (first pass may then be the cheaper unstable kernel).
 // Reads `in`, ping-pongs between the scratch buffers a and b (pass 1: in -> a, pass 2: a -> b,
 // pass 3: b -> a, ...).  `in` may alias b (classic two-buffer sort) but not a.  *sorted is set
 // to the buffer that holds the result, which is `in` itself when no pass was necessary.
@@ -632,7 +778,16 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     for (int k = 0; k < plan.nd; k++) {
         u64 *dst = (k & 1) ? b : a;
         FieldFn f  = {plan.d[k].shift, plan.d[k].mask};
-        int     rc = launch_onesweep(ctx, cur, dst, n, f, d_bases + (size_t)k * RADIX_NB,
+        int     rc;
+        if (k == 0 && key_only == 2) {  // order among equal keys is irrelevant to the caller
+            rc = (f.mask >= 256)
+                     ? launch_unstable<9>(ctx, cur, dst, n, f, d_bases)
+                     : launch_unstable<8>(ctx, cur, dst, n, f, d_bases);
+            if (rc) return rc;
+            cur = dst;
+            continue;
+        }
+        rc = launch_onesweep(ctx, cur, dst, n, f, d_bases + (size_t)k * RADIX_NB,
                                      (u64 *)((char *)d_status + sbytes * k), d_count + k, plan.d[k],
                                      nullptr);
         if (rc) return rc;
