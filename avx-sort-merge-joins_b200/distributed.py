@@ -1,0 +1,131 @@
+"""Multi-GPU sort-merge join: one process per GPU, torch.distributed (NCCL over NVLink) for the
+plumbing, the library's CUDA kernels for everything that touches tuples.
+
+This replaces the reference's cross-socket step: there, thread t owns partitions [t*F/T, (t+1)*F/T)
+and its multiway merge PULLS the sorted runs of those partitions out of every other thread's
+memory in NUMA-shuffle order (src/joins/sortmergejoin_multiway.c:492-517,
+src/util/numa_shuffle.c:56-85).  Here rank g owns a key range; every rank range-partitions its
+slice of R and S by the same splitters (smjdev_range_partition: one stable scatter pass whose
+output is already laid out as per-destination contiguous send regions, so there is no pack
+kernel), the slices are exchanged with one all-to-all per relation, each rank joins what it
+received with the single-GPU pipeline and the counts / checksums are all-reduced.
+
+    exchange-then-sort instead of the reference's sort-then-merge: the same bytes cross the
+    links, but no G-way merge is needed afterwards.
+
+The per-rank engine is pluggable so that the orchestration (splitters, count exchange, ragged
+all-to-all, reduction) can be tested on CPU with the gloo backend; the product engine is
+CudaEngine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class CudaEngine:
+    """Local engine backed by libsmj_b200.so; relations are torch.int64 CUDA tensors holding the
+    8-byte items (key<<32 | payload)."""
+
+    def __init__(self, smj, device: torch.device):
+        self.smj, self.lib, self.device = smj, smj.lib, device
+        torch.cuda.set_device(device)
+        smj.check(self.lib.smjdev_init(device.index if device.index is not None else 0), "smjdev_init")
+        # run on torch's current stream so that NCCL collectives and our kernels are ordered
+        smj.check(self.lib.smjdev_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def empty(self, n: int) -> torch.Tensor:
+        return torch.empty(max(int(n), 1), dtype=torch.int64, device=self.device)
+
+    def to_local(self, host: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(host.view(np.int64)).to(self.device, non_blocking=True)
+
+    def gen_unique(self, n_total: int, first: int, count: int, seed: int) -> torch.Tensor:
+        t = self.empty(count)
+        self.smj.check(self.lib.smjdev_gen_unique(t.data_ptr(), n_total, first, count, seed), "gen")
+        return t
+
+    def range_partition(self, src: torch.Tensor, n: int, splitters: np.ndarray, nparts: int):
+        out, counts = self.empty(n), torch.zeros(nparts, dtype=torch.int64, device=self.device)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        self.smj.check(self.lib.smjdev_range_partition(
+            src.data_ptr(), out.data_ptr(), n, sp.ctypes.data_as(C.POINTER(C.c_uint32)), nparts,
+            counts.data_ptr()), "range_partition")
+        return out, counts
+
+    def join(self, r: torch.Tensor, nr: int, s: torch.Tensor, ns: int):
+        st = self.smj.smj_join_stats_t()
+        self.smj.check(self.lib.smjdev_join(self.smj.ALGO_MWAY, r.data_ptr(), nr, s.data_ptr(), ns, 1,
+                                            C.byref(st)), "smjdev_join")
+        return st.matches, st.checksum
+
+    def sample_keys(self, t: torch.Tensor, n: int, k: int) -> torch.Tensor:
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        stride = max(n // k, 1)
+        return (t[:n:stride] >> 32).contiguous()
+
+    def result_tensor(self, count: int, checksum: int) -> torch.Tensor:
+        # two's complement view: the checksum is a uint64, all-reduce sums wrap the same way
+        vals = np.array([count, checksum], dtype=np.uint64).view(np.int64)
+        return torch.from_numpy(vals).to(self.device)
+
+
+def uniform_splitters(maxkey: int, nparts: int) -> np.ndarray:
+    """Equal-width key ranges for dense keys 1..maxkey: dest(key) = #splitters <= key."""
+    return np.array([(i * maxkey) // nparts + 1 for i in range(1, nparts)], dtype=np.uint32)
+
+
+class DistributedJoin:
+    def __init__(self, engine, rank: int, world: int):
+        self.e, self.rank, self.world = engine, rank, world
+
+    # ---- splitters: the same on every rank, for R and S alike
+    def sampled_splitters(self, r, nr: int, s, ns: int, per_rank: int = 4096) -> np.ndarray:
+        """Quantiles of a sample of the keys of both relations gathered from all ranks (skewed
+        keys: SURVEY.md 8e).  Heavy hitters end up on one rank: the result stays exact, the load
+        becomes uneven."""
+        mine = torch.cat([self.e.sample_keys(r, nr, per_rank), self.e.sample_keys(s, ns, per_rank)])
+        size = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
+        sizes = [torch.zeros_like(size) for _ in range(self.world)]
+        dist.all_gather(sizes, size)
+        cap = int(max(int(x.item()) for x in sizes))
+        padded = torch.full((cap,), -1, dtype=torch.int64, device=mine.device)
+        padded[:mine.numel()] = mine
+        allp = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(allp, padded)
+        keys = torch.cat(allp)
+        keys = torch.sort(keys[keys >= 0]).values.cpu().numpy()
+        if keys.size == 0:
+            return np.zeros(self.world - 1, dtype=np.uint32)
+        q = [keys[min(keys.size - 1, (i * keys.size) // self.world)] for i in range(1, self.world)]
+        return np.asarray(q, dtype=np.uint32)
+
+    # ---- ragged all-to-all of one partitioned relation
+    def exchange(self, part: torch.Tensor, counts: torch.Tensor):
+        recv_counts = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts, counts)
+        send = [int(x) for x in counts.cpu().tolist()]  # the collective needs host-side sizes
+        recv = [int(x) for x in recv_counts.cpu().tolist()]
+        n_recv = sum(recv)
+        out = self.e.empty(n_recv)
+        dist.all_to_all_single(out[:n_recv], part[:sum(send)], output_split_sizes=recv,
+                               input_split_sizes=send)
+        return out, n_recv, send, recv
+
+    def step(self, r, nr: int, s, ns: int, splitters: np.ndarray):
+        """One complete distributed join of the local slices; returns the GLOBAL (count, checksum)
+        and the number of item bytes this rank sent to other ranks."""
+        pr, cr = self.e.range_partition(r, nr, splitters, self.world)
+        ps, cs = self.e.range_partition(s, ns, splitters, self.world)
+        rr, nrr, send_r, _ = self.exchange(pr, cr)
+        ss, nss, send_s, _ = self.exchange(ps, cs)
+        cnt, cks = self.e.join(rr, nrr, ss, nss)
+        res = self.e.result_tensor(cnt, cks)
+        dist.all_reduce(res, op=dist.ReduceOp.SUM)
+        out = res.cpu().numpy().view(np.uint64)
+        sent = 8 * (sum(send_r) - send_r[self.rank] + sum(send_s) - send_s[self.rank])
+        return int(out[0]), int(out[1]), sent

@@ -317,7 +317,13 @@ def main() -> None:
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     smj = importlib.import_module("avx-sort-merge-joins_b200")  # fails loudly if the .so is missing
-    if world > 1 or args.gpus > 1:
+    if world == 1 and args.gpus > 1:
+        # not started by torchrun: start one rank per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if world > 1:
         import bench_multigpu
         line = bench_multigpu.run(args, smj)
     else:

@@ -1,0 +1,112 @@
+"""N-GPU leg of bench.py (launched by torchrun, one rank per GPU): the 128M x 128M m-way join with
+the relations spread evenly over the ranks, range-partition + NCCL all-to-all + local join +
+all-reduce per step (avx-sort-merge-joins_b200/distributed.py).  Strong scaling: the total work
+is the same at every N."""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench as B
+
+
+def run(args, smj):
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dj_mod = importlib.import_module("avx-sort-merge-joins_b200.distributed")
+    eng = dj_mod.CudaEngine(smj, dev)
+    dj = dj_mod.DistributedJoin(eng, rank, world)
+    lib = smj.lib
+
+    n = args.size
+    first, count = (n * rank) // world, (n * (rank + 1)) // world - (n * rank) // world
+    r = eng.gen_unique(n, first, count, B.SEED_R)
+    s = eng.gen_unique(n, first, count, B.SEED_S)
+    splitters = dj_mod.uniform_splitters(n, world)  # keys are a permutation of 1..n
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        cnt, cks, sent = dj.step(r, count, s, count, splitters)
+    assert cnt == n, f"rank {rank}: distributed join returned {cnt}, expected {n}"
+
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    launches0 = lib.smjdev_launch_count()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cnt, cks, sent = dj.step(r, count, s, count, splitters)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([lib.smjdev_launch_count() - launches0], dtype=torch.int64, device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if sampler else None
+    ms_step = float(ms.item()) / args.steps
+    value = 2 * n / (ms_step * 1e-3) / 1e6
+    assert cnt == n
+
+    # ---- end to end: each rank's slices start in pinned host memory
+    hr = torch.empty(count, dtype=torch.int64).pin_memory()
+    hs = torch.empty(count, dtype=torch.int64).pin_memory()
+    hr.copy_(r[:count])
+    hs.copy_(s[:count])
+    sync_all()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dr = hr.to(dev, non_blocking=True)
+        ds = hs.to(dev, non_blocking=True)
+        c2, _, _ = dj.step(dr, count, ds, count, splitters)
+        assert c2 == n
+    sync_all()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    line = None
+    if rank == 0:
+        peak, peak_src = B.measured_peak()
+        link_gbs = sent / (ms_step * 1e-3) / 1e9  # exchange bytes leaving this GPU / whole step
+        line = {
+            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"sortmergejoins -a m-way, |R|=|S|={n} 8-byte tuples, uniform unique keys "
+                                   f"(BASELINE.json configs[0]), relations spread evenly over {world} GPUs",
+                       "parallelism": f"range partition by key + NCCL all-to-all over {world} GPUs, local m-way join, "
+                                      f"all-reduce of count/checksum",
+                       "l2": "per-rank inputs (2 x %.2f GB) are larger than L2" % (count * 8 / 1e9),
+                       "timing": "CUDA events on the stream shared with NCCL, max over ranks",
+                       "exchange_bytes_sent_per_rank": sent},
+            "clocks": clocks,
+            "e2e": {"value": 2 * n / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": 2 * n * 8,
+                    "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "api": "DistributedJoin.step on per-rank pinned host slices"},
+            "gpu_launches": int(launches.item()),
+            "roofline": {"bound": "hbm", "achieved": 40.0 * 2 * n / (ms_step * 1e-3) / 1e9 / world,
+                         "peak": peak, "unit": "GB/s", "frac": 40.0 * 2 * n / (ms_step * 1e-3) / 1e9 / world / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "whole step per GPU at 40 algorithmic B/tuple; per-kernel figures are in the N=1 line",
+                         "nvlink_gbs_sent_per_gpu_over_step": link_gbs},
+            "cpu_baseline": None, "matches": cnt, "checksum": cks,
+        }
+    dist.barrier()
+    dist.destroy_process_group()
+    return line

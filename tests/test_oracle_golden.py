@@ -1,0 +1,46 @@
+"""The C oracle against the frozen reference outputs in tests/golden/ref_golden.npz (generated from
+the unmodified reference by tests/golden/make_golden.py).  CPU only; runs where /root/reference
+does not exist."""
+import os
+
+import numpy as np
+import pytest
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+
+
+def test_sort_golden(orc):
+    for n in G["sort_sizes"]:
+        assert np.array_equal(orc.sort(G[f"sort_in_{n}"]), G[f"sort_out_{n}"])
+        assert orc.placement(int(n)) == int(G[f"sort_place_{n}"])
+    for n, v in zip(G["place_n"], G["place_v"]):
+        assert orc.placement(int(n)) == int(v), n
+
+
+def test_merge_golden(orc):
+    assert np.array_equal(orc.merge(G["merge_a"], G["merge_b"], 0), G["merge_avx"])
+    assert np.array_equal(orc.merge(G["merge_ak"], G["merge_bk"], 1), G["merge_scalar"])
+    runs = np.split(G["mway_in"], np.cumsum(G["mway_lens"])[:-1])
+    assert np.array_equal(orc.multiway_merge(runs), G["mway_out"])
+
+
+@pytest.mark.parametrize("nbits,shift", [(4, 0), (7, 3), (10, 1)])
+def test_partition_golden(orc, nbits, shift):
+    for tag, padded in (("plain", False), ("opt", True), ("v2", True)):
+        out, hist, offs, _ = orc.partition(G["part_in"], nbits, shift, padded)
+        assert np.array_equal(hist, G[f"part_{tag}_{nbits}_{shift}_hist"])
+        assert np.array_equal(offs, G[f"part_{tag}_{nbits}_{shift}_offs"])
+        packed = np.concatenate([out[int(o):int(o) + int(c)] for o, c in zip(offs, hist)])
+        assert np.array_equal(packed, G[f"part_{tag}_{nbits}_{shift}_data"])
+
+
+def test_join_golden(orc):
+    assert orc.merge_join(G["mj_r"], G["mj_s"])[0] == int(G["mj_count"])
+    assert orc.merge_join_runs(G["mj_r"], G["mj_s"]) == orc.merge_join(G["mj_r"], G["mj_s"])
+    assert orc.merge_join_interpolation(G["mji_r"], G["mji_s"]) == int(G["mji_count"])
+    R, S, D1, D2 = G["join_R"], G["join_S"], G["join_D1"], G["join_D2"]
+    assert orc.join_bruteforce(R, S)[0] == int(G["join_RS_mway_2"]) == int(G["join_RS_mway_4"]) == \
+        int(G["join_RS_mpass_4"])
+    assert orc.join_mway(R, S, 2, 128) == orc.join_mway(R, S, 4, 64) == orc.join_bruteforce(R, S)
+    assert orc.join_bruteforce(D1, D2)[0] == int(G["join_DD_mway_2"]) == int(G["join_DD_mpass_2"])
+    assert orc.join_mway(D1, D2, 2, 128) == orc.join_bruteforce(D1, D2)
