@@ -74,6 +74,7 @@ SIGNATURES = {
     "smjdev_init": (C.c_int, [C.c_int]),
     "smjdev_current_device": (C.c_int, []),
     "smjdev_set_stream": (C.c_int, [_vp]),
+    "smjdev_use_own_stream": (C.c_int, []),
     "smjdev_get_stream": (_vp, []),
     "smjdev_sync": (C.c_int, []),
     "smjdev_last_error": (C.c_char_p, []),

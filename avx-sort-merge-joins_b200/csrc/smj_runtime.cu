@@ -109,7 +109,13 @@ int smjdev_current_device(void) {
 int smjdev_set_stream(void *s) {
     SmjCtx *c = smj_ctx();
     if (!c) return -1;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;  // NULL is CUDA's legacy default stream (what torch uses by default)
+    return 0;
+}
+int smjdev_use_own_stream(void) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    c->stream = c->own_stream;
     return 0;
 }
 void *smjdev_get_stream(void) {

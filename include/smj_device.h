@@ -25,7 +25,8 @@ extern "C" {
 int         smjdev_device_count(void);
 int         smjdev_init(int device);          /* idempotent; device<0 -> $SMJ_DEVICE, $LOCAL_RANK or 0 */
 int         smjdev_current_device(void);
-int         smjdev_set_stream(void *cuda_stream); /* run on the caller's stream (NULL -> own stream) */
+int         smjdev_set_stream(void *cuda_stream); /* run on the caller's stream; NULL = legacy default stream */
+int         smjdev_use_own_stream(void);          /* back to the library's own non-blocking stream (the default) */
 void       *smjdev_get_stream(void);
 int         smjdev_sync(void);
 const char *smjdev_last_error(void);
