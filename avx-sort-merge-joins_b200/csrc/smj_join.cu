@@ -21,12 +21,16 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
 int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, const u64 *lens,
                        u32 nruns, int mode);
+int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
+                      u64 *offsets, u64 *maxbucket, u64 *exact_bits);
+int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
 
 namespace {
 
@@ -394,6 +398,83 @@ extern "C" int smjdev_merge_join_ex(const uint64_t *r, uint64_t nr, const uint64
 }
 
 // ---------------------------------------------------------------------------------------
+// In-partition sort + merge-join, fused, for the 2^18 key-range buckets of smj_msd_partition.
+//
+// Inside a bucket only L <= 10 key bits still differ, so the in-partition sort degenerates to a
+// counting sort over 2^L key slots, and the merge-join scan over two sorted buckets only needs,
+// per key, |run_R| and sum A(r) -- exactly the counting sort's histogram.  One warp owns a bucket:
+// it builds {count, sum A} per key slot from the R bucket in shared memory and streams the S
+// bucket past it:  count += |run_R(key(s))|,  checksum += sum A(run_R(key(s))) * B(s).
+// Sorted buckets are never written back: 8 B per input tuple of HBM traffic instead of 16 + 8.
+// Buckets are handed out through an atomic counter, so uneven bucket sizes balance themselves.
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr int BJ_WARPS = 8;
+
+__global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__restrict__ r,
+                                                               const u64 *__restrict__ roffs,
+                                                               const u64 *__restrict__ s,
+                                                               const u64 *__restrict__ soffs,
+                                                               u32 nbuckets, u32 lo_shift, u32 lbits,
+                                                               u32 *next_bucket, u64 *__restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 slots = 1u << lbits, mask = slots - 1;
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per warp: u64 sumA[slots] followed by u32 cnt[slots]
+    u64 *t_sum = (u64 *)(smem_raw + (size_t)warp * slots * 12);
+    u32 *t_cnt = (u32 *)(t_sum + slots);
+    u64  my_cnt = 0, my_cks = 0;
+    while (true) {
+        u32 b = 0;
+        if (lane == 0) b = atomicAdd(next_bucket, 1u);
+        b = __shfl_sync(SMJ_FULL_MASK, b, 0);
+        if (b >= nbuckets) break;
+        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        if (r0 == r1 || s0 == s1) continue;
+        for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;  // sums and counts
+        __syncwarp();
+        for (u64 i = r0 + lane; i < r1; i += 128) {  // 4 independent loads in flight per lane
+            u64 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = (i + 32 * u < r1) ? ld_stream(r + i + 32 * u) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i + 32 * u < r1) {
+                    const u32 slot = (u32)(x[u] >> lo_shift) & mask;
+                    atomicAdd(&t_cnt[slot], 1u);
+                    atomicAdd(&t_sum[slot], smj_cks_a(x[u]));
+                }
+            }
+        }
+        __syncwarp();
+        for (u64 j = s0 + lane; j < s1; j += 128) {
+            u64 y[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) y[u] = (j + 32 * u < s1) ? ld_stream(s + j + 32 * u) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (j + 32 * u < s1) {
+                    const u32 slot = (u32)(y[u] >> lo_shift) & mask;
+                    const u32 c    = t_cnt[slot];
+                    if (c) {
+                        my_cnt += c;
+                        my_cks += t_sum[slot] * smj_cks_b(y[u]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    my_cnt = warp_reduce_add(my_cnt);
+    my_cks = warp_reduce_add(my_cks);
+    if (lane == 0) {
+        if (my_cnt) atomicAdd(acc, my_cnt);
+        if (my_cks) atomicAdd(acc + 1, my_cks);
+    }
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
 // join pipelines
 // ---------------------------------------------------------------------------------------
 namespace {
@@ -449,6 +530,63 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
 }
 }  // namespace
 
+// m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
+// fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
+// do not suit it; the caller then takes the general sort + scan path.
+static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *aR, u64 *bR, u64 *aS,
+                    u64 *bS, u64 *acc, int *used, PhaseTimer &tm, int &t_part, int &t_sort,
+                    int &t_join) {
+    *used = 0;
+    if (nr + ns < (1u << 20)) return 0;  // 2^18 buckets only pay off on large inputs
+    u64 bits[4];
+    // The key range is guessed from a sample (5 us instead of a full read of R and S); the first
+    // histogram pass computes the exact OR / AND on the side and the guess is verified before the
+    // result is used.
+    int rc = smj_key_bits_sampled(ctx, r, nr, s, ns, bits);
+    if (rc) return rc;
+    const u32 vor = (u32)((bits[0] | bits[2]) >> 32), vand = (u32)((bits[1] & bits[3]) >> 32);
+    const u32 v   = vor & ~vand;
+    if (v == 0) return 0;
+    const int hi = 31 - __builtin_clz(v), lo = __builtin_ctz(v), k = hi - lo + 1;
+    if (k < 19 || k > 28) return 0;
+    const u32 lbits  = (u32)(k - 18);
+    const u32 shift1 = 32 + (u32)hi - 8, shift2 = shift1 - 9, lo_shift = 32 + (u32)lo;
+    const u32 nb2    = 512u * 512u;
+    SmjScratch sc(ctx);
+    u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
+    u64 *d_max = (u64 *)sc.get(48);  // [0] max bucket, [1] bucket counter, [2..5] exact OR/AND of R, S
+    if (!offR || !offS || !d_max) return smj_fail_msg("mway_msd: scratch allocation failed");
+    const u64 init[6] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d_max, init, 48, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = smj_msd_partition(ctx, r, nr, aR, bR, shift1, shift2, offR, d_max, d_max + 2))) return rc;
+    if ((rc = smj_msd_partition(ctx, s, ns, aS, bS, shift1, shift2, offS, d_max, d_max + 4))) return rc;
+    u64 h[6];
+    SMJ_CHECK(cudaMemcpyAsync(h, d_max, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    t_part = t_sort = tm.mark();  // the in-partition sort is fused into the join kernel
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    {   // verify the sampled guess: no key bit outside [lo, hi] may vary in R or S
+        const u32 xor_ = (u32)((h[2] | h[4]) >> 32), xand = (u32)((h[3] & h[5]) >> 32);
+        const u32 range = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+        if ((xor_ & ~xand) & ~range) return 0;
+    }
+    if (h[0] > (1ull << 20)) return 0;  // heavy hitters: one warp per bucket would crawl
+    const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        smem_set = smem;
+    }
+    u32 *d_next = (u32 *)(d_max + 1);  // zeroed above
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
+    SMJ_ITEMS(ctx, nr + ns);
+    SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS, offS, nb2,
+               lo_shift, lbits, d_next, acc);
+    t_join = tm.mark();
+    *used  = 1;
+    return 0;
+}
+
 extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint64_t *s_,
                            uint64_t ns, int nruns, smj_join_stats_t *stats) {
     SmjCtx *ctx = smj_ctx();
@@ -478,13 +616,24 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             // range partition + in-partition sort == a global key sort on one GPU: the sorted
             // partitions are disjoint key ranges, so no run merging is needed
             // (the reference's nthreads == 1 path, sortmergejoin_multiway.c:476-489)
-            u64 *sr = nullptr, *ss = nullptr;
-            t_part = tm.mark();
-            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
-            if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
-            t_sort = t_merge = tm.mark();
-            if ((rc = smj_merge_join_acc(ctx, sr, nr, ss, ns, acc))) return rc;
-            t_join = tm.mark();
+            int used = 0;
+            const char *path = getenv("SMJ_MWAY_PATH");  // "lsd" forces the general path
+            if (!(path && path[0] == 'l')) {
+                if ((rc = mway_msd(ctx, r, nr, s, ns, aR, bR, aS, bS, acc, &used, tm, t_part, t_sort,
+                                   t_join)))
+                    return rc;
+                t_merge = t_sort;
+            }
+            if (!used) {
+                u64 *sr = nullptr, *ss = nullptr;
+                SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+                t_part = tm.mark();
+                if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
+                if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
+                t_sort = t_merge = tm.mark();
+                if ((rc = smj_merge_join_acc(ctx, sr, nr, ss, ns, acc))) return rc;
+                t_join = tm.mark();
+            }
         } else if (algo == SMJ_ALGO_MPASS) {
             // sorted runs, then pairwise merge passes (sortmergejoin_multipass.c:410-708)
             std::vector<const u64 *> pr, ps;

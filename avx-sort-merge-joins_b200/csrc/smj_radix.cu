@@ -69,8 +69,10 @@ struct DigitPlan {
 
 __global__ void __launch_bounds__(512) k_hist_digits(const u64 *__restrict__ in, u64 n,
                                                      DigitPlan plan,
-                                                     u64 *__restrict__ hist /* [nd][256] */) {
+                                                     u64 *__restrict__ hist /* [nd][RADIX_NB] */,
+                                                     u64 *__restrict__ bits /* OR, AND or null */) {
     __shared__ u32 sh[8 * RADIX_NB];
+    u64 vor = 0, vand = ~0ull;
     for (int i = threadIdx.x; i < plan.nd * RADIX_NB; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(512) k_hist_digits(const u64 *__restrict__ in,
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             if (ok[u]) {
+                vor |= x[u];
+                vand &= x[u];
 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     if (k < plan.nd) atomicAdd(&sh[k * RADIX_NB + plan.d[k](x[u])], 1u);
@@ -95,6 +99,32 @@ __global__ void __launch_bounds__(512) k_hist_digits(const u64 *__restrict__ in,
     __syncthreads();
     for (int i = threadIdx.x; i < plan.nd * RADIX_NB; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
+    if (bits) {
+        vor  = warp_reduce_or(vor);
+        vand = warp_reduce_and(vand);
+        if (lane_id() == 0) {
+            atomicOr(bits, vor);
+            atomicAnd(bits + 1, vand);
+        }
+    }
+}
+
+// OR / AND of every stride-th item: a cheap guess of the varying bits (verified later)
+__global__ void __launch_bounds__(256) k_bits_sample(const u64 *__restrict__ in, u64 n, u64 stride,
+                                                     u64 *__restrict__ out) {
+    u64 vor = 0, vand = ~0ull;
+    for (u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * stride; i < n;
+         i += (u64)gridDim.x * blockDim.x * stride) {
+        u64 a = in[i];
+        vor |= a;
+        vand &= a;
+    }
+    vor  = warp_reduce_or(vor);
+    vand = warp_reduce_and(vand);
+    if (lane_id() == 0) {
+        atomicOr(out, vor);
+        atomicAnd(out + 1, vand);
+    }
 }
 
 // one digit with up to 2^14 bins in dynamic shared memory (partition API, fan-out sweep)
@@ -771,7 +801,8 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     SMJ_CHECK(cudaMemsetAsync(d_status, 0, sbytes * plan.nd, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_count, 0, sizeof(u32) * 8, ctx->stream));
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, buf, n, plan, d_hist);
+    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, buf, n, plan, d_hist,
+               (u64 *)nullptr);
     SMJ_LAUNCH(ctx, k_bases_multi, plan.nd, RADIX_NB, 0, d_hist, d_bases);
 
     const u64 *cur = in;
@@ -917,4 +948,251 @@ extern "C" int smjdev_range_partition(const uint64_t *in, uint64_t *out, uint64_
     DigitFn none = {0, 0, 0};
     return launch_onesweep(ctx, (const u64 *)in, (u64 *)out, n, fn, d_bases, d_status, d_count, none,
                            nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-level MSD range partition (the m-way join's partitioning phase on one GPU).
+//
+// The reference partitions each thread's chunk once by PARTFANOUT key bits and then needs a
+// multiway merge to bring the threads' runs together (sortmergejoin_multiway.c:331-386, 463-556).
+// Here the whole relation is range-partitioned by its top 18 varying key bits in two unstable
+// passes (9 bits each, atomic bin cursors, no look-back chain): pass A scatters by the top 9
+// bits, pass B partitions every pass-A bucket by the next 9 bits.  Tiles of pass B never straddle
+// a pass-A bucket, so a tile only needs the 512 cursors of its own bucket.  The result is 2^18
+// key-range buckets in key order; what remains of the key inside a bucket is <= 10 bits.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+constexpr int MSD_THREADS = 512, MSD_IPT = 16, MSD_TILE = MSD_THREADS * MSD_IPT, MSD_NB = 512;
+
+// per pass-A bucket: first tile index and first item index (exclusive scans over the 512 buckets)
+__global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restrict__ hist1,
+                                                            u64 *__restrict__ tile_prefix,
+                                                            u64 *__restrict__ bucket_start) {
+    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB];
+    const int      b = threadIdx.x;
+    const u64      c = hist1[b], t = (c + MSD_TILE - 1) / MSD_TILE;
+    s_t[b]           = t;
+    s_c[b]           = c;
+    __syncthreads();
+    for (int o = 1; o < MSD_NB; o <<= 1) {
+        u64 at = (b >= o) ? s_t[b - o] : 0, ac = (b >= o) ? s_c[b - o] : 0;
+        __syncthreads();
+        s_t[b] += at;
+        s_c[b] += ac;
+        __syncthreads();
+    }
+    tile_prefix[b]  = s_t[b] - t;
+    bucket_start[b] = s_c[b] - c;
+    if (b == MSD_NB - 1) {
+        tile_prefix[MSD_NB]  = s_t[b];
+        bucket_start[MSD_NB] = s_c[b];
+    }
+}
+
+// which pass-A bucket does tile `tile` belong to, and which items does it cover
+__device__ __forceinline__ bool msd_locate(const u64 *__restrict__ tile_prefix,
+                                           const u64 *__restrict__ bucket_start, u64 tile, u32 &bucket,
+                                           u64 &start, u32 &valid) {
+    if (tile >= tile_prefix[MSD_NB]) return false;
+    u32 lo = 0, hi = MSD_NB;  // last bucket with tile_prefix <= tile (empty buckets share a prefix)
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (tile_prefix[mid] <= tile)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    bucket        = lo;
+    start         = bucket_start[lo] + (tile - tile_prefix[lo]) * (u64)MSD_TILE;
+    const u64 end = bucket_start[lo + 1];
+    valid         = (u32)min((u64)MSD_TILE, end - start);
+    return true;
+}
+
+__global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict__ in,
+                                                           const u64 *__restrict__ tile_prefix,
+                                                           const u64 *__restrict__ bucket_start,
+                                                           FieldFn fn2, u64 *__restrict__ hist2) {
+    __shared__ u32 sh[MSD_NB];
+    __shared__ u32 s_bucket, s_valid;
+    __shared__ u64 s_start;
+    if (threadIdx.x == 0) {
+        u32 b = 0, v = 0;
+        u64 st = 0;
+        if (!msd_locate(tile_prefix, bucket_start, blockIdx.x, b, st, v)) v = 0;
+        s_bucket = b;
+        s_valid  = v;
+        s_start  = st;
+    }
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 valid = s_valid;
+    if (valid == 0) return;
+    const u64 *src = in + s_start;
+#pragma unroll 4
+    for (u32 i = threadIdx.x; i < valid; i += MSD_THREADS) atomicAdd(&sh[fn2(ld_stream(src + i))], 1u);
+    __syncthreads();
+    const u32 c = sh[threadIdx.x];
+    if (c) atomicAdd(&hist2[(u64)s_bucket * MSD_NB + threadIdx.x], (u64)c);
+}
+
+__global__ void __launch_bounds__(MSD_THREADS, 2)
+    k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out,
+                   const u64 *__restrict__ tile_prefix, const u64 *__restrict__ bucket_start,
+                   FieldFn fn2, u64 *cursors2 /* [512][512], initialised to the bucket starts */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_items = (u64 *)smem_raw;
+    u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
+    u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
+    __shared__ u32 s_wsum[32];
+    __shared__ u32 s_bucket, s_valid;
+    __shared__ u64 s_start;
+    if (threadIdx.x == 0) {
+        u32 b = 0, v = 0;
+        u64 st = 0;
+        if (!msd_locate(tile_prefix, bucket_start, blockIdx.x, b, st, v)) v = 0;
+        s_bucket = b;
+        s_valid  = v;
+        s_start  = st;
+    }
+    s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 valid = s_valid;
+    if (valid == 0) return;
+    u64 *cur = cursors2 + (u64)s_bucket * MSD_NB;
+    if (valid == (u32)MSD_TILE)
+        unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + s_start, out, fn2, cur, 0u, valid,
+                                                              s_items, s_cnt, s_goff, s_wsum);
+    else
+        unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + s_start, out, fn2, cur, 0u, valid,
+                                                               s_items, s_cnt, s_goff, s_wsum);
+}
+
+// exclusive scan of nb entries in two launches: per-block scan + block totals, then add the
+// totals of the preceding blocks (nb / 1024 <= 1024 blocks)
+__global__ void __launch_bounds__(1024) k_scan_local(const u64 *__restrict__ in, u64 nb,
+                                                     u64 *__restrict__ out, u64 *__restrict__ totals) {
+    __shared__ u64 s_w[32];
+    const u64 i    = (u64)blockIdx.x * 1024 + threadIdx.x;
+    const u64 v    = i < nb ? in[i] : 0ull;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64       incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 t = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u64 base = 0;
+    for (u32 w = 0; w < warp; w++) base += s_w[w];
+    if (i < nb) out[i] = base + incl - v;
+    if (threadIdx.x == 1023) totals[blockIdx.x] = base + incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_add(u64 *__restrict__ out, u64 nb,
+                                                   const u64 *__restrict__ totals) {
+    __shared__ u64 s_w[32];
+    u64 p = (threadIdx.x < blockIdx.x) ? totals[threadIdx.x] : 0ull;  // blockIdx.x <= 1024
+    p     = warp_reduce_add(p);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = p;
+    __syncthreads();
+    u64 base = 0;
+    for (int w = 0; w < 32; w++) base += s_w[w];
+    const u64 i = (u64)blockIdx.x * 1024 + threadIdx.x;
+    if (i < nb) out[i] += base;
+}
+
+__global__ void __launch_bounds__(256) k_max_u64(const u64 *__restrict__ v, u64 n, u64 *out) {
+    u64 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(SMJ_FULL_MASK, m, o));
+    if (lane_id() == 0 && m) atomicMax(out, m);
+}
+
+}  // namespace
+
+// in -> a (pass A) -> b (pass B).  shift1 = position of the top 9-bit digit, shift2 = shift1 - 9.
+// offsets: device array of 2^18 + 1 entries, receives the start of every bucket in b (and n).
+// maxbucket: device u64, receives the size of the largest bucket (accumulated with atomicMax, so
+// one variable can be shared by R and S; the caller zeroes it).
+// exact_bits: device pair {OR, AND} (initialised to {0, ~0} by the caller, may be null) that
+// receives the OR / AND of all items as a by-product of the first histogram pass.
+int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
+                      u64 *offsets, u64 *maxbucket, u64 *exact_bits) {
+    const u32  NB2 = MSD_NB * MSD_NB;
+    SmjScratch sc(ctx);
+    u64 *d_hist1 = (u64 *)sc.get(RADIX_NB * 8), *d_bases1 = (u64 *)sc.get(RADIX_NB * 8);
+    u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get((MSD_NB + 1) * 8);
+    u64 *d_hist2 = (u64 *)sc.get((size_t)NB2 * 8), *d_cur2 = (u64 *)sc.get((size_t)NB2 * 8);
+    if (!d_hist1 || !d_bases1 || !d_tpref || !d_bstart || !d_hist2 || !d_cur2)
+        return smj_fail_msg("smj_msd_partition: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_hist1, 0, RADIX_NB * 8, ctx->stream));
+    SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
+    DigitPlan plan;
+    plan.nd   = 1;
+    plan.d[0] = {0ull, shift1, (u32)MSD_NB - 1};
+    FieldFn f1 = {shift1, (u32)MSD_NB - 1}, f2 = {shift2, (u32)MSD_NB - 1};
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, in, n, plan, d_hist1, exact_bits);
+    SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist1, d_bases1);
+    SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_hist1, d_tpref, d_bstart);
+    int rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1);  // consumes d_bases1
+    if (rc) return rc;
+    const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    static bool    attr_set  = false;
+    constexpr size_t SMEM    = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
+    if (!attr_set) {
+        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM));
+        attr_set = true;
+    }
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, f2, d_hist2);
+    u64 *d_tot = (u64 *)sc.get((NB2 / 1024) * 8);
+    if (!d_tot) return smj_fail_msg("smj_msd_partition: scratch allocation failed");
+    SMJ_LAUNCH(ctx, k_scan_local, NB2 / 1024, 1024, 0, d_hist2, (u64)NB2, offsets, d_tot);
+    SMJ_LAUNCH(ctx, k_scan_add, NB2 / 1024, 1024, 0, offsets, (u64)NB2, d_tot);
+    SMJ_LAUNCH(ctx, k_max_u64, 64, 256, 0, d_hist2, (u64)NB2, maxbucket);
+    SMJ_CHECK(cudaMemcpyAsync(d_cur2, offsets, (size_t)NB2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, k_msd_scatter2, max_tiles, MSD_THREADS, SMEM, a, b, d_tpref, d_bstart, f2, d_cur2);
+    return 0;
+}
+
+// Same from a strided sample of about 2^16 items per relation (a guess, to be verified).
+int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *host) {
+    SmjScratch sc(ctx);
+    u64 *d = (u64 *)sc.get(32);
+    if (!d) return smj_fail_msg("smj_key_bits: scratch allocation failed");
+    const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d, init, 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (nr) SMJ_LAUNCH(ctx, k_bits_sample, 64, 256, 0, r, nr, std::max<u64>(1, nr >> 16), d);
+    if (ns) SMJ_LAUNCH(ctx, k_bits_sample, 64, 256, 0, s, ns, std::max<u64>(1, ns >> 16), d + 2);
+    SMJ_CHECK(cudaMemcpyAsync(host, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// OR / AND of all items of two relations: host[0..1] = R, host[2..3] = S.  Synchronises.
+int smj_key_bits(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *host) {
+    SmjScratch sc(ctx);
+    u64 *d = (u64 *)sc.get(32);
+    if (!d) return smj_fail_msg("smj_key_bits: scratch allocation failed");
+    const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d, init, 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (nr) {
+        SMJ_ITEMS(ctx, nr);
+        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, nr, 256, 16), 256, 0, r, nr, d);
+    }
+    if (ns) {
+        SMJ_ITEMS(ctx, ns);
+        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, ns, 256, 16), 256, 0, s, ns, d + 2);
+    }
+    SMJ_CHECK(cudaMemcpyAsync(host, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
