@@ -990,24 +990,22 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restric
     }
 }
 
-// which pass-A bucket does tile `tile` belong to, and which items does it cover
-__device__ __forceinline__ bool msd_locate(const u64 *__restrict__ tile_prefix,
-                                           const u64 *__restrict__ bucket_start, u64 tile, u32 &bucket,
-                                           u64 &start, u32 &valid) {
-    if (tile >= tile_prefix[MSD_NB]) return false;
-    u32 lo = 0, hi = MSD_NB;  // last bucket with tile_prefix <= tile (empty buckets share a prefix)
-    while (hi - lo > 1) {
-        u32 mid = (lo + hi) >> 1;
-        if (tile_prefix[mid] <= tile)
-            lo = mid;
-        else
-            hi = mid;
+// Which pass-A bucket does tile `tile` belong to, and which items does it cover?  Called by all
+// MSD_THREADS (== number of buckets) threads of a CTA: thread b tests bucket b, so the lookup is
+// one coalesced load instead of a ten-step dependent binary search per tile.
+__device__ __forceinline__ void msd_locate(const u64 *__restrict__ tile_prefix,
+                                           const u64 *__restrict__ bucket_start, u64 tile,
+                                           u32 *s_bucket, u64 *s_start, u32 *s_valid) {
+    const u32 b  = threadIdx.x;
+    const u64 t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
+    if (b == 0) *s_valid = 0;  // stays 0 when the tile lies past the last bucket
+    __syncthreads();
+    if (t0 <= tile && tile < t1) {  // exactly one non-empty bucket matches
+        const u64 start = bucket_start[b] + (tile - t0) * (u64)MSD_TILE;
+        *s_bucket       = b;
+        *s_start        = start;
+        *s_valid        = (u32)min((u64)MSD_TILE, bucket_start[b + 1] - start);
     }
-    bucket        = lo;
-    start         = bucket_start[lo] + (tile - tile_prefix[lo]) * (u64)MSD_TILE;
-    const u64 end = bucket_start[lo + 1];
-    valid         = (u32)min((u64)MSD_TILE, end - start);
-    return true;
 }
 
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict__ in,
@@ -1017,14 +1015,7 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict
     __shared__ u32 sh[MSD_NB];
     __shared__ u32 s_bucket, s_valid;
     __shared__ u64 s_start;
-    if (threadIdx.x == 0) {
-        u32 b = 0, v = 0;
-        u64 st = 0;
-        if (!msd_locate(tile_prefix, bucket_start, blockIdx.x, b, st, v)) v = 0;
-        s_bucket = b;
-        s_valid  = v;
-        s_start  = st;
-    }
+    msd_locate(tile_prefix, bucket_start, blockIdx.x, &s_bucket, &s_start, &s_valid);
     sh[threadIdx.x] = 0;
     __syncthreads();
     const u32 valid = s_valid;
@@ -1048,14 +1039,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     __shared__ u32 s_wsum[32];
     __shared__ u32 s_bucket, s_valid;
     __shared__ u64 s_start;
-    if (threadIdx.x == 0) {
-        u32 b = 0, v = 0;
-        u64 st = 0;
-        if (!msd_locate(tile_prefix, bucket_start, blockIdx.x, b, st, v)) v = 0;
-        s_bucket = b;
-        s_valid  = v;
-        s_start  = st;
-    }
+    msd_locate(tile_prefix, bucket_start, blockIdx.x, &s_bucket, &s_start, &s_valid);
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u32 valid = s_valid;
