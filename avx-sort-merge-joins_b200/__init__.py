@@ -109,6 +109,9 @@ SIGNATURES = {
                               C.POINTER(smj_join_stats_t)]),
     "smjdev_range_partition": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32,
                                          _vp]),
+    "smjdev_check_order": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
+    "smjdev_check_partition": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
+                                         _u64p]),
     "smjdev_gen_unique": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "smjdev_gen_fk": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]),
     # --- reference-facing entry points (include/smj_b200.h)

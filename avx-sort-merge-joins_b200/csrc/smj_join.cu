@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
                                                                const u64 *__restrict__ s,
                                                                const u64 *__restrict__ soffs,
                                                                u32 nbuckets, u32 lo_shift, u32 lbits,
-                                                               u32 *next_bucket, u64 *__restrict__ acc) {
+                                                               u64 big, u32 *next_bucket,
+                                                               u64 *__restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 slots = 1u << lbits, mask = slots - 1;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
         if (b >= nbuckets) break;
         const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
         if (r0 == r1 || s0 == s1) continue;
+        if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy hitters: k_big_bucket_join
         for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;  // sums and counts
         __syncwarp();
         for (u64 i = r0 + lane; i < r1; i += 128) {  // 4 independent loads in flight per lane
@@ -530,6 +532,81 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
 }
 }  // namespace
 
+// ---- heavy hitters (Zipf-skewed S): buckets with more than `big` tuples on either side are
+// listed by k_collect_big and joined by ALL warps of the grid together: every warp builds the
+// (small) R table of the bucket and takes an equal slice of its S side.
+namespace {
+__global__ void __launch_bounds__(256) k_collect_big(const u64 *__restrict__ roffs,
+                                                     const u64 *__restrict__ soffs, u32 nbuckets,
+                                                     u64 big, u64 rmax, u32 *__restrict__ list,
+                                                     u32 *__restrict__ info /* [0] count, [1] unsupported */) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const u64 nr = roffs[b + 1] - roffs[b], ns = soffs[b + 1] - soffs[b];
+    if (nr == 0 || ns == 0) return;
+    if (nr > big || ns > big) {
+        if (nr > rmax) atomicExch(&info[1], 1u);  // both sides heavy: leave it to the general path
+        list[atomicAdd(&info[0], 1u)] = b;
+    }
+}
+
+__global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__restrict__ r,
+                                                                   const u64 *__restrict__ roffs,
+                                                                   const u64 *__restrict__ s,
+                                                                   const u64 *__restrict__ soffs,
+                                                                   const u32 *__restrict__ list,
+                                                                   const u32 *__restrict__ info,
+                                                                   u32 lo_shift, u32 lbits,
+                                                                   u64 *__restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 slots = 1u << lbits, mask = slots - 1;
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u64 *t_sum = (u64 *)(smem_raw + (size_t)warp * slots * 12);
+    u32 *t_cnt = (u32 *)(t_sum + slots);
+    const u64 gw = (u64)blockIdx.x * BJ_WARPS + warp, nw = (u64)gridDim.x * BJ_WARPS;
+    const u32 nbig = info[0];
+    u64       my_cnt = 0, my_cks = 0;
+    for (u32 q = 0; q < nbig; q++) {
+        const u32 b  = list[q];
+        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        const u64 len = s1 - s0, j0 = s0 + (len * gw) / nw, j1 = s0 + (len * (gw + 1)) / nw;
+        if (j0 == j1) continue;
+        for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;
+        __syncwarp();
+        for (u64 i = r0 + lane; i < r1; i += 32) {
+            const u64 x    = r[i];
+            const u32 slot = (u32)(x >> lo_shift) & mask;
+            atomicAdd(&t_cnt[slot], 1u);
+            atomicAdd(&t_sum[slot], smj_cks_a(x));
+        }
+        __syncwarp();
+        for (u64 j = j0 + lane; j < j1; j += 128) {
+            u64 y[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) y[u] = (j + 32 * u < j1) ? ld_stream(s + j + 32 * u) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (j + 32 * u < j1) {
+                    const u32 slot = (u32)(y[u] >> lo_shift) & mask;
+                    const u32 c    = t_cnt[slot];
+                    if (c) {
+                        my_cnt += c;
+                        my_cks += t_sum[slot] * smj_cks_b(y[u]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    my_cnt = warp_reduce_add(my_cnt);
+    my_cks = warp_reduce_add(my_cks);
+    if (lane == 0) {
+        if (my_cnt) atomicAdd(acc, my_cnt);
+        if (my_cks) atomicAdd(acc + 1, my_cks);
+    }
+}
+}  // namespace
+
 // m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
 // fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
 // do not suit it; the caller then takes the general sort + scan path.
@@ -554,14 +631,18 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
     const u32 nb2    = 512u * 512u;
     SmjScratch sc(ctx);
     u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
-    u64 *d_max = (u64 *)sc.get(48);  // [0] max bucket, [1] bucket counter, [2..5] exact OR/AND of R, S
-    if (!offR || !offS || !d_max) return smj_fail_msg("mway_msd: scratch allocation failed");
-    const u64 init[6] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d_max, init, 48, cudaMemcpyHostToDevice, ctx->stream));
+    constexpr u64 BIG = 1u << 16, RMAX = 1u << 16;  // bucket sizes: cooperative above BIG
+    u64 *d_max  = (u64 *)sc.get(64);  // [0] max bucket, [1] bucket counter, [2..5] exact OR/AND of R, S,
+                                      // [6] = {big count, unsupported flag}
+    u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4);
+    if (!offR || !offS || !d_max || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
+    const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d_max, init, 64, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = smj_msd_partition(ctx, r, nr, aR, bR, shift1, shift2, offR, d_max, d_max + 2))) return rc;
     if ((rc = smj_msd_partition(ctx, s, ns, aS, bS, shift1, shift2, offS, d_max, d_max + 4))) return rc;
-    u64 h[6];
-    SMJ_CHECK(cudaMemcpyAsync(h, d_max, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, offR, offS, nb2, BIG, RMAX, d_list, (u32 *)(d_max + 6));
+    u64 h[8];
+    SMJ_CHECK(cudaMemcpyAsync(h, d_max, 64, cudaMemcpyDeviceToHost, ctx->stream));
     t_part = t_sort = tm.mark();  // the in-partition sort is fused into the join kernel
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     {   // verify the sampled guess: no key bit outside [lo, hi] may vary in R or S
@@ -569,11 +650,14 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         const u32 range = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
         if ((xor_ & ~xand) & ~range) return 0;
     }
-    if (h[0] > (1ull << 20)) return 0;  // heavy hitters: one warp per bucket would crawl
+    const u32 nbig = (u32)(h[6] & 0xffffffffu), unsupported = (u32)(h[6] >> 32);
+    if (unsupported) return 0;  // a key that is heavy in R and in S: general path
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        SMJ_CHECK(cudaFuncSetAttribute(k_big_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         smem_set = smem;
     }
@@ -581,7 +665,10 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
     SMJ_ITEMS(ctx, nr + ns);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS, offS, nb2,
-               lo_shift, lbits, d_next, acc);
+               lo_shift, lbits, BIG, d_next, acc);
+    if (nbig)
+        SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS,
+                   offS, d_list, (u32 *)(d_max + 6), lo_shift, lbits, acc);
     t_join = tm.mark();
     *used  = 1;
     return 0;

@@ -5,6 +5,7 @@
 //   * LSD one-sweep radix passes over the varying bits      (smj_radix.cu, any distribution)
 //   * MSD range partition + in-shared-memory segment sort   (smj_segsort.cu, when segments fit)
 #include "smj_common.cuh"
+#include <algorithm>
 #include "../../include/smj_device.h"
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
@@ -73,6 +74,111 @@ extern "C" int smjdev_sort_int32(int32_t *data, uint64_t n) {
     SMJ_LAUNCH(ctx, k_narrow_i32, grid, 256, 0, res, n, d32);
     if (!on_device)
         SMJ_CHECK(cudaMemcpyAsync(data, d32, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-side verification helpers (full-size property tests: the arrays never leave HBM).
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_check_order(const u64 *__restrict__ x, u64 n, int key_only,
+                                                     u64 *__restrict__ out /* inv, sum, xor */) {
+    u64       inv = 0, sum = 0, xr = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 v = x[i];
+        sum += v;
+        xr ^= v;
+        if (i > 0) {
+            const u64 p = x[i - 1];
+            inv += key_only ? ((v >> 32) < (p >> 32)) : (v < p);
+        }
+    }
+    inv = warp_reduce_add(inv);
+    sum = warp_reduce_add(sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xr ^= __shfl_xor_sync(SMJ_FULL_MASK, xr, o);
+    if (lane_id() == 0) {
+        atomicAdd(out, inv);
+        atomicAdd(out + 1, sum);
+        atomicXor(out + 2, xr);
+    }
+}
+
+// every slot of a partitioned output: does the item belong to the partition that owns the slot,
+// and (stable scatter of rows whose payload is the row number) do payloads ascend inside it?
+__global__ void __launch_bounds__(256) k_check_partition(const u64 *__restrict__ x,
+                                                         const u64 *__restrict__ offs,
+                                                         const u64 *__restrict__ hist, u32 fanout,
+                                                         u64 used, DigitFn fn,
+                                                         u64 *__restrict__ out /* misplaced, unstable, items, sum */) {
+    u64       bad = 0, unst = 0, cnt = 0, sum = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < used; i += stride) {
+        u32 lo = 0, hi = fanout;  // last partition with offs <= i
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (offs[mid] <= i)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        if (i >= offs[lo] + hist[lo]) continue;  // padding slot
+        const u64 v = x[i];
+        cnt++;
+        sum += v;
+        bad += fn(v) != lo;
+        if (i > offs[lo]) unst += (u32)v <= (u32)x[i - 1];
+    }
+    bad  = warp_reduce_add(bad);
+    unst = warp_reduce_add(unst);
+    cnt  = warp_reduce_add(cnt);
+    sum  = warp_reduce_add(sum);
+    if (lane_id() == 0) {
+        atomicAdd(out, bad);
+        atomicAdd(out + 1, unst);
+        atomicAdd(out + 2, cnt);
+        atomicAdd(out + 3, sum);
+    }
+}
+}  // namespace
+
+// stats (host, 3 x u64): number of descents, sum of the items mod 2^64, xor of the items
+extern "C" int smjdev_check_order(const uint64_t *items, uint64_t n, int key_only, uint64_t *stats) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    SmjScratch sc(ctx);
+    u64 *d = (u64 *)sc.get(24);
+    if (!d) return smj_fail_msg("smjdev_check_order: scratch");
+    SMJ_CHECK(cudaMemsetAsync(d, 0, 24, ctx->stream));
+    if (n) {
+        const unsigned grid = (unsigned)std::min<u64>(div_up(n, 256), (u64)ctx->sm_count * 16);
+        SMJ_LAUNCH(ctx, k_check_order, grid, 256, 0, (const u64 *)items, n, key_only, d);
+    }
+    SMJ_CHECK(cudaMemcpyAsync(stats, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// stats (host, 4 x u64): items in a wrong partition, payload descents inside partitions, items
+// found, sum of the items mod 2^64.  offs/hist: device arrays as written by smjdev_partition.
+extern "C" int smjdev_check_partition(const uint64_t *out, const uint64_t *offs, const uint64_t *hist,
+                                      uint32_t nbits, uint32_t shift, int key_minus_one,
+                                      uint64_t used, uint64_t *stats) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    SmjScratch sc(ctx);
+    u64 *d = (u64 *)sc.get(32);
+    if (!d) return smj_fail_msg("smjdev_check_partition: scratch");
+    SMJ_CHECK(cudaMemsetAsync(d, 0, 32, ctx->stream));
+    DigitFn fn = {key_minus_one ? (1ull << 32) : 0ull, 32 + shift, (1u << nbits) - 1};
+    if (used) {
+        const unsigned grid = (unsigned)std::min<u64>(div_up(used, 256), (u64)ctx->sm_count * 16);
+        SMJ_LAUNCH(ctx, k_check_partition, grid, 256, 0, (const u64 *)out, (const u64 *)offs,
+                   (const u64 *)hist, 1u << nbits, used, fn, d);
+    }
+    SMJ_CHECK(cudaMemcpyAsync(stats, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -225,13 +225,22 @@ def run_single_gpu(args, smj) -> dict:
     prof = parse_profile(buf.value.decode())
     total_kernel_ms = sum(p["ms"] for p in prof.values()) or 1.0
     top = max(prof, key=lambda k: prof[k]["ms"])
-    bytes_per_item = {"k_onesweep": 16, "k_segsort": 16, "k_mj_tile": 8, "k_hist_digits": 8,
-                      "k_bits_reduce": 8, "k_msd": 16}
+    bytes_per_item = {"k_onesweep": 16, "k_msd_scatter2": 16, "k_msd_hist2": 8, "k_bucket_join": 8,
+                      "k_mj_tile": 8, "k_hist_digits": 8, "k_bits_reduce": 8}
     bpi = next((v for k, v in bytes_per_item.items() if k in top), 16)
     peak, peak_src = measured_peak()
     achieved = bpi * prof[top]["items"] / (prof[top]["ms"] * 1e-3) / 1e9 if prof[top]["ms"] else 0.0
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        for kname, rec in tj.get("kernels", {}).items():
+            if kname in top and rec.get("items"):
+                traffic = rec["dram_bytes_per_launch"] * (prof[top]["items"] / prof[top]["launches"]) / rec["items"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_item": bpi, "launches": prof[top]["launches"],
                 "avg_launch_ms": prof[top]["ms"] / max(prof[top]["launches"], 1),
                 "share_of_step": prof[top]["ms"] / total_kernel_ms,
@@ -250,10 +259,15 @@ def run_single_gpu(args, smj) -> dict:
     libc = C.CDLL(None)
     libc.free.argtypes = [C.c_void_p]
 
+    h2d_ms = []
+
     def host_join():
         res = lib.sortmergejoin_multiway(C.byref(relr), C.byref(rels), C.byref(cfg))
         assert res, "sortmergejoin_multiway failed: " + lib.smjdev_last_error().decode()
         total = res.contents.totalresults
+        hst = smj.smj_join_stats_t()
+        lib.smj_last_join_stats(C.byref(hst))
+        h2d_ms.append(hst.ms_h2d)
         libc.free(C.cast(res.contents.resultlist, C.c_void_p))
         libc.free(C.cast(res, C.c_void_p))
         return total
@@ -267,6 +281,7 @@ def run_single_gpu(args, smj) -> dict:
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e = {"value": 2 * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8,
            "d2h_bytes_per_step": 16, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "h2d_ms_per_step": sum(h2d_ms[-e2e_steps:]) / e2e_steps,
            "api": "sortmergejoin_multiway(relation_t*, relation_t*, joinconfig_t*) with pinned host buffers"}
 
     # ---- CPU baseline: the reference's own m-way join on this box's host cores

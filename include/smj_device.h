@@ -145,6 +145,20 @@ int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uin
 int smjdev_range_partition(const uint64_t *in, uint64_t *out, uint64_t n,
                            const uint32_t *splitters, uint32_t nparts, uint64_t *counts);
 
+/* ------------------------------------------------------------------ verification ----- */
+/* Device-side property checks for arrays that are too large to bring back to the host.
+ * check_order: stats[0] = number of positions i with items[i] < items[i-1] (whole word, or key
+ * only), stats[1] = sum of the items mod 2^64, stats[2] = xor of the items (multiset
+ * fingerprints: equal before and after a sort).
+ * check_partition: for the output of smjdev_partition (offs/hist device arrays, `used` = slots in
+ * use): stats[0] = items whose bucket is not the partition that holds them, stats[1] = payload
+ * descents inside partitions (0 for a stable scatter of rows numbered by payload), stats[2] =
+ * items found, stats[3] = their sum mod 2^64. */
+int smjdev_check_order(const uint64_t *items, uint64_t n, int key_only, uint64_t *stats);
+int smjdev_check_partition(const uint64_t *out, const uint64_t *offs, const uint64_t *hist,
+                           uint32_t nbits, uint32_t shift, int key_minus_one, uint64_t used,
+                           uint64_t *stats);
+
 /* ------------------------------------------------------------------ data generators -- */
 /* Deterministic on-device relation generators (replace src/datagen/generator.c:83-93, 234-350
  * and :458-488 for the benchmark workloads; the reference's own are seeded from time()).
