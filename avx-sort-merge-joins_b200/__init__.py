@@ -109,6 +109,14 @@ SIGNATURES = {
                               C.POINTER(smj_join_stats_t)]),
     "smjdev_range_partition": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32,
                                          _vp]),
+    "smjdev_range_count": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, _vp]),
+    "smjdev_range_scatter": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(_vp),
+                                       _u64p]),
+    "smjdev_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "smjdev_ipc_free": (C.c_int, [_vp]),
+    "smjdev_ipc_export": (C.c_int, [_vp, C.c_char_p]),
+    "smjdev_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "smjdev_ipc_close": (C.c_int, [_vp]),
     "smjdev_check_order": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
     "smjdev_check_partition": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                          _u64p]),

@@ -1180,3 +1180,58 @@ int smj_key_bits(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *h
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// Fused range partition + exchange: the scatter kernel stores every item straight into the
+// receive buffer of the GPU that owns its key range.  dest_ptrs[d] may be a peer GPU's buffer
+// (CUDA IPC mapping over NVLink) or a local one; dest_offsets[d] is where this rank's slice
+// starts inside it (computed by the caller from the all-gathered count matrix).  The order of
+// items inside a destination is irrelevant (the receiver partitions/sorts them anyway), so this
+// is the unstable kernel with one cursor per destination holding an ABSOLUTE item index
+// (address / 8): no pack buffer, no separate copy kernel, the transfer overlaps the partitioning
+// tile by tile.
+// ---------------------------------------------------------------------------------------
+extern "C" int smjdev_range_count(const uint64_t *in, uint64_t n, const uint32_t *splitters,
+                                  uint32_t nparts, uint64_t *counts) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (nparts < 1 || nparts > 32) return smj_fail_msg("smjdev_range_count: 1..32 parts");
+    SplitFn fn;
+    fn.nparts = nparts;
+    for (u32 i = 0; i < 31; i++) fn.sp[i] = (i + 1 < nparts) ? splitters[i] : 0xffffffffu;
+    SmjScratch sc(ctx);
+    u64 *d_hist = (u64 *)sc.get(RADIX_NB * 8);
+    if (!d_hist) return smj_fail_msg("smjdev_range_count: scratch");
+    SMJ_CHECK(cudaMemsetAsync(d_hist, 0, RADIX_NB * 8, ctx->stream));
+    if (n) {
+        SMJ_ITEMS(ctx, n);
+        SMJ_LAUNCH(ctx, k_hist_fn<SplitFn>, hist_grid(ctx, n, 512, 8), 512, 0, (const u64 *)in, n, fn,
+                   d_hist);
+    }
+    SMJ_CHECK(cudaMemcpyAsync(counts, d_hist, (size_t)nparts * 8, cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    return 0;
+}
+
+extern "C" int smjdev_range_scatter(const uint64_t *in, uint64_t n, const uint32_t *splitters,
+                                    uint32_t nparts, uint64_t *const *dest_ptrs,
+                                    const uint64_t *dest_offsets) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (nparts < 1 || nparts > 32) return smj_fail_msg("smjdev_range_scatter: 1..32 parts");
+    if (n == 0) return 0;
+    SplitFn fn;
+    fn.nparts = nparts;
+    for (u32 i = 0; i < 31; i++) fn.sp[i] = (i + 1 < nparts) ? splitters[i] : 0xffffffffu;
+    u64 h_cur[RADIX_NB];
+    memset(h_cur, 0, sizeof(h_cur));
+    for (u32 d = 0; d < nparts; d++) {
+        if ((uintptr_t)dest_ptrs[d] & 7) return smj_fail_msg("smjdev_range_scatter: unaligned buffer");
+        h_cur[d] = (u64)((uintptr_t)dest_ptrs[d] >> 3) + dest_offsets[d];
+    }
+    SmjScratch sc(ctx);
+    u64 *d_cur = (u64 *)sc.get(RADIX_NB * 8);
+    if (!d_cur) return smj_fail_msg("smjdev_range_scatter: scratch");
+    SMJ_CHECK(cudaMemcpyAsync(d_cur, h_cur, RADIX_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_unstable<8>(ctx, (const u64 *)in, (u64 *)nullptr, n, fn, d_cur);
+}

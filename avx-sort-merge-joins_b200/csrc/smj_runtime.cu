@@ -283,3 +283,36 @@ int smjdev_event_destroy(void *ev) {
 }
 
 }  // extern "C"
+
+// ---- buffers other processes (one per GPU) can map: CUDA IPC over NVLink / NVSwitch
+extern "C" {
+int smjdev_ipc_alloc(size_t bytes, void **dptr) {
+    if (!smj_ctx()) return -1;
+    if (bytes == 0) bytes = 16;
+    SMJ_CHECK(cudaMalloc(dptr, bytes));  // pool (cudaMallocAsync) memory cannot be exported
+    return 0;
+}
+int smjdev_ipc_free(void *dptr) {
+    if (dptr) SMJ_CHECK(cudaFree(dptr));
+    return 0;
+}
+int smjdev_ipc_export(void *dptr, unsigned char *handle64) {
+    if (!smj_ctx()) return -1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    SMJ_CHECK(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int smjdev_ipc_open(const unsigned char *handle64, void **peer_ptr) {
+    if (!smj_ctx()) return -1;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SMJ_CHECK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int smjdev_ipc_close(void *peer_ptr) {
+    if (peer_ptr) SMJ_CHECK(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+}

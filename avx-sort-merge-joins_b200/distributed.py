@@ -74,6 +74,62 @@ class CudaEngine:
         return torch.from_numpy(vals).to(self.device)
 
 
+def p2p_layout(counts: np.ndarray, rank: int):
+    """counts[src][rel][dst] = items rank `src` sends to rank `dst` for relation `rel` (the
+    all-gathered count matrix).  Returns (offs, recv): offs[rel][dst] = where this rank's slice
+    starts in dst's receive buffer of relation rel (slices are laid out in source-rank order),
+    recv[rel] = number of items this rank receives."""
+    counts = np.asarray(counts, dtype=np.int64)
+    offs = counts[:rank].sum(axis=0)          # [rel][dst]: everything lower ranks send there
+    recv = counts[:, :, rank].sum(axis=0)     # [rel]
+    return offs, recv
+
+
+class P2PExchange:
+    """Receive buffers for R and S on every GPU, mapped into every process with CUDA IPC.  With it
+    DistributedJoin.step_p2p partitions and exchanges in ONE kernel per relation: the scatter
+    stores each item directly into the receive buffer of its destination GPU over NVLink."""
+
+    def __init__(self, engine: "CudaEngine", rank: int, world: int, capacity_r: int, capacity_s: int):
+        self.e, self.rank, self.world = engine, rank, world
+        lib, smj = engine.lib, engine.smj
+        self.cap = [int(capacity_r), int(capacity_s)]
+        self.local, handles = [], []
+        for cap in self.cap:
+            p = C.c_void_p()
+            smj.check(lib.smjdev_ipc_alloc(max(cap, 1) * 8, C.byref(p)), "ipc_alloc")
+            h = C.create_string_buffer(64)
+            smj.check(lib.smjdev_ipc_export(p, h), "ipc_export")
+            self.local.append(p.value)
+            handles.append(np.frombuffer(h.raw, dtype=np.uint8).copy())
+        mine = torch.from_numpy(np.concatenate(handles)).to(engine.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        self.ptrs = [[0] * world for _ in range(2)]  # [rel][rank] -> pointer usable in THIS process
+        self.opened = []
+        for g in range(world):
+            raw = allh[g].cpu().numpy().tobytes()
+            for rel in range(2):
+                if g == rank:
+                    self.ptrs[rel][g] = self.local[rel]
+                else:
+                    q = C.c_void_p()
+                    smj.check(lib.smjdev_ipc_open(raw[64 * rel:64 * rel + 64], C.byref(q)), "ipc_open")
+                    self.ptrs[rel][g] = q.value
+                    self.opened.append(q.value)
+        dist.barrier()
+
+    def close(self):
+        lib = self.e.lib
+        dist.barrier()
+        for q in self.opened:
+            lib.smjdev_ipc_close(q)
+        dist.barrier()
+        for p in self.local:
+            lib.smjdev_ipc_free(p)
+        self.opened, self.local = [], []
+
+
 def uniform_splitters(maxkey: int, nparts: int) -> np.ndarray:
     """Equal-width key ranges for dense keys 1..maxkey: dest(key) = #splitters <= key."""
     return np.array([(i * maxkey) // nparts + 1 for i in range(1, nparts)], dtype=np.uint32)
@@ -115,6 +171,38 @@ class DistributedJoin:
         dist.all_to_all_single(out[:n_recv], part[:sum(send)], output_split_sizes=recv,
                                input_split_sizes=send)
         return out, n_recv, send, recv
+
+    def step_p2p(self, r, nr: int, s, ns: int, splitters: np.ndarray, px: "P2PExchange"):
+        """Same result as step(), but partition + exchange are fused: count per destination,
+        all-gather the counts, then one scatter kernel per relation writes straight into the peers'
+        receive buffers (no send buffer, no NCCL data collective)."""
+        e, lib, smj, W = self.e, self.e.lib, self.e.smj, self.world
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        spp = sp.ctypes.data_as(C.POINTER(C.c_uint32))
+        cnt = torch.zeros(2, W, dtype=torch.int64, device=e.device)
+        smj.check(lib.smjdev_range_count(r.data_ptr(), nr, spp, W, cnt[0].data_ptr()), "range_count")
+        smj.check(lib.smjdev_range_count(s.data_ptr(), ns, spp, W, cnt[1].data_ptr()), "range_count")
+        allc = [torch.empty_like(cnt) for _ in range(W)]
+        dist.all_gather(allc, cnt)
+        counts = torch.stack(allc).cpu().numpy()  # [src][rel][dst]; the copy synchronises
+        offs, recv = p2p_layout(counts, self.rank)
+        for rel in range(2):
+            if int(recv[rel]) > px.cap[rel]:
+                raise RuntimeError(f"receive buffer too small: {int(recv[rel])} > {px.cap[rel]}")
+        for rel, (t, n) in enumerate(((r, nr), (s, ns))):
+            dptr = (C.c_void_p * W)(*px.ptrs[rel])
+            doff = (C.c_uint64 * W)(*[int(x) for x in offs[rel]])
+            smj.check(lib.smjdev_range_scatter(t.data_ptr(), n, spp, W, dptr, doff), "range_scatter")
+        torch.cuda.current_stream().synchronize()  # my stores have left
+        dist.barrier()                              # ... and so have everybody else's
+        st = smj.smj_join_stats_t()
+        smj.check(lib.smjdev_join(smj.ALGO_MWAY, px.local[0], int(recv[0]), px.local[1], int(recv[1]), 1,
+                                  C.byref(st)), "smjdev_join")
+        res = e.result_tensor(st.matches, st.checksum)
+        dist.all_reduce(res, op=dist.ReduceOp.SUM)  # also keeps anyone from scattering into a buffer in use
+        out = res.cpu().numpy().view(np.uint64)
+        sent = 8 * int(counts[self.rank].sum() - counts[self.rank, :, self.rank].sum())
+        return int(out[0]), int(out[1]), sent
 
     def step(self, r, nr: int, s, ns: int, splitters: np.ndarray):
         """One complete distributed join of the local slices; returns the GLOBAL (count, checksum)

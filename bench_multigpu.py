@@ -35,13 +35,25 @@ def run(args, smj):
     s = eng.gen_unique(n, first, count, B.SEED_S)
     splitters = dj_mod.uniform_splitters(n, world)  # keys are a permutation of 1..n
 
+    # fused partition + exchange over peer memory (default); SMJ_EXCHANGE=nccl uses the all-to-all
+    use_p2p = os.environ.get("SMJ_EXCHANGE", "p2p") != "nccl"
+    px = None
+    if use_p2p:
+        cap = int(count * 1.25) + 65536
+        px = dj_mod.P2PExchange(eng, rank, world, cap, cap)
+
+    def one_step(rr, ss):
+        if use_p2p:
+            return dj.step_p2p(rr, count, ss, count, splitters, px)
+        return dj.step(rr, count, ss, count, splitters)
+
     def sync_all():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        cnt, cks, sent = dj.step(r, count, s, count, splitters)
+        cnt, cks, sent = one_step(r, s)
     assert cnt == n, f"rank {rank}: distributed join returned {cnt}, expected {n}"
 
     sampler = B.ClockSampler(local) if rank == 0 else None
@@ -50,7 +62,7 @@ def run(args, smj):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        cnt, cks, sent = dj.step(r, count, s, count, splitters)
+        cnt, cks, sent = one_step(r, s)
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -73,7 +85,7 @@ def run(args, smj):
     for _ in range(e2e_steps):
         dr = hr.to(dev, non_blocking=True)
         ds = hs.to(dev, non_blocking=True)
-        c2, _, _ = dj.step(dr, count, ds, count, splitters)
+        c2, _, _ = one_step(dr, ds)
         assert c2 == n
     sync_all()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
@@ -90,8 +102,10 @@ def run(args, smj):
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"sortmergejoins -a m-way, |R|=|S|={n} 8-byte tuples, uniform unique keys "
                                    f"(BASELINE.json configs[0]), relations spread evenly over {world} GPUs",
-                       "parallelism": f"range partition by key + NCCL all-to-all over {world} GPUs, local m-way join, "
-                                      f"all-reduce of count/checksum",
+                       "parallelism": (f"range partition fused with the exchange (scatter kernel stores into peer receive "
+                                       f"buffers over NVLink, CUDA IPC) over {world} GPUs" if use_p2p else
+                                       f"range partition by key + NCCL all-to-all over {world} GPUs")
+                                      + ", local m-way join, all-reduce of count/checksum",
                        "l2": "per-rank inputs (2 x %.2f GB) are larger than L2" % (count * 8 / 1e9),
                        "timing": "CUDA events on the stream shared with NCCL, max over ranks",
                        "exchange_bytes_sent_per_rank": sent},
@@ -107,6 +121,8 @@ def run(args, smj):
                          "nvlink_gbs_sent_per_gpu_over_step": link_gbs},
             "cpu_baseline": None, "matches": cnt, "checksum": cks,
         }
+    if px is not None:
+        px.close()
     dist.barrier()
     dist.destroy_process_group()
     return line

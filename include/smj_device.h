@@ -145,6 +145,24 @@ int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uin
 int smjdev_range_partition(const uint64_t *in, uint64_t *out, uint64_t n,
                            const uint32_t *splitters, uint32_t nparts, uint64_t *counts);
 
+/* Fused range partition + exchange (one process per GPU): smjdev_range_count gives the number
+ * of items per destination (device array of nparts uint64); after the ranks have exchanged their
+ * counts, smjdev_range_scatter stores every item straight into the receive buffer of the GPU
+ * that owns its key range.  dest_ptrs (HOST array of nparts device pointers) may point into peer
+ * GPUs' memory mapped with smjdev_ipc_open (stores travel over NVLink); dest_offsets (HOST array)
+ * is where this rank's slice starts inside each buffer, in items.  Order inside a destination is
+ * unspecified.  The caller synchronises all ranks before reading the receive buffers. */
+int smjdev_range_count(const uint64_t *in, uint64_t n, const uint32_t *splitters, uint32_t nparts,
+                       uint64_t *counts);
+int smjdev_range_scatter(const uint64_t *in, uint64_t n, const uint32_t *splitters, uint32_t nparts,
+                         uint64_t *const *dest_ptrs, const uint64_t *dest_offsets);
+/* device buffers that other processes can map (cudaMalloc + CUDA IPC handles, 64 bytes each) */
+int smjdev_ipc_alloc(size_t bytes, void **dptr);
+int smjdev_ipc_free(void *dptr);
+int smjdev_ipc_export(void *dptr, unsigned char *handle64);
+int smjdev_ipc_open(const unsigned char *handle64, void **peer_ptr);
+int smjdev_ipc_close(void *peer_ptr);
+
 /* ------------------------------------------------------------------ verification ----- */
 /* Device-side property checks for arrays that are too large to bring back to the host.
  * check_order: stats[0] = number of positions i with items[i] < items[i-1] (whole word, or key

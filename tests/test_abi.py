@@ -105,3 +105,20 @@ def test_no_cpu_fallback(smj, capfd):
     assert np.array_equal(a, items), "nothing may be computed on the CPU"
     total, _ = smj.join_host("multiway", items, items, nthreads=2)
     assert total is None
+
+
+def test_p2p_layout():
+    """offsets of the fused partition + exchange: slices land in source-rank order, no overlap."""
+    import importlib
+    dj = importlib.import_module("avx-sort-merge-joins_b200.distributed")
+    rng = np.random.default_rng(3)
+    W = 4
+    counts = rng.integers(0, 1000, size=(W, 2, W))  # [src][rel][dst]
+    layouts = [dj.p2p_layout(counts, g) for g in range(W)]
+    for rel in range(2):
+        for dst in range(W):
+            pos = 0
+            for src in range(W):
+                assert layouts[src][0][rel][dst] == pos
+                pos += counts[src][rel][dst]
+            assert layouts[dst][1][rel] == pos
