@@ -26,36 +26,38 @@ constexpr int RADIX_NB = 512;  // stride of every per-digit table; a pass uses 2
 // OR / AND of all items: tells which bit positions vary at all (constant bits need no pass)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bits_reduce(const u64 *__restrict__ in, u64 n,
-                                                     u64 *__restrict__ out /* [0]=OR [1]=AND */) {
-    u64 vor = 0, vand = ~0ull;
+                                                     u64 *__restrict__ out /* [0]=OR [1]=AND [2]=order flags */) {
+    // order flags: bit 0 = some item is smaller than its predecessor (whole word), bit 1 = some
+    // payload (low 32 bits) is smaller than its predecessor's.  An input whose payloads already
+    // ascend needs no payload passes: a stable sort on the key alone gives the whole-word order.
+    u64 vor = 0, vand = ~0ull, flags = 0;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    u64       i      = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        u64 a = ld_stream(in + i), b = ld_stream(in + i + stride);
-        u64 c = ld_stream(in + i + 2 * stride), d = ld_stream(in + i + 3 * stride);
-        vor |= (a | b) | (c | d);
-        vand &= (a & b) & (c & d);
-    }
-    for (; i < n; i += stride) {
-        u64 a = ld_stream(in + i);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 a = ld_stream(in + i);
+        const u64 p = i ? in[i - 1] : 0ull;  // the neighbour's load: same sector, served by L1/L2
         vor |= a;
         vand &= a;
+        flags |= (a < p ? 1ull : 0ull) | ((u32)a < (u32)p ? 2ull : 0ull);
     }
-    vor  = warp_reduce_or(vor);
-    vand = warp_reduce_and(vand);
-    __shared__ u64 s_or[8], s_and[8];
+    vor   = warp_reduce_or(vor);
+    vand  = warp_reduce_and(vand);
+    flags = warp_reduce_or(flags);
+    __shared__ u64 s_or[8], s_and[8], s_fl[8];
     if (lane_id() == 0) {
         s_or[threadIdx.x >> 5]  = vor;
         s_and[threadIdx.x >> 5] = vand;
+        s_fl[threadIdx.x >> 5]  = flags;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; w++) {
             vor |= s_or[w];
             vand &= s_and[w];
+            flags |= s_fl[w];
         }
         atomicOr(out, vor);
         atomicAnd(out + 1, vand);
+        if (flags) atomicOr(out + 2, flags);
     }
 }
 
@@ -630,10 +632,8 @@ int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *base
     return 0;
 }
 
-// Tile shapes (SMJ_OS_CFG selects one; default 1).  Wide digits want big tiles: with 512 bins a
-// 4096-item tile has only 8 items per bin to amortise the per-bin scan and look-back over.
-//   0: 256 threads x 16 items, 4 CTAs/SM    1: 512 x 16, 2 CTAs/SM
-//   2: 256 x 24, 3 CTAs/SM                  3: 384 x 16, 2 CTAs/SM
+// Wide digits want big tiles: with 512 bins a 4096-item tile has only 8 items per bin to amortise
+// the per-bin scan and look-back over.
 constexpr int OS_MIN_TILE = 4096;
 
 inline size_t status_bytes(u64 n) {
@@ -669,28 +669,14 @@ inline int rank_mode() {
     static int mode = env_int("SMJ_RANK_MODE", 1);
     return mode;
 }
-inline int os_cfg() {
-    static int cfg = env_int("SMJ_OS_CFG", 1);
-    return cfg;
-}
 
 template <int BITS, int RANK, class F>
 int launch_onesweep_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64 *bases,
                           u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
-    switch (os_cfg()) {
-        case 0:
-            return launch_onesweep_cfg<256, 16, BITS, F, RANK, 4>(ctx, in, out, n, fn, bases, status,
-                                                                  counter, fn_full, padshift);
-        case 2:
-            return launch_onesweep_cfg<256, 24, BITS, F, RANK, 3>(ctx, in, out, n, fn, bases, status,
-                                                                  counter, fn_full, padshift);
-        case 3:
-            return launch_onesweep_cfg<384, 16, BITS, F, RANK, 2>(ctx, in, out, n, fn, bases, status,
-                                                                  counter, fn_full, padshift);
-        default:
-            return launch_onesweep_cfg<512, 16, BITS, F, RANK, 2>(ctx, in, out, n, fn, bases, status,
-                                                                  counter, fn_full, padshift);
-    }
+    // 512 threads x 16 items, 2 CTAs/SM: the best of the four shapes measured in round 1
+    // (256x16x4: 1.25 ms, 256x24x3: 1.06 ms, 384x16x2: 1.19 ms, 512x16x2: 0.89 ms per 128M-item pass)
+    return launch_onesweep_cfg<512, 16, BITS, F, RANK, 2>(ctx, in, out, n, fn, bases, status, counter,
+                                                          fn_full, padshift);
 }
 
 template <class F>
@@ -747,17 +733,19 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
     const u64 *buf = in;
     if (n <= 1) return 0;
     SmjScratch sc(ctx);
-    u64 *d_bits = (u64 *)sc.get(16);
+    u64 *d_bits = (u64 *)sc.get(24);
     if (!d_bits) return smj_fail_msg("smj_lsd_sort: scratch allocation failed");
-    const u64 init[2] = {0ull, ~0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d_bits, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    const u64 init[3] = {0ull, ~0ull, 0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d_bits, init, 24, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, n, 256, 16), 256, 0, buf, n, d_bits);
-    u64 h_bits[2];
-    SMJ_CHECK(cudaMemcpyAsync(h_bits, d_bits, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    u64 h_bits[3];
+    SMJ_CHECK(cudaMemcpyAsync(h_bits, d_bits, 24, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     u64 varying = h_bits[0] & ~h_bits[1];
-    if (key_only) varying &= 0xffffffff00000000ull;
+    if (!key_only && !(h_bits[2] & 1)) return 0;  // already in whole-word order
+    // payloads already ascend in input order (e.g. row numbers): the stable key passes suffice
+    if (key_only || !(h_bits[2] & 2)) varying &= 0xffffffff00000000ull;
 
     // plan: cover the varying bits, least significant first.  Bits that are closer than 9
     // positions form a group; a group of span s takes ceil(s/9) passes of equal width (27 key
@@ -1164,20 +1152,22 @@ int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns
 // OR / AND of all items of two relations: host[0..1] = R, host[2..3] = S.  Synchronises.
 int smj_key_bits(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *host) {
     SmjScratch sc(ctx);
-    u64 *d = (u64 *)sc.get(32);
+    u64 *d = (u64 *)sc.get(48);
     if (!d) return smj_fail_msg("smj_key_bits: scratch allocation failed");
-    const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d, init, 32, cudaMemcpyHostToDevice, ctx->stream));
+    const u64 init[6] = {0ull, ~0ull, 0ull, 0ull, ~0ull, 0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d, init, 48, cudaMemcpyHostToDevice, ctx->stream));
     if (nr) {
         SMJ_ITEMS(ctx, nr);
         SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, nr, 256, 16), 256, 0, r, nr, d);
     }
     if (ns) {
         SMJ_ITEMS(ctx, ns);
-        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, ns, 256, 16), 256, 0, s, ns, d + 2);
+        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, ns, 256, 16), 256, 0, s, ns, d + 3);
     }
-    SMJ_CHECK(cudaMemcpyAsync(host, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    u64 h[6];
+    SMJ_CHECK(cudaMemcpyAsync(h, d, 48, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    host[0] = h[0], host[1] = h[1], host[2] = h[3], host[3] = h[4];
     return 0;
 }
 
