@@ -953,6 +953,40 @@ namespace {
 
 constexpr int MSD_THREADS = 512, MSD_IPT = 16, MSD_TILE = MSD_THREADS * MSD_IPT, MSD_NB = 512;
 
+// histogram of ONE 9-bit digit + exact OR / AND of the items (first pass of the MSD partition)
+__global__ void __launch_bounds__(512) k_msd_hist1(const u64 *__restrict__ in, u64 n, FieldFn fn,
+                                                   u64 *__restrict__ hist, u64 *__restrict__ bits) {
+    __shared__ u32 sh[MSD_NB];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    u64       vor = 0, vand = ~0ull;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 8 * stride) {
+        u64 x[8];  // eight independent loads in flight per thread
+#pragma unroll
+        for (int u = 0; u < 8; u++) x[u] = (i + u * stride < n) ? ld_stream(in + i + u * stride) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i + u * stride < n) {
+                vor |= x[u];
+                vand &= x[u];
+                atomicAdd(&sh[fn(x[u])], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    const u32 c = sh[threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], (u64)c);
+    if (bits) {
+        vor  = warp_reduce_or(vor);
+        vand = warp_reduce_and(vand);
+        if (lane_id() == 0) {
+            atomicOr(bits, vor);
+            atomicAnd(bits + 1, vand);
+        }
+    }
+}
+
 // per pass-A bucket: first tile index and first item index (exclusive scans over the 512 buckets)
 __global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restrict__ hist1,
                                                             u64 *__restrict__ tile_prefix,
@@ -1103,12 +1137,9 @@ int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shi
         return smj_fail_msg("smj_msd_partition: scratch allocation failed");
     SMJ_CHECK(cudaMemsetAsync(d_hist1, 0, RADIX_NB * 8, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
-    DigitPlan plan;
-    plan.nd   = 1;
-    plan.d[0] = {0ull, shift1, (u32)MSD_NB - 1};
     FieldFn f1 = {shift1, (u32)MSD_NB - 1}, f2 = {shift2, (u32)MSD_NB - 1};
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, in, n, plan, d_hist1, exact_bits);
+    SMJ_LAUNCH(ctx, k_msd_hist1, hist_grid(ctx, n, 512, 16), 512, 0, in, n, f1, d_hist1, exact_bits);
     SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist1, d_bases1);
     SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_hist1, d_tpref, d_bstart);
     int rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1);  // consumes d_bases1
