@@ -532,6 +532,66 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
 }
 }  // namespace
 
+// Same join for 11..13 remaining key bits (key domains up to 2^31): the 2^L-slot table no longer
+// fits a warp's share of shared memory, so a whole CTA owns a bucket.
+__global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__ r,
+                                                         const u64 *__restrict__ roffs,
+                                                         const u64 *__restrict__ s,
+                                                         const u64 *__restrict__ soffs, u32 nbuckets,
+                                                         u32 lo_shift, u32 lbits, u32 *next_bucket,
+                                                         u64 *__restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 slots = 1u << lbits, mask = slots - 1;
+    u64 *t_sum = (u64 *)smem_raw;
+    u32 *t_cnt = (u32 *)(t_sum + slots);
+    __shared__ u32 s_b;
+    __shared__ u64 s_red[2][8];
+    u64 my_cnt = 0, my_cks = 0;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_b = atomicAdd(next_bucket, 1u);
+        __syncthreads();
+        const u32 b = s_b;
+        if (b >= nbuckets) break;
+        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        if (r0 == r1 || s0 == s1) continue;
+        for (u32 i = threadIdx.x; i < slots * 3 / 2; i += 256) ((u64 *)t_sum)[i] = 0;
+        __syncthreads();
+        for (u64 i = r0 + threadIdx.x; i < r1; i += 256) {
+            const u64 x    = ld_stream(r + i);
+            const u32 slot = (u32)(x >> lo_shift) & mask;
+            atomicAdd(&t_cnt[slot], 1u);
+            atomicAdd(&t_sum[slot], smj_cks_a(x));
+        }
+        __syncthreads();
+        for (u64 j = s0 + threadIdx.x; j < s1; j += 256) {
+            const u64 y    = ld_stream(s + j);
+            const u32 slot = (u32)(y >> lo_shift) & mask;
+            const u32 c    = t_cnt[slot];
+            if (c) {
+                my_cnt += c;
+                my_cks += t_sum[slot] * smj_cks_b(y);
+            }
+        }
+    }
+    my_cnt = warp_reduce_add(my_cnt);
+    my_cks = warp_reduce_add(my_cks);
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5] = my_cnt;
+        s_red[1][threadIdx.x >> 5] = my_cks;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 c = 0, x = 0;
+        for (int w = 0; w < 8; w++) {
+            c += s_red[0][w];
+            x += s_red[1][w];
+        }
+        if (c) atomicAdd(acc, c);
+        if (x) atomicAdd(acc + 1, x);
+    }
+}
+
 // ---- heavy hitters (Zipf-skewed S): buckets with more than `big` tuples on either side are
 // listed by k_collect_big and joined by ALL warps of the grid together: every warp builds the
 // (small) R table of the bucket and takes an equal slice of its S side.
@@ -625,7 +685,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
     const u32 v   = vor & ~vand;
     if (v == 0) return 0;
     const int hi = 31 - __builtin_clz(v), lo = __builtin_ctz(v), k = hi - lo + 1;
-    if (k < 19 || k > 28) return 0;
+    if (k < 19 || k > 31) return 0;
     const u32 lbits  = (u32)(k - 18);
     const u32 shift1 = 32 + (u32)hi - 8, shift2 = shift1 - 9, lo_shift = 32 + (u32)lo;
     const u32 nb2    = 512u * 512u;
@@ -651,6 +711,25 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         if ((xor_ & ~xand) & ~range) return 0;
     }
     const u32 nbig = (u32)(h[6] & 0xffffffffu), unsupported = (u32)(h[6] >> 32);
+    u32 *d_next = (u32 *)(d_max + 1);  // zeroed above
+    if (lbits > 10) {
+        // wide key domains (up to 2^31): one CTA per bucket, no cooperative heavy-hitter kernel
+        if (nbig) return 0;
+        const size_t smem = (size_t)(1u << lbits) * 12;
+        static size_t smem_set_cta = 0;
+        if (smem > smem_set_cta) {
+            SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+            smem_set_cta = smem;
+        }
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / smem));
+        SMJ_ITEMS(ctx, nr + ns);
+        SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, bR, offR, bS, offS, nb2,
+                   lo_shift, lbits, d_next, acc);
+        t_join = tm.mark();
+        *used  = 1;
+        return 0;
+    }
     if (unsupported) return 0;  // a key that is heavy in R and in S: general path
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
     static size_t smem_set = 0;
@@ -661,7 +740,6 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
                                        (int)smem));
         smem_set = smem;
     }
-    u32 *d_next = (u32 *)(d_max + 1);  // zeroed above
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
     SMJ_ITEMS(ctx, nr + ns);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS, offS, nb2,

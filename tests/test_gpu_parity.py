@@ -300,3 +300,54 @@ def test_range_partition(smj, orc):
         dest = np.searchsorted(sp, (items >> np.uint64(32)).astype(np.uint32), side="right")
         assert np.array_equal(cnt, np.bincount(dest, minlength=nparts).astype(np.uint64))
         assert np.array_equal(out, items[np.argsort(dest, kind="stable")])  # stable
+
+
+# ------------------------------------------------------------------------------------ m-way fast path
+def _device_mway(smj, r, s):
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    st = smj.device_join(smj.ALGO_MWAY, dr, ds)
+    dr.free()
+    ds.free()
+    return st.matches, st.checksum
+
+
+@pytest.mark.parametrize("key_bits", [19, 23, 28, 29, 31])
+def test_mway_fast_path_key_domains(smj, orc, key_bits):
+    """The MSD fast path (>= 2^20 tuples, 19..31 varying key bits) against the oracle, including the
+    CTA-per-bucket variant for domains wider than 2^28."""
+    rng = np.random.default_rng(key_bits)
+    nr, ns = 1_300_003, 2_700_001
+    kmax = (1 << key_bits) - 1
+    keys = np.unique(rng.integers(1, kmax + 1, size=int(nr * 1.2), dtype=np.uint64))[:nr]
+    rng.shuffle(keys)
+    keys[0], keys[1] = np.uint64(1), np.uint64(kmax)  # make the whole domain vary
+    r = ol.keys_ok((keys << np.uint64(32)) | np.arange(keys.size, dtype=np.uint64))
+    s = ol.keys_ok((rng.choice(keys, size=ns) << np.uint64(32)) | rng.integers(0, 1 << 32, size=ns, dtype=np.uint64))
+    assert _device_mway(smj, r, s) == orc.join_bruteforce(r, s)
+
+
+def test_mway_fast_path_heavy_hitters(smj, orc):
+    rng = np.random.default_rng(77)
+    n = 1 << 22
+    r = orc.gen_unique(n // 4, 5)
+    zk = ol.zipf_keys(rng, n, n // 4, 1.0)  # hottest key: ~ n / 14 tuples -> cooperative bucket join
+    s = (zk << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    assert np.bincount(zk.astype(np.int64)).max() > (1 << 16)
+    exp = orc.join_bruteforce(r, s)
+    assert exp[0] == n
+    assert _device_mway(smj, r, s) == exp
+    # a key that is heavy on BOTH sides is left to the general sort + scan path
+    hot = np.full(100_000, (12345 << 32) | 7, dtype=np.uint64)
+    r2, s2 = np.concatenate([r, hot]), np.concatenate([s, hot, hot])
+    assert _device_mway(smj, r2, s2) == orc.join_bruteforce(r2, s2)
+
+
+def test_mway_fast_path_wrong_sample_guess(smj, orc):
+    """Two outliers far outside the sampled key range: the sampled plan must be rejected by the
+    exact OR/AND check and the general path must take over."""
+    n = 1 << 21
+    r, s = orc.gen_unique(n, 12345), orc.gen_unique(n, 54321)
+    r, s = r.copy(), s.copy()
+    r[n // 3 + 1] = np.uint64(((1 << 30) + 5) << 32 | 1)
+    s[n // 5 + 7] = np.uint64(((1 << 30) + 5) << 32 | 2)
+    assert _device_mway(smj, r, s) == orc.join_bruteforce(r, s)
