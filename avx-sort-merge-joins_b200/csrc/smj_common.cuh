@@ -19,6 +19,7 @@ struct SmjCtx {
     bool         ready;
     bool         profiling;   // smjdev_profile_begin(): CUDA events around every launch
     u64          next_items;  // items the next launch processes (annotation for the profile)
+    int          generation;  // bumped whenever the device changes: per-device kernel attributes
 };
 void smj_prof_before(SmjCtx *ctx, const char *kernel_name);
 void smj_prof_after(SmjCtx *ctx);

@@ -717,7 +717,9 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         if (nbig) return 0;
         const size_t smem = (size_t)(1u << lbits) * 12;
         static size_t smem_set_cta = 0;
-        if (smem > smem_set_cta) {
+        static int    gen_cta      = -1;
+        if (smem > smem_set_cta || gen_cta != ctx->generation) {
+            gen_cta = ctx->generation;
             SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
             smem_set_cta = smem;
@@ -733,7 +735,9 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
     if (unsupported) return 0;  // a key that is heavy in R and in S: general path
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
     static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static int    smem_gen = -1;
+    if (smem > smem_set || smem_gen != ctx->generation) {
+        smem_gen = ctx->generation;
         SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         SMJ_CHECK(cudaFuncSetAttribute(k_big_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -620,11 +620,11 @@ template <int BITS, class F>
 int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases) {
     constexpr int    THREADS = 512, IPT = 16, NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM    = (size_t)TILE * 8 + NB * 4 + NB * 8;
-    static bool      attr_set = false;
-    if (!attr_set) {
+    static int       attr_gen = -1;
+    if (attr_gen != ctx->generation) {
         SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_set = true;
+        attr_gen = ctx->generation;
     }
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F>), (unsigned)div_up(n, TILE), THREADS,
@@ -646,12 +646,12 @@ int launch_onesweep_cfg(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const
                         u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
     using Cfg = OneSweepCfg<THREADS, IPT, BITS>;
     static_assert(Cfg::TILE >= OS_MIN_TILE, "status_bytes assumes tiles of at least OS_MIN_TILE");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_gen = -1;  // kernel attributes are per device
+    if (attr_gen != ctx->generation) {
         SMJ_CHECK(cudaFuncSetAttribute(k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM));
-        attr_set = true;
+        attr_gen = ctx->generation;
     }
     const u64 tiles = div_up(n, Cfg::TILE);
     SMJ_ITEMS(ctx, n);
@@ -823,11 +823,11 @@ static int run_hist_wide(SmjCtx *ctx, const u64 *in, u64 n, DigitFn fn, u32 nbin
     SMJ_CHECK(cudaMemsetAsync(hist, 0, (size_t)nbins * 8, ctx->stream));
     if (n == 0) return 0;
     if (nbins <= (1u << 14)) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static int attr_gen = -1;
+        if (attr_gen != ctx->generation) {
             SMJ_CHECK(cudaFuncSetAttribute(k_hist_wide_smem,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            attr_set = true;
+            attr_gen = ctx->generation;
         }
         SMJ_LAUNCH(ctx, k_hist_wide_smem, hist_grid(ctx, n, 512, 16), 512, (size_t)nbins * 4, in, n,
                    fn, nbins, hist);
@@ -1145,12 +1145,12 @@ int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shi
     int rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1);  // consumes d_bases1
     if (rc) return rc;
     const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
-    static bool    attr_set  = false;
+    static int     attr_gen  = -1;
     constexpr size_t SMEM    = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
-    if (!attr_set) {
+    if (attr_gen != ctx->generation) {
         SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM));
-        attr_set = true;
+        attr_gen = ctx->generation;
     }
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, f2, d_hist2);

@@ -9,7 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false, false, 0};
+static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false, false, 0, 0};
 
 // ---- optional per-kernel timing (bench.py's roofline numbers): CUDA events on the launch stream
 struct ProfRec {
@@ -67,6 +67,7 @@ static int ctx_init_locked(int device) {
     cudaDeviceProp prop;
     SMJ_CHECK(cudaGetDeviceProperties(&prop, device));
     g_ctx.device   = device;
+    g_ctx.generation++;
     g_ctx.sm_count = prop.multiProcessorCount;
     SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
     g_ctx.stream = g_ctx.own_stream;

@@ -99,28 +99,25 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
     int              nthreads = cfg->NTHREADS > 0 ? cfg->NTHREADS : 1;
     float            ms_h2d   = 0.f;
 
+    int failed;
     gettimeofday(&start, NULL);
-    if (smjdev_init(-1)) {
-        smj_fatal(name);
-        return NULL;
-    }
-    if (smjdev_event_create(&e0) || smjdev_event_create(&e1) || smjdev_event_record(e0) ||
-        stage_in(&dr, relR->tuples, relR->num_tuples, 1) ||
-        stage_in(&ds, relS->tuples, relS->num_tuples, 1) || smjdev_event_record(e1)) {
-        smj_fatal(name);
-        return NULL;
-    }
-    /* m-pass / mpsm work on NTHREADS sorted runs per relation, like the reference's threads */
-    if (smjdev_join(algo, dr.d, relR->num_tuples, ds.d, relS->num_tuples, nthreads, &st)) {
-        smj_fatal(name);
-        return NULL;
-    }
-    if (dr.owned || ds.owned) smjdev_event_elapsed_ms(e0, e1, &ms_h2d);
-    st.ms_h2d = ms_h2d;
+    memset(&dr, 0, sizeof(dr));
+    memset(&ds, 0, sizeof(ds));
+    failed = smjdev_init(-1) || smjdev_event_create(&e0) || smjdev_event_create(&e1) ||
+             smjdev_event_record(e0) || stage_in(&dr, relR->tuples, relR->num_tuples, 1) ||
+             stage_in(&ds, relS->tuples, relS->num_tuples, 1) || smjdev_event_record(e1) ||
+             /* m-pass / mpsm work on NTHREADS sorted runs per relation, like the reference's threads */
+             smjdev_join(algo, dr.d, relR->num_tuples, ds.d, relS->num_tuples, nthreads, &st);
+    if (!failed && (dr.owned || ds.owned)) smjdev_event_elapsed_ms(e0, e1, &ms_h2d);
     stage_free(&dr);
     stage_free(&ds);
     smjdev_event_destroy(e0);
     smjdev_event_destroy(e1);
+    if (failed) {
+        smj_fatal(name); /* exits unless SMJ_NO_EXIT */
+        return NULL;
+    }
+    st.ms_h2d = ms_h2d;
     gettimeofday(&end, NULL);
 
     g_last_stats = st;
@@ -188,14 +185,18 @@ static uint64_t merge_join_common(tuple_t *r, tuple_t *s, uint64_t nr, uint64_t 
                                   const char *name) {
     devbuf_t dr, ds;
     uint64_t count = 0, cks = 0;
+    int      failed;
     if (nr == 0 || ns == 0) return 0;
-    if (stage_in(&dr, r, nr, 1) || stage_in(&ds, s, ns, 1) ||
-        smjdev_merge_join_ex(dr.d, nr, ds.d, ns, semi, &count, &cks)) {
+    memset(&dr, 0, sizeof(dr));
+    memset(&ds, 0, sizeof(ds));
+    failed = stage_in(&dr, r, nr, 1) || stage_in(&ds, s, ns, 1) ||
+             smjdev_merge_join_ex(dr.d, nr, ds.d, ns, semi, &count, &cks);
+    stage_free(&dr);
+    stage_free(&ds);
+    if (failed) {
         smj_fatal(name);
         return 0;
     }
-    stage_free(&dr);
-    stage_free(&ds);
     return count;
 }
 
@@ -379,14 +380,15 @@ static void sort_common(uint64_t **inputptr, uint64_t **outputptr, uint64_t n, i
     }
     uint64_t *da = (uint64_t *)smjdev_malloc(n * 8), *db = (uint64_t *)smjdev_malloc(n * 8);
     uint64_t *dst = placement ? out : in;
-    if (!da || !db || smjdev_memcpy_h2d(da, in, n * 8) ||
-        smjdev_sort(da, db, n, key_only, 0, &sorted) || smjdev_memcpy_d2h(dst, sorted, n * 8) ||
-        smjdev_sync()) {
+    int failed = !da || !db || smjdev_memcpy_h2d(da, in, n * 8) ||
+                 smjdev_sort(da, db, n, key_only, 0, &sorted) ||
+                 smjdev_memcpy_d2h(dst, sorted, n * 8) || smjdev_sync();
+    smjdev_free(da);
+    smjdev_free(db);
+    if (failed) {
         smj_fatal(name);
         return;
     }
-    smjdev_free(da);
-    smjdev_free(db);
     *outputptr = dst;
     *inputptr  = placement ? in : out;
 }
@@ -460,24 +462,26 @@ static int partition_common(relation_t *input, relation_t *output, uint32_t nbit
     devbuf_t       din, dout;
     uint64_t      *dtmp = NULL, *dhist = NULL, *doffs = NULL;
     int            rc   = -1;
+    memset(&din, 0, sizeof(din));
+    memset(&dout, 0, sizeof(dout));
     if (smjdev_init(-1)) return -1;
-    if (stage_in(&din, input->tuples, n, 1)) return -1;
-    if (stage_in(&dout, output->tuples, cap, 0)) return -1;
+    if (stage_in(&din, input->tuples, n, 1) || stage_in(&dout, output->tuples, cap, 0)) goto done;
     dhist = (uint64_t *)smjdev_malloc(fanout * 8);
     doffs = (uint64_t *)smjdev_malloc(fanout * 8);
     if (nbits > 8 && n) dtmp = (uint64_t *)smjdev_malloc(n * 8);
-    if (!dhist || !doffs || (nbits > 8 && n && !dtmp)) return -1;
+    if (!dhist || !doffs || (nbits > 8 && n && !dtmp)) goto done;
     /* the gaps between padded partitions are never written by the kernels: define them */
-    if (dout.owned && padded && smjdev_memset(dout.d, 0, cap * 8)) return -1;
-    if (smjdev_partition(din.d, dout.d, dtmp, n, nbits, shift, 1, padded, dhist, doffs)) return -1;
+    if (dout.owned && padded && smjdev_memset(dout.d, 0, cap * 8)) goto done;
+    if (smjdev_partition(din.d, dout.d, dtmp, n, nbits, shift, 1, padded, dhist, doffs)) goto done;
     if (smjdev_memcpy_d2h(hist_h, dhist, fanout * 8) || smjdev_memcpy_d2h(offs_h, doffs, fanout * 8) ||
         smjdev_sync())
-        return -1;
+        goto done;
     if (dout.owned && n) {
         uint64_t used = offs_h[fanout - 1] + hist_h[fanout - 1];
-        if (smjdev_memcpy_d2h(output->tuples, dout.d, used * 8) || smjdev_sync()) return -1;
+        if (smjdev_memcpy_d2h(output->tuples, dout.d, used * 8) || smjdev_sync()) goto done;
     }
     rc = 0;
+done:
     stage_free(&din);
     stage_free(&dout);
     smjdev_free(dtmp);
@@ -542,20 +546,21 @@ void histogram_memcpy_bench(relation_t **partitions, relation_t *input, relation
                             uint32_t nbits) {
     const uint64_t n = input->num_tuples;
     devbuf_t       din, dout;
-    uint64_t      *dhist;
+    uint64_t      *dhist = NULL;
+    int            failed;
     (void)partitions;
-    if (smjdev_init(-1) || stage_in(&din, input->tuples, n, 1) ||
-        stage_in(&dout, output->tuples, n, 0) ||
-        !(dhist = (uint64_t *)smjdev_malloc((1ull << nbits) * 8)) ||
-        smjdev_histogram(din.d, n, nbits, 0, 1, dhist) ||
-        (n && smjdev_memcpy_d2d(dout.d, din.d, n * 8)) ||
-        (dout.owned && n && smjdev_memcpy_d2h(output->tuples, dout.d, n * 8)) || smjdev_sync()) {
-        smj_fatal("histogram_memcpy_bench");
-        return;
-    }
+    memset(&din, 0, sizeof(din));
+    memset(&dout, 0, sizeof(dout));
+    failed = smjdev_init(-1) || stage_in(&din, input->tuples, n, 1) ||
+             stage_in(&dout, output->tuples, n, 0) ||
+             !(dhist = (uint64_t *)smjdev_malloc((1ull << nbits) * 8)) ||
+             smjdev_histogram(din.d, n, nbits, 0, 1, dhist) ||
+             (n && smjdev_memcpy_d2d(dout.d, din.d, n * 8)) ||
+             (dout.owned && n && smjdev_memcpy_d2h(output->tuples, dout.d, n * 8)) || smjdev_sync();
     stage_free(&din);
     stage_free(&dout);
     smjdev_free(dhist);
+    if (failed) smj_fatal("histogram_memcpy_bench");
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -564,17 +569,22 @@ void histogram_memcpy_bench(relation_t **partitions, relation_t *input, relation
 static uint64_t merge_common(const void *a, const void *b, void *out, uint64_t lenA, uint64_t lenB,
                              int mode, const char *name) {
     devbuf_t da, db, dout;
+    int      failed;
     if (lenA + lenB == 0) return 0;
-    if (smjdev_init(-1) || stage_in(&da, a, lenA, 1) || stage_in(&db, b, lenB, 1) ||
-        stage_in(&dout, out, lenA + lenB, 0) ||
-        smjdev_merge(da.d, lenA, db.d, lenB, dout.d, mode) ||
-        (dout.owned && smjdev_memcpy_d2h(out, dout.d, (lenA + lenB) * 8)) || smjdev_sync()) {
-        smj_fatal(name);
-        return 0;
-    }
+    memset(&da, 0, sizeof(da));
+    memset(&db, 0, sizeof(db));
+    memset(&dout, 0, sizeof(dout));
+    failed = smjdev_init(-1) || stage_in(&da, a, lenA, 1) || stage_in(&db, b, lenB, 1) ||
+             stage_in(&dout, out, lenA + lenB, 0) ||
+             smjdev_merge(da.d, lenA, db.d, lenB, dout.d, mode) ||
+             (dout.owned && smjdev_memcpy_d2h(out, dout.d, (lenA + lenB) * 8)) || smjdev_sync();
     stage_free(&da);
     stage_free(&db);
     stage_free(&dout);
+    if (failed) {
+        smj_fatal(name);
+        return 0;
+    }
     return lenA + lenB;
 }
 
@@ -604,7 +614,7 @@ static uint64_t multiway_common(tuple_t *output, relation_t **parts, uint32_t np
     devbuf_t        *runs  = (devbuf_t *)calloc(nparts ? nparts : 1, sizeof(devbuf_t));
     const uint64_t **ptrs  = (const uint64_t **)calloc(nparts ? nparts : 1, sizeof(uint64_t *));
     uint64_t        *lens  = (uint64_t *)calloc(nparts ? nparts : 1, sizeof(uint64_t));
-    devbuf_t         dout;
+    devbuf_t         dout  = {NULL, 0};
     uint64_t        *dtmp  = NULL;
     int              fail  = smjdev_init(-1);
     for (uint32_t i = 0; i < nparts && !fail; i++) {
@@ -619,11 +629,9 @@ static uint64_t multiway_common(tuple_t *output, relation_t **parts, uint32_t np
         if (!fail) fail = smjdev_multiway_merge(dout.d, dtmp, ptrs, lens, nparts, mode);
         if (!fail && dout.owned) fail = smjdev_memcpy_d2h(output, dout.d, total * 8);
         if (!fail) fail = smjdev_sync();
-        if (!fail) {
-            stage_free(&dout);
-            smjdev_free(dtmp);
-        }
     }
+    stage_free(&dout);
+    smjdev_free(dtmp);
     for (uint32_t i = 0; i < nparts; i++) stage_free(&runs[i]);
     free(runs);
     free(ptrs);
