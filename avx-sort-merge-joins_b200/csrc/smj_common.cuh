@@ -103,9 +103,7 @@ struct SplitFn {
     __host__ __device__ __forceinline__ u32 operator()(u64 x) const {
         const u32 k = (u32)(x >> 32);
         u32       d = 0;
-#pragma unroll
-        for (int i = 0; i < 31; i++)
-            if (i + 1 < (int)nparts) d += (sp[i] <= k) ? 1u : 0u;
+        for (u32 i = 0; i + 1 < nparts; i++) d += (sp[i] <= k) ? 1u : 0u;  // nparts - 1 compares
         return d;
     }
     __host__ __device__ __forceinline__ u32 last_bin() const { return nparts - 1; }

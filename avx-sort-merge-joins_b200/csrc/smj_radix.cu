@@ -508,7 +508,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // preserve yet) and for MSD passes; much cheaper, because the rank of an item is simply the value
 // a shared-memory atomicAdd on the bin counter returns: no per-warp histograms, no peer search.
 // ---------------------------------------------------------------------------------------
-template <int THREADS, int IPT, int BITS, class F, bool FULL>
+// AGG: rank through warp aggregation (match.any) instead of one atomic per lane; for bucket
+// functions with few bins (range partitioning over the GPUs), where per-lane atomics would all
+// hit the same few counters.
+template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false>
 __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
                                               const F &fn, u64 *cursors, u32 tile, u32 valid,
                                               u64 *s_items, u32 *s_cnt, u64 *s_goff, u32 *s_wsum) {
@@ -528,7 +531,18 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
         u32 r = 0;  // rank inside the tile's bin; items past the end of the input take no part
-        if (FULL || j * THREADS + threadIdx.x < valid) r = atomicAdd(&s_cnt[fn(item[j])], 1u);
+        if (AGG) {
+            const bool ok = FULL || j * THREADS + threadIdx.x < valid;
+            const u32  d  = ok ? fn(item[j]) : 0xffffffffu;
+            const u32  m  = __match_any_sync(SMJ_FULL_MASK, d);
+            const u32  ld = __ffs(m) - 1;
+            u32        base = 0;
+            if (ok && lane == ld) base = atomicAdd(&s_cnt[d], (u32)__popc(m));
+            base = __shfl_sync(SMJ_FULL_MASK, base, ld);
+            r    = base + __popc(m & lanemask_lt());
+        } else if (FULL || j * THREADS + threadIdx.x < valid) {
+            r = atomicAdd(&s_cnt[fn(item[j])], 1u);
+        }
         if (j & 1)
             pos2[j / 2] |= r << 16;
         else
@@ -591,7 +605,7 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
     }
 }
 
-template <int THREADS, int IPT, int BITS, class F>
+template <int THREADS, int IPT, int BITS, class F, bool AGG>
 __global__ void __launch_bounds__(THREADS, 2)
     k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, F fn,
                         u64 *cursors /* [NB], initialised to the start of every bin */) {
@@ -607,28 +621,28 @@ __global__ void __launch_bounds__(THREADS, 2)
     const u32 tile   = blockIdx.x;
     const u64 remain = n - (u64)tile * TILE;
     if (remain >= (u64)TILE)
-        unstable_tile<THREADS, IPT, BITS, F, true>(in, out, fn, cursors, tile, (u32)TILE, s_items,
-                                                   s_cnt, s_goff, s_wsum);
+        unstable_tile<THREADS, IPT, BITS, F, true, AGG>(in, out, fn, cursors, tile, (u32)TILE,
+                                                        s_items, s_cnt, s_goff, s_wsum);
     else
-        unstable_tile<THREADS, IPT, BITS, F, false>(in, out, fn, cursors, tile, (u32)remain,
-                                                    s_items, s_cnt, s_goff, s_wsum);
+        unstable_tile<THREADS, IPT, BITS, F, false, AGG>(in, out, fn, cursors, tile, (u32)remain,
+                                                         s_items, s_cnt, s_goff, s_wsum);
 }
 
 // bases: [NB] start of every bin; it is used as the cursor array and is CONSUMED (on return
 // bases[b] is the end of bin b)
-template <int BITS, class F>
+template <int BITS, class F, bool AGG = false>
 int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases) {
     constexpr int    THREADS = 512, IPT = 16, NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM    = (size_t)TILE * 8 + NB * 4 + NB * 8;
     static int       attr_gen = -1;
     if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F>,
+        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F, AGG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_gen = ctx->generation;
     }
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F>), (unsigned)div_up(n, TILE), THREADS,
-               SMEM, in, out, n, fn, bases);
+    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F, AGG>), (unsigned)div_up(n, TILE),
+               THREADS, SMEM, in, out, n, fn, bases);
     return 0;
 }
 
@@ -697,7 +711,10 @@ int launch_onesweep(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const u64
                                           padshift);
 }
 
-// histogram of one bucket function with <= 256 bins
+// histogram of one bucket function with few (<= 32) bins, e.g. destinations of a range
+// partition: lanes with the same bin are found with match.any (cheap when there are only a few
+// distinct values in a warp) and their leader adds the whole group with one shared-memory atomic;
+// plain per-lane atomics would serialise 32 ways on the same counter
 template <class F>
 __global__ void __launch_bounds__(512) k_hist_fn(const u64 *__restrict__ in, u64 n, F fn,
                                                  u64 *__restrict__ hist) {
@@ -705,11 +722,16 @@ __global__ void __launch_bounds__(512) k_hist_fn(const u64 *__restrict__ in, u64
     for (int i = threadIdx.x; i < RADIX_NB; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&sh[fn(ld_stream(in + i))], 1u);
+    const u64 rounds = (n + stride - 1) / stride;
+    u64       i      = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (u64 k = 0; k < rounds; k++, i += stride) {
+        const u32 d = (i < n) ? fn(ld_stream(in + i)) : 0xffffffffu;
+        const u32 m = __match_any_sync(SMJ_FULL_MASK, d);
+        if (i < n && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(&sh[d], (u32)__popc(m));
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < RADIX_NB; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
+    for (int i2 = threadIdx.x; i2 < RADIX_NB; i2 += blockDim.x)
+        if (sh[i2]) atomicAdd(&hist[i2], (u64)sh[i2]);
 }
 
 int hist_grid(SmjCtx *ctx, u64 n, int threads, int per_thread) {
@@ -798,7 +820,10 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
         u64 *dst = (k & 1) ? b : a;
         FieldFn f  = {plan.d[k].shift, plan.d[k].mask};
         int     rc;
-        if (k == 0 && key_only == 2) {  // order among equal keys is irrelevant to the caller
+        // The first pass may scramble items that agree on its digit when nothing depends on their
+        // input order: key-only sorts that promise no order among equal keys, and whole-word sorts
+        // (ties are then bit-identical items) unless the payload passes were dropped above.
+        if (k == 0 && (key_only == 2 || (key_only == 0 && (h_bits[2] & 2)))) {
             rc = (f.mask >= 256)
                      ? launch_unstable<9>(ctx, cur, dst, n, f, d_bases)
                      : launch_unstable<8>(ctx, cur, dst, n, f, d_bases);
@@ -1254,5 +1279,5 @@ extern "C" int smjdev_range_scatter(const uint64_t *in, uint64_t n, const uint32
     u64 *d_cur = (u64 *)sc.get(RADIX_NB * 8);
     if (!d_cur) return smj_fail_msg("smjdev_range_scatter: scratch");
     SMJ_CHECK(cudaMemcpyAsync(d_cur, h_cur, RADIX_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    return launch_unstable<8>(ctx, (const u64 *)in, (u64 *)nullptr, n, fn, d_cur);
+    return launch_unstable<8, SplitFn, true>(ctx, (const u64 *)in, (u64 *)nullptr, n, fn, d_cur);
 }

@@ -193,8 +193,10 @@ class DistributedJoin:
             dptr = (C.c_void_p * W)(*px.ptrs[rel])
             doff = (C.c_uint64 * W)(*[int(x) for x in offs[rel]])
             smj.check(lib.smjdev_range_scatter(t.data_ptr(), n, spp, W, dptr, doff), "range_scatter")
-        torch.cuda.current_stream().synchronize()  # my stores have left
-        dist.barrier()                              # ... and so have everybody else's
+        # Device-side barrier: the tiny all-reduce is enqueued behind this rank's scatter kernels and
+        # completes only when every rank has reached it, i.e. when all stores into this GPU's
+        # receive buffers have been issued and retired.  No host synchronisation.
+        dist.all_reduce(self._token(e.device), op=dist.ReduceOp.SUM)
         st = smj.smj_join_stats_t()
         smj.check(lib.smjdev_join(smj.ALGO_MWAY, px.local[0], int(recv[0]), px.local[1], int(recv[1]), 1,
                                   C.byref(st)), "smjdev_join")
@@ -203,6 +205,11 @@ class DistributedJoin:
         out = res.cpu().numpy().view(np.uint64)
         sent = 8 * int(counts[self.rank].sum() - counts[self.rank, :, self.rank].sum())
         return int(out[0]), int(out[1]), sent
+
+    def _token(self, device):
+        if getattr(self, "_tok", None) is None:
+            self._tok = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._tok
 
     def step(self, r, nr: int, s, ns: int, splitters: np.ndarray):
         """One complete distributed join of the local slices; returns the GLOBAL (count, checksum)

@@ -71,6 +71,14 @@ def run(args, smj):
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     clocks = sampler.stop() if sampler else None
     ms_step = float(ms.item()) / args.steps
+    # how much of a step is kernels of this library (rank 0, CUDA events around every launch)
+    lib.smjdev_profile_begin()
+    for _ in range(args.steps):
+        one_step(r, s)
+    pbuf = C.create_string_buffer(1 << 16)
+    lib.smjdev_profile_end(pbuf, len(pbuf))
+    prof = B.parse_profile(pbuf.value.decode())
+    kernel_ms = sum(p["ms"] for p in prof.values()) / args.steps
     value = 2 * n / (ms_step * 1e-3) / 1e6
     assert cnt == n
 
@@ -108,7 +116,9 @@ def run(args, smj):
                                       + ", local m-way join, all-reduce of count/checksum",
                        "l2": "per-rank inputs (2 x %.2f GB) are larger than L2" % (count * 8 / 1e9),
                        "timing": "CUDA events on the stream shared with NCCL, max over ranks",
-                       "exchange_bytes_sent_per_rank": sent},
+                       "exchange_bytes_sent_per_rank": sent,
+                       "rank0_kernel_ms_per_step": kernel_ms,
+                       "rank0_kernels": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}},
             "clocks": clocks,
             "e2e": {"value": 2 * n / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": 2 * n * 8,
                     "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
