@@ -109,6 +109,11 @@ SIGNATURES = {
                               C.POINTER(smj_join_stats_t)]),
     "smjdev_range_partition": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32,
                                          _vp]),
+    "smjdev_sample_key_bits": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
+    "smjdev_msd_hist": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "smjdev_msd_scatter": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(_vp), _u64p]),
+    "smjdev_join_level1": (C.c_int, [_vp, _u64p, _vp, _u64p, C.c_uint32, C.c_uint32,
+                                     C.POINTER(smj_join_stats_t)]),
     "smjdev_range_count": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, _vp]),
     "smjdev_range_scatter": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(_vp),
                                        _u64p]),

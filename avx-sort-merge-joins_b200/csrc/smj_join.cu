@@ -29,7 +29,12 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
 int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, const u64 *lens,
                        u32 nruns, int mode);
 int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
-                      u64 *offsets, u64 *maxbucket, u64 *exact_bits);
+                      u64 *offsets, u64 *exact_bits);
+int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_hist1, u64 *b, u32 shift2,
+                   u64 *offsets);
+int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 *exact_bits);
+int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
+                       const u64 *dest_offsets);
 int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
 
 namespace {
@@ -667,51 +672,25 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
 }
 }  // namespace
 
-// m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
-// fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
-// do not suit it; the caller then takes the general sort + scan path.
-static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *aR, u64 *bR, u64 *aS,
-                    u64 *bS, u64 *acc, int *used, PhaseTimer &tm, int &t_part, int &t_sort,
-                    int &t_join) {
-    *used = 0;
-    if (nr + ns < (1u << 20)) return 0;  // 2^18 buckets only pay off on large inputs
-    u64 bits[4];
-    // The key range is guessed from a sample (5 us instead of a full read of R and S); the first
-    // histogram pass computes the exact OR / AND on the side and the guess is verified before the
-    // result is used.
-    int rc = smj_key_bits_sampled(ctx, r, nr, s, ns, bits);
-    if (rc) return rc;
-    const u32 vor = (u32)((bits[0] | bits[2]) >> 32), vand = (u32)((bits[1] & bits[3]) >> 32);
-    const u32 v   = vor & ~vand;
-    if (v == 0) return 0;
-    const int hi = 31 - __builtin_clz(v), lo = __builtin_ctz(v), k = hi - lo + 1;
-    if (k < 19 || k > 31) return 0;
-    const u32 lbits  = (u32)(k - 18);
-    const u32 shift1 = 32 + (u32)hi - 8, shift2 = shift1 - 9, lo_shift = 32 + (u32)lo;
-    const u32 nb2    = 512u * 512u;
-    SmjScratch sc(ctx);
-    u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
+// Join of the 2^18 second-level buckets (bR/offR, bS/offS as written by smj_msd_pass_b).
+// d_state (device, 8 x u64, initialised by the caller to {0, 0, 0, ~0, 0, ~0, 0, 0}):
+//   [1] bucket counter, [2..5] exact OR / AND of R and S (filled by the histogram passes),
+//   [6] = {number of heavy buckets, flag "a bucket is heavy on both sides"}.
+// h_state receives a copy (the call synchronises once).  *done = 0 when the buckets do not suit
+// the bucket kernels (the caller then takes the general sort + scan path).
+static int bucket_stage(SmjCtx *ctx, const u64 *bR, const u64 *offR, u64 nr, const u64 *bS,
+                        const u64 *offS, u64 ns, u32 lo_shift, u32 lbits, u64 *d_state, u64 *h_state,
+                        u32 *d_list, u64 *acc, int *done, PhaseTimer *tm, int *t_mid) {
     constexpr u64 BIG = 1u << 16, RMAX = 1u << 16;  // bucket sizes: cooperative above BIG
-    u64 *d_max  = (u64 *)sc.get(64);  // [0] max bucket, [1] bucket counter, [2..5] exact OR/AND of R, S,
-                                      // [6] = {big count, unsupported flag}
-    u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4);
-    if (!offR || !offS || !d_max || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
-    const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d_max, init, 64, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = smj_msd_partition(ctx, r, nr, aR, bR, shift1, shift2, offR, d_max, d_max + 2))) return rc;
-    if ((rc = smj_msd_partition(ctx, s, ns, aS, bS, shift1, shift2, offS, d_max, d_max + 4))) return rc;
-    SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, offR, offS, nb2, BIG, RMAX, d_list, (u32 *)(d_max + 6));
-    u64 h[8];
-    SMJ_CHECK(cudaMemcpyAsync(h, d_max, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    t_part = t_sort = tm.mark();  // the in-partition sort is fused into the join kernel
+    const u32     nb2 = 512u * 512u;
+    *done             = 0;
+    SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, offR, offS, nb2, BIG, RMAX, d_list,
+               (u32 *)(d_state + 6));
+    SMJ_CHECK(cudaMemcpyAsync(h_state, d_state, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tm && t_mid) *t_mid = tm->mark();
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-    {   // verify the sampled guess: no key bit outside [lo, hi] may vary in R or S
-        const u32 xor_ = (u32)((h[2] | h[4]) >> 32), xand = (u32)((h[3] & h[5]) >> 32);
-        const u32 range = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
-        if ((xor_ & ~xand) & ~range) return 0;
-    }
-    const u32 nbig = (u32)(h[6] & 0xffffffffu), unsupported = (u32)(h[6] >> 32);
-    u32 *d_next = (u32 *)(d_max + 1);  // zeroed above
+    const u32 nbig = (u32)(h_state[6] & 0xffffffffu), unsupported = (u32)(h_state[6] >> 32);
+    u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
         // wide key domains (up to 2^31): one CTA per bucket, no cooperative heavy-hitter kernel
         if (nbig) return 0;
@@ -728,8 +707,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         SMJ_ITEMS(ctx, nr + ns);
         SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, bR, offR, bS, offS, nb2,
                    lo_shift, lbits, d_next, acc);
-        t_join = tm.mark();
-        *used  = 1;
+        *done = 1;
         return 0;
     }
     if (unsupported) return 0;  // a key that is heavy in R and in S: general path
@@ -750,7 +728,74 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
                lo_shift, lbits, BIG, d_next, acc);
     if (nbig)
         SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS,
-                   offS, d_list, (u32 *)(d_max + 6), lo_shift, lbits, acc);
+                   offS, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
+    *done = 1;
+    return 0;
+}
+
+// The key digits of the MSD plan from the OR / AND of the keys of R and S (bits = {OR_R, AND_R,
+// OR_S, AND_S} of the items).  Returns false when the key domain does not suit the fast path.
+static bool msd_plan(const u64 *bits, int *lo, int *hi, u32 *shift1, u32 *shift2, u32 *lo_shift,
+                     u32 *lbits) {
+    const u32 vor = (u32)((bits[0] | bits[2]) >> 32), vand = (u32)((bits[1] & bits[3]) >> 32);
+    const u32 v   = vor & ~vand;
+    if (v == 0) return false;
+    *hi         = 31 - __builtin_clz(v);
+    *lo         = __builtin_ctz(v);
+    const int k = *hi - *lo + 1;
+    if (k < 19 || k > 31) return false;
+    *lbits    = (u32)(k - 18);
+    *shift1   = 32 + (u32)*hi - 8;
+    *shift2   = *shift1 - 9;
+    *lo_shift = 32 + (u32)*lo;
+    return true;
+}
+// no key bit outside [lo, hi] may vary in R or S (exact = {OR_R, AND_R, OR_S, AND_S})
+static bool msd_plan_holds(const u64 *exact, int lo, int hi) {
+    const u32 xor_ = (u32)((exact[0] | exact[2]) >> 32), xand = (u32)((exact[1] & exact[3]) >> 32);
+    const u32 range = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+    return ((xor_ & ~xand) & ~range) == 0;
+}
+
+// m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
+// fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
+// do not suit it; the caller then takes the general sort + scan path.
+static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *aR, u64 *bR, u64 *aS,
+                    u64 *bS, u64 *acc, int *used, PhaseTimer &tm, int &t_part, int &t_sort,
+                    int &t_join) {
+    *used = 0;
+    if (nr + ns < (1u << 20)) return 0;  // 2^18 buckets only pay off on large inputs
+    u64 bits[4];
+    // The key range is guessed from a sample (5 us instead of a full read of R and S); the first
+    // histogram pass computes the exact OR / AND on the side and the guess is verified before the
+    // result is used.
+    int rc = smj_key_bits_sampled(ctx, r, nr, s, ns, bits);
+    if (rc) return rc;
+    int lo, hi;
+    u32 shift1, shift2, lo_shift, lbits;
+    if (!msd_plan(bits, &lo, &hi, &shift1, &shift2, &lo_shift, &lbits)) return 0;
+    const u32  nb2 = 512u * 512u;
+    SmjScratch sc(ctx);
+    u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
+    u64 *d_state = (u64 *)sc.get(64);
+    u32 *d_list  = (u32 *)sc.get((size_t)nb2 * 4);
+    if (!offR || !offS || !d_state || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
+    const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d_state, init, 64, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = smj_msd_partition(ctx, r, nr, aR, bR, shift1, shift2, offR, d_state + 2))) return rc;
+    if ((rc = smj_msd_partition(ctx, s, ns, aS, bS, shift1, shift2, offS, d_state + 4))) return rc;
+    u64 h[8];
+    int done = 0, t_mid = -1;
+    if ((rc = bucket_stage(ctx, bR, offR, nr, bS, offS, ns, lo_shift, lbits, d_state, h, d_list, acc, &done,
+                           &tm, &t_mid)))
+        return rc;
+    t_part = t_sort = t_mid;  // the in-partition sort is fused into the join kernel
+    if (!msd_plan_holds(h + 2, lo, hi)) {
+        // the sample missed key bits that do vary: whatever the bucket kernels added is void
+        SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+        return 0;
+    }
+    if (!done) return 0;
     t_join = tm.mark();
     *used  = 1;
     return 0;
@@ -848,6 +893,105 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     stats->ms_sort      = tm.ms(t_part, t_sort);
     stats->ms_merge     = tm.ms(t_sort, t_merge);
     stats->ms_join      = tm.ms(t_merge, t_join);
+    stats->ms_total     = tm.ms(t0, t_end);
+    stats->launches     = ctx->launches - launches0;
+    stats->hbm_bytes    = sc.bytes;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-GPU building blocks: on G GPUs the FIRST pass of the MSD partition is the exchange.
+// Every rank histograms its slice by the top 9 key bits (smjdev_msd_hist), the ranks agree on
+// bucket owners and write offsets, and each rank's pass-A scatter stores its items directly into
+// the owners' buffers over NVLink (smjdev_msd_scatter).  What a rank then holds is exactly the
+// input of pass B: smjdev_join_level1 finishes the join from there.
+// ---------------------------------------------------------------------------------------
+extern "C" int smjdev_sample_key_bits(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                                      uint64_t *host4) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    return smj_key_bits_sampled(ctx, (const u64 *)r, nr, (const u64 *)s, ns, (u64 *)host4);
+}
+
+extern "C" int smjdev_msd_hist(const uint64_t *in, uint64_t n, uint32_t shift1, uint64_t *hist512,
+                               uint64_t *bits2) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (shift1 < 32 || shift1 > 55) return smj_fail_msg("smjdev_msd_hist: digit outside the key");
+    return smj_msd_hist1(ctx, (const u64 *)in, n, shift1, (u64 *)hist512, (u64 *)bits2);
+}
+
+extern "C" int smjdev_msd_scatter(const uint64_t *in, uint64_t n, uint32_t shift1,
+                                  uint64_t *const *dest_ptrs512, const uint64_t *dest_offsets512) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (shift1 < 32 || shift1 > 55) return smj_fail_msg("smjdev_msd_scatter: digit outside the key");
+    return smj_msd_scatter_to(ctx, (const u64 *)in, n, shift1, (u64 *const *)dest_ptrs512,
+                              (const u64 *)dest_offsets512);
+}
+
+extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512, const uint64_t *s_,
+                                  const uint64_t *scounts512, uint32_t shift1, uint32_t lo_bit,
+                                  smj_join_stats_t *stats) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (!stats) return smj_fail_msg("smjdev_join_level1: stats must not be NULL");
+    if (shift1 < 41 || shift1 > 55 || 32 + lo_bit + 1 > shift1 - 9 || shift1 - 9 - (32 + lo_bit) > 13)
+        return smj_fail_msg("smjdev_join_level1: key digits out of range");
+    const u64 *r = (const u64 *)r_, *s = (const u64 *)s_;
+    memset(stats, 0, sizeof(*stats));
+    u64 nr = 0, ns = 0;
+    for (int b = 0; b < 512; b++) {
+        nr += rcounts512[b];
+        ns += scounts512[b];
+    }
+    const u64  launches0 = ctx->launches;
+    const u32  shift2 = shift1 - 9, lo_shift = 32 + lo_bit, lbits = shift2 - lo_shift, nb2 = 512u * 512u;
+    SmjScratch sc(ctx);
+    u64 *acc = (u64 *)sc.get(16);
+    if (!acc) return smj_fail_msg("smjdev_join_level1: scratch allocation failed");
+    PhaseTimer tm(ctx);
+    const int  t0 = tm.mark();
+    int        t_part = t0, t_join = t0;
+    SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+    if (nr && ns) {
+        u64 *bR = (u64 *)sc.get(nr * 8), *bS = (u64 *)sc.get(ns * 8);
+        u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
+        u64 *d_h1 = (u64 *)sc.get(2 * 512 * 8), *d_state = (u64 *)sc.get(64);
+        u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4);
+        if (!bR || !bS || !offR || !offS || !d_h1 || !d_state || !d_list)
+            return smj_fail_msg("smjdev_join_level1: out of device memory");
+        const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
+        SMJ_CHECK(cudaMemcpyAsync(d_state, init, 64, cudaMemcpyHostToDevice, ctx->stream));
+        SMJ_CHECK(cudaMemcpyAsync(d_h1, rcounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SMJ_CHECK(cudaMemcpyAsync(d_h1 + 512, scounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
+        int rc;
+        if ((rc = smj_msd_pass_b(ctx, r, nr, d_h1, bR, shift2, offR))) return rc;
+        if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, bS, shift2, offS))) return rc;
+        u64 h[8];
+        int done = 0;
+        if ((rc = bucket_stage(ctx, bR, offR, nr, bS, offS, ns, lo_shift, lbits, d_state, h, d_list, acc,
+                               &done, &tm, &t_part)))
+            return rc;
+        if (!done) {
+            // heavy on both sides: general path on the same items (partitioning does not matter to it)
+            u64 *aR = (u64 *)sc.get(nr * 8), *aS = (u64 *)sc.get(ns * 8), *sr = nullptr, *ss = nullptr;
+            if (!aR || !aS) return smj_fail_msg("smjdev_join_level1: out of device memory");
+            SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+            if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
+            if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
+            if ((rc = smj_merge_join_acc(ctx, sr, nr, ss, ns, acc))) return rc;
+        }
+        t_join = tm.mark();
+    }
+    u64 hres[2];
+    SMJ_CHECK(cudaMemcpyAsync(hres, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    const int t_end = tm.mark();
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    stats->matches      = hres[0];
+    stats->checksum     = hres[1];
+    stats->ms_partition = tm.ms(t0, t_part);
+    stats->ms_join      = tm.ms(t_part, t_join);
     stats->ms_total     = tm.ms(t0, t_end);
     stats->launches     = ctx->launches - launches0;
     stats->hbm_bytes    = sc.bytes;

@@ -1134,44 +1134,27 @@ __global__ void __launch_bounds__(1024) k_scan_add(u64 *__restrict__ out, u64 nb
     if (i < nb) out[i] += base;
 }
 
-__global__ void __launch_bounds__(256) k_max_u64(const u64 *__restrict__ v, u64 n, u64 *out) {
-    u64 m = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        m = max(m, v[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(SMJ_FULL_MASK, m, o));
-    if (lane_id() == 0 && m) atomicMax(out, m);
-}
-
 }  // namespace
 
-// in -> a (pass A) -> b (pass B).  shift1 = position of the top 9-bit digit, shift2 = shift1 - 9.
-// offsets: device array of 2^18 + 1 entries, receives the start of every bucket in b (and n).
-// maxbucket: device u64, receives the size of the largest bucket (accumulated with atomicMax, so
-// one variable can be shared by R and S; the caller zeroes it).
-// exact_bits: device pair {OR, AND} (initialised to {0, ~0} by the caller, may be null) that
-// receives the OR / AND of all items as a by-product of the first histogram pass.
-int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
-                      u64 *offsets, u64 *maxbucket, u64 *exact_bits) {
+// Pass B of the MSD partition: `a` holds n items already partitioned by the first-level digit,
+// d_hist1 (device, 512 entries) the sizes of the first-level buckets laid out back to back in a.
+// Every bucket is partitioned by the 9-bit digit at shift2 into b.  offsets (device, 2^18 + 1
+// entries) receives the start of every second-level bucket in b (and n).
+int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_hist1, u64 *b, u32 shift2,
+                   u64 *offsets) {
     const u32  NB2 = MSD_NB * MSD_NB;
     SmjScratch sc(ctx);
-    u64 *d_hist1 = (u64 *)sc.get(RADIX_NB * 8), *d_bases1 = (u64 *)sc.get(RADIX_NB * 8);
     u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get((MSD_NB + 1) * 8);
     u64 *d_hist2 = (u64 *)sc.get((size_t)NB2 * 8), *d_cur2 = (u64 *)sc.get((size_t)NB2 * 8);
-    if (!d_hist1 || !d_bases1 || !d_tpref || !d_bstart || !d_hist2 || !d_cur2)
-        return smj_fail_msg("smj_msd_partition: scratch allocation failed");
-    SMJ_CHECK(cudaMemsetAsync(d_hist1, 0, RADIX_NB * 8, ctx->stream));
+    u64 *d_tot   = (u64 *)sc.get((NB2 / 1024) * 8);
+    if (!d_tpref || !d_bstart || !d_hist2 || !d_cur2 || !d_tot)
+        return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
     SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
-    FieldFn f1 = {shift1, (u32)MSD_NB - 1}, f2 = {shift2, (u32)MSD_NB - 1};
-    SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_hist1, hist_grid(ctx, n, 512, 16), 512, 0, in, n, f1, d_hist1, exact_bits);
-    SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist1, d_bases1);
+    FieldFn f2 = {shift2, (u32)MSD_NB - 1};
     SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_hist1, d_tpref, d_bstart);
-    int rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1);  // consumes d_bases1
-    if (rc) return rc;
-    const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
-    static int     attr_gen  = -1;
-    constexpr size_t SMEM    = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
+    const unsigned   max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    static int       attr_gen  = -1;
+    constexpr size_t SMEM      = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
     if (attr_gen != ctx->generation) {
         SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM));
@@ -1179,16 +1162,62 @@ int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shi
     }
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, f2, d_hist2);
-    u64 *d_tot = (u64 *)sc.get((NB2 / 1024) * 8);
-    if (!d_tot) return smj_fail_msg("smj_msd_partition: scratch allocation failed");
     SMJ_LAUNCH(ctx, k_scan_local, NB2 / 1024, 1024, 0, d_hist2, (u64)NB2, offsets, d_tot);
     SMJ_LAUNCH(ctx, k_scan_add, NB2 / 1024, 1024, 0, offsets, (u64)NB2, d_tot);
-    SMJ_LAUNCH(ctx, k_max_u64, 64, 256, 0, d_hist2, (u64)NB2, maxbucket);
     SMJ_CHECK(cudaMemcpyAsync(d_cur2, offsets, (size_t)NB2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2, max_tiles, MSD_THREADS, SMEM, a, b, d_tpref, d_bstart, f2, d_cur2);
     return 0;
+}
+
+// first-level histogram (512 bins, digit at shift1) + exact OR / AND of the items.
+// hist: device, 512 entries, overwritten.  exact_bits: device pair {OR, AND} that is ACCUMULATED
+// into (the caller initialises it to {0, ~0}); may be null.
+int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 *exact_bits) {
+    SMJ_CHECK(cudaMemsetAsync(hist, 0, MSD_NB * 8, ctx->stream));
+    if (n == 0) return 0;
+    FieldFn f1 = {shift1, (u32)MSD_NB - 1};
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, k_msd_hist1, hist_grid(ctx, n, 512, 16), 512, 0, in, n, f1, hist, exact_bits);
+    return 0;
+}
+
+// in -> a (pass A) -> b (pass B).  shift1 = position of the top 9-bit digit, shift2 = shift1 - 9.
+// offsets: device array of 2^18 + 1 entries, receives the start of every bucket in b (and n).
+// exact_bits: see smj_msd_hist1.
+int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
+                      u64 *offsets, u64 *exact_bits) {
+    SmjScratch sc(ctx);
+    u64 *d_hist1 = (u64 *)sc.get(RADIX_NB * 8), *d_bases1 = (u64 *)sc.get(RADIX_NB * 8);
+    if (!d_hist1 || !d_bases1) return smj_fail_msg("smj_msd_partition: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_hist1, 0, RADIX_NB * 8, ctx->stream));
+    int rc = smj_msd_hist1(ctx, in, n, shift1, d_hist1, exact_bits);
+    if (rc) return rc;
+    SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist1, d_bases1);
+    FieldFn f1 = {shift1, (u32)MSD_NB - 1};
+    if (n && (rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1))) return rc;  // consumes d_bases1
+    return smj_msd_pass_b(ctx, a, n, d_hist1, b, shift2, offsets);
+}
+
+// Pass A of the MSD partition with caller-supplied destinations: bucket d of the 9-bit digit at
+// shift1 goes to dest_ptrs[d] (device pointer, possibly a peer GPU's buffer) starting at item
+// dest_offsets[d].  Host arrays of 512 entries.  Used by the multi-GPU join, where the first
+// partitioning pass IS the exchange.
+int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
+                       const u64 *dest_offsets) {
+    if (n == 0) return 0;
+    u64 h_cur[RADIX_NB];
+    for (int d = 0; d < MSD_NB; d++) {
+        if ((uintptr_t)dest_ptrs[d] & 7) return smj_fail_msg("smj_msd_scatter_to: unaligned buffer");
+        h_cur[d] = (u64)((uintptr_t)dest_ptrs[d] >> 3) + dest_offsets[d];
+    }
+    SmjScratch sc(ctx);
+    u64 *d_cur = (u64 *)sc.get(RADIX_NB * 8);
+    if (!d_cur) return smj_fail_msg("smj_msd_scatter_to: scratch");
+    SMJ_CHECK(cudaMemcpyAsync(d_cur, h_cur, RADIX_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FieldFn f1 = {shift1, (u32)MSD_NB - 1};
+    return launch_unstable<9>(ctx, in, (u64 *)nullptr, n, f1, d_cur);
 }
 
 // Same from a strided sample of about 2^16 items per relation (a guess, to be verified).

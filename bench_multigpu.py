@@ -36,13 +36,16 @@ def run(args, smj):
     splitters = dj_mod.uniform_splitters(n, world)  # keys are a permutation of 1..n
 
     # fused partition + exchange over peer memory (default); SMJ_EXCHANGE=nccl uses the all-to-all
-    use_p2p = os.environ.get("SMJ_EXCHANGE", "p2p") != "nccl"
+    mode = os.environ.get("SMJ_EXCHANGE", "msd")  # msd (default) | p2p | nccl
+    use_p2p = mode != "nccl"
     px = None
     if use_p2p:
         cap = int(count * 1.25) + 65536
         px = dj_mod.P2PExchange(eng, rank, world, cap, cap)
 
     def one_step(rr, ss):
+        if mode == "msd":
+            return dj.step_msd(rr, count, ss, count, px)
         if use_p2p:
             return dj.step_p2p(rr, count, ss, count, splitters, px)
         return dj.step(rr, count, ss, count, splitters)
@@ -110,7 +113,10 @@ def run(args, smj):
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"sortmergejoins -a m-way, |R|=|S|={n} 8-byte tuples, uniform unique keys "
                                    f"(BASELINE.json configs[0]), relations spread evenly over {world} GPUs",
-                       "parallelism": (f"range partition fused with the exchange (scatter kernel stores into peer receive "
+                       "parallelism": (f"first MSD partitioning pass fused with the exchange (the scatter kernel stores "
+                                       f"into the bucket owners' buffers over NVLink, CUDA IPC) over {world} GPUs"
+                                       if mode == "msd" else
+                                       f"range partition fused with the exchange (scatter kernel stores into peer receive "
                                        f"buffers over NVLink, CUDA IPC) over {world} GPUs" if use_p2p else
                                        f"range partition by key + NCCL all-to-all over {world} GPUs")
                                       + ", local m-way join, all-reduce of count/checksum",

@@ -137,6 +137,10 @@ typedef struct smj_join_stats_t {
 int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                 int nruns, smj_join_stats_t *stats);
 
+int smjdev_join_level1(const uint64_t *r, const uint64_t *rcounts512, const uint64_t *s,
+                       const uint64_t *scounts512, uint32_t shift1, uint32_t lo_bit,
+                       smj_join_stats_t *stats);
+
 /* Multi-GPU building blocks (one process per GPU; the exchange itself is done by the
  * caller with NCCL).
  * Range-partition n items into nparts (<= 32) destinations by splitters[0..nparts-2] (ascending
@@ -156,6 +160,26 @@ int smjdev_range_count(const uint64_t *in, uint64_t n, const uint32_t *splitters
                        uint64_t *counts);
 int smjdev_range_scatter(const uint64_t *in, uint64_t n, const uint32_t *splitters, uint32_t nparts,
                          uint64_t *const *dest_ptrs, const uint64_t *dest_offsets);
+/* The same idea one level deeper (what DistributedJoin.step_msd uses): the FIRST pass of the m-way
+ * join's two-level MSD partition is the exchange.
+ *   smjdev_sample_key_bits: {OR_R, AND_R, OR_S, AND_S} of a 2^16-item sample (host array of 4; syncs):
+ *                           a guess of the varying key bits, to be verified with the exact values
+ *   smjdev_msd_hist:        sizes of the 512 first-level buckets (digit = 9 bits at bit `shift1` of
+ *                           the item) into hist512 (device), exact OR / AND accumulated into bits2
+ *                           (device pair, caller initialises {0, ~0}; may be NULL)
+ *   smjdev_msd_scatter:     first-level scatter with caller-supplied destinations: bucket d goes
+ *                           to dest_ptrs512[d] (device pointer, possibly a peer GPU's buffer)
+ *                           starting at item dest_offsets512[d] (HOST arrays of 512)
+ *   smjdev_join_level1:     joins two relations that are already partitioned by the first-level
+ *                           digit (buckets back to back, sizes in the HOST arrays rcounts512 /
+ *                           scounts512): second-level partition + fused bucket join.  lo_bit =
+ *                           lowest varying KEY bit (0..31). */
+int smjdev_sample_key_bits(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                           uint64_t *host4);
+int smjdev_msd_hist(const uint64_t *in, uint64_t n, uint32_t shift1, uint64_t *hist512, uint64_t *bits2);
+int smjdev_msd_scatter(const uint64_t *in, uint64_t n, uint32_t shift1, uint64_t *const *dest_ptrs512,
+                       const uint64_t *dest_offsets512);
+/* (smjdev_join_level1 is declared after smj_join_stats_t below) */
 /* device buffers that other processes can map (cudaMalloc + CUDA IPC handles, 64 bytes each) */
 int smjdev_ipc_alloc(size_t bytes, void **dptr);
 int smjdev_ipc_free(void *dptr);

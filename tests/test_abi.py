@@ -122,3 +122,35 @@ def test_p2p_layout():
                 assert layouts[src][0][rel][dst] == pos
                 pos += counts[src][rel][dst]
             assert layouts[dst][1][rel] == pos
+
+
+def test_msd_layout_and_plan():
+    """bucket ownership / write offsets of the exchange-as-first-partition-pass (pure host logic)."""
+    import importlib
+    dj = importlib.import_module("avx-sort-merge-joins_b200.distributed")
+    rng = np.random.default_rng(11)
+    W = 4
+    hist = rng.integers(0, 5000, size=(W, 2, 512))
+    hist[:, :, 400:] = 0                       # unused buckets at the top of the key range
+    hist[:, 1, 17] += 500000                   # a heavy S bucket
+    lay = [dj.msd_layout(hist, g) for g in range(W)]
+    owner = lay[0][0]
+    assert all(np.array_equal(owner, l[0]) for l in lay) and np.all(np.diff(owner) >= 0)
+    assert set(owner.tolist()) <= set(range(W))
+    tot = hist.sum(axis=0)
+    for rel in range(2):
+        for g in range(W):
+            pos = 0
+            for b in np.nonzero(owner == g)[0]:
+                for src in range(W):            # slices of a bucket in source-rank order, buckets back to back
+                    assert lay[src][1][rel][b] == pos
+                    pos += hist[src][rel][b]
+                assert lay[g][2][rel][b] == tot[rel][b]
+            assert lay[g][2][rel].sum() == pos
+        assert sum(l[2][rel].sum() for l in lay) == tot[rel].sum()
+    # plan: keys 1..128M -> 27 varying bits, top digit at item bit 32+26-8
+    items_or, items_and = (128_000_000 | 0x7FFFFFF) << 32, 0
+    assert dj.msd_plan(items_or, items_and, items_or, items_and) == (0, 26, 50)
+    assert dj.msd_plan(5 << 32, 5 << 32, 5 << 32, 5 << 32) is None
+    assert dj.msd_plan_holds(items_or, 0, items_or, 0, 0, 26)
+    assert not dj.msd_plan_holds(items_or | (1 << 62), 0, items_or, 0, 0, 26)
