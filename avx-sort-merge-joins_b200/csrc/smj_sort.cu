@@ -1,16 +1,14 @@
 // smj_sort.cu -- C-ABI sort entry points (include/smj_device.h).
 //
 // smjdev_sort replaces src/avxsort/avxsort.c:128-245 (avxsort_aligned/_unaligned behind
-// avxsort_tuples / avxsort_int64): it picks between the two device sorts
-//   * LSD one-sweep radix passes over the varying bits      (smj_radix.cu, any distribution)
-//   * MSD range partition + in-shared-memory segment sort   (smj_segsort.cu, when segments fit)
+// avxsort_tuples / avxsort_int64) with LSD one-sweep radix passes over the varying bits
+// (smj_radix.cu).  The m-way join does not go through here: it partitions MSD-first and never
+// materialises sorted buckets (smj_join.cu).
 #include "smj_common.cuh"
 #include <algorithm>
 #include "../../include/smj_device.h"
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
-int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted,
-                 int *used);
 
 extern "C" int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_only, int algo,
                            uint64_t **sorted) {
@@ -18,18 +16,9 @@ extern "C" int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_onl
     if (!ctx) return -1;
     if (!sorted) return smj_fail_msg("smjdev_sort: sorted must not be NULL");
     u64 *res = nullptr;
-    int  rc;
-    if (algo == 0 || algo == 2) {
-        int used = 0;
-        rc       = smj_msd_sort(ctx, (const u64 *)buf, (u64 *)tmp, (u64 *)buf, n, key_only, &res, &used);
-        if (rc) return rc;
-        if (used) {
-            *sorted = (uint64_t *)res;
-            return 0;
-        }
-    }
+    if (algo != 0 && algo != 1) return smj_fail_msg("smjdev_sort: unknown algorithm");
     // classic two-buffer ping-pong: pass 1 buf -> tmp, pass 2 tmp -> buf, ...
-    rc = smj_lsd_sort(ctx, (const u64 *)buf, (u64 *)tmp, (u64 *)buf, n, key_only, &res);
+    int rc = smj_lsd_sort(ctx, (const u64 *)buf, (u64 *)tmp, (u64 *)buf, n, key_only, &res);
     if (rc) return rc;
     *sorted = (uint64_t *)res;
     return 0;

@@ -63,8 +63,7 @@ int smjdev_profile_end(char *out, size_t cap);
  * buf and tmp are two n-item device buffers, both clobbered; *sorted is set to whichever
  * of the two holds the result.  key_only != 0 orders by the key (upper 32 bits) only and
  * keeps the input order among equal keys (stable) -- enough for the merge-join and cheaper.
- * algo: 0 = auto, 1 = LSD one-sweep radix passes, 2 = MSD partition + in-shared-memory
- * segment sort (falls back to 1 when a segment does not fit). */
+ * algo: 0 = auto, 1 = LSD one-sweep radix passes over the varying bits (the only sort so far). */
 int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_only, int algo,
                 uint64_t **sorted);
 
