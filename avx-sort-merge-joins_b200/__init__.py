@@ -87,6 +87,8 @@ SIGNATURES = {
     "smjdev_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t]),
     "smjdev_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_size_t]),
     "smjdev_memcpy_d2d": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "smjdev_upload": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "smjdev_download": (C.c_int, [_vp, _vp, C.c_size_t]),
     "smjdev_memset": (C.c_int, [_vp, C.c_int, C.c_size_t]),
     "smjdev_pointer_kind": (C.c_int, [_vp]),
     "smjdev_event_create": (C.c_int, [C.POINTER(_vp)]),

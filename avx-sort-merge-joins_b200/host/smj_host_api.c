@@ -54,7 +54,7 @@ static int stage_in(devbuf_t *b, const void *p, uint64_t n, int copy) {
     b->d = (uint64_t *)smjdev_malloc(n * sizeof(uint64_t));
     if (!b->d) return -1;
     b->owned = 1;
-    if (copy && smjdev_memcpy_h2d(b->d, p, n * sizeof(uint64_t))) return -1;
+    if (copy && smjdev_upload(b->d, p, n * sizeof(uint64_t))) return -1;
     return 0;
 }
 
@@ -380,9 +380,8 @@ static void sort_common(uint64_t **inputptr, uint64_t **outputptr, uint64_t n, i
     }
     uint64_t *da = (uint64_t *)smjdev_malloc(n * 8), *db = (uint64_t *)smjdev_malloc(n * 8);
     uint64_t *dst = placement ? out : in;
-    int failed = !da || !db || smjdev_memcpy_h2d(da, in, n * 8) ||
-                 smjdev_sort(da, db, n, key_only, 0, &sorted) ||
-                 smjdev_memcpy_d2h(dst, sorted, n * 8) || smjdev_sync();
+    int failed = !da || !db || smjdev_upload(da, in, n * 8) ||
+                 smjdev_sort(da, db, n, key_only, 0, &sorted) || smjdev_download(dst, sorted, n * 8);
     smjdev_free(da);
     smjdev_free(db);
     if (failed) {
@@ -478,7 +477,7 @@ static int partition_common(relation_t *input, relation_t *output, uint32_t nbit
         goto done;
     if (dout.owned && n) {
         uint64_t used = offs_h[fanout - 1] + hist_h[fanout - 1];
-        if (smjdev_memcpy_d2h(output->tuples, dout.d, used * 8) || smjdev_sync()) goto done;
+        if (smjdev_download(output->tuples, dout.d, used * 8)) goto done;
     }
     rc = 0;
 done:
@@ -556,7 +555,7 @@ void histogram_memcpy_bench(relation_t **partitions, relation_t *input, relation
              !(dhist = (uint64_t *)smjdev_malloc((1ull << nbits) * 8)) ||
              smjdev_histogram(din.d, n, nbits, 0, 1, dhist) ||
              (n && smjdev_memcpy_d2d(dout.d, din.d, n * 8)) ||
-             (dout.owned && n && smjdev_memcpy_d2h(output->tuples, dout.d, n * 8)) || smjdev_sync();
+             (dout.owned && n && smjdev_download(output->tuples, dout.d, n * 8)) || smjdev_sync();
     stage_free(&din);
     stage_free(&dout);
     smjdev_free(dhist);
@@ -577,7 +576,7 @@ static uint64_t merge_common(const void *a, const void *b, void *out, uint64_t l
     failed = smjdev_init(-1) || stage_in(&da, a, lenA, 1) || stage_in(&db, b, lenB, 1) ||
              stage_in(&dout, out, lenA + lenB, 0) ||
              smjdev_merge(da.d, lenA, db.d, lenB, dout.d, mode) ||
-             (dout.owned && smjdev_memcpy_d2h(out, dout.d, (lenA + lenB) * 8)) || smjdev_sync();
+             (dout.owned && smjdev_download(out, dout.d, (lenA + lenB) * 8)) || smjdev_sync();
     stage_free(&da);
     stage_free(&db);
     stage_free(&dout);
@@ -627,7 +626,7 @@ static uint64_t multiway_common(tuple_t *output, relation_t **parts, uint32_t np
         fail = stage_in(&dout, output, total, 0);
         if (!fail) fail = !(dtmp = (uint64_t *)smjdev_malloc(total * 8));
         if (!fail) fail = smjdev_multiway_merge(dout.d, dtmp, ptrs, lens, nparts, mode);
-        if (!fail && dout.owned) fail = smjdev_memcpy_d2h(output, dout.d, total * 8);
+        if (!fail && dout.owned) fail = smjdev_download(output, dout.d, total * 8);
         if (!fail) fail = smjdev_sync();
     }
     stage_free(&dout);

@@ -284,6 +284,29 @@ def run_single_gpu(args, smj) -> dict:
            "h2d_ms_per_step": sum(h2d_ms[-e2e_steps:]) / e2e_steps,
            "api": "sortmergejoin_multiway(relation_t*, relation_t*, joinconfig_t*) with pinned host buffers"}
 
+    # ---- the same call with ordinary malloc'ed (pageable) relations, as the reference's main.c
+    #      allocates them: goes through the library's threaded staging pipeline
+    try:
+        r_pg = np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+        s_pg = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_uint64)), shape=(n,)).copy()
+        relr_pg, rels_pg = smj.relation_t(r_pg.ctypes.data, n), smj.relation_t(s_pg.ctypes.data, n)
+
+        def pageable_join():
+            res = lib.sortmergejoin_multiway(C.byref(relr_pg), C.byref(rels_pg), C.byref(cfg))
+            assert res and res.contents.totalresults == n
+            libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+            libc.free(C.cast(res, C.c_void_p))
+
+        pageable_join()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pageable_join()
+        pg_s = (time.perf_counter() - t0) / 2
+        e2e["pageable_host_memory"] = {"value": 2 * n / pg_s / 1e6, "unit": UNIT, "ms_per_step": pg_s * 1e3}
+        del r_pg, s_pg
+    except Exception as exc:
+        e2e["pageable_host_memory"] = {"value": None, "error": str(exc)}
+
     # ---- CPU baseline: the reference's own m-way join on this box's host cores
     cpu = None
     if not args.no_cpu_baseline:
