@@ -351,3 +351,42 @@ def test_mway_fast_path_wrong_sample_guess(smj, orc):
     r[n // 3 + 1] = np.uint64(((1 << 30) + 5) << 32 | 1)
     s[n // 5 + 7] = np.uint64(((1 << 30) + 5) << 32 | 2)
     assert _device_mway(smj, r, s) == orc.join_bruteforce(r, s)
+
+
+# ------------------------------------------------------------------------------------ host memory paths
+def test_pageable_relations_use_the_staging_pipeline(smj, orc):
+    """Relations in ordinary malloc'ed memory above the staging threshold (32 MiB): upload through
+    the threaded bounce-buffer pipeline, sort results downloaded the same way."""
+    nr, ns = 4_500_000, 6_000_001
+    r, s = orc.gen_unique(nr, 7), orc.gen_fk(ns, nr, 8)
+    assert r.nbytes > 32 << 20 and s.nbytes > 32 << 20
+    total, st = smj.join_host("multiway", r, s, nthreads=2)
+    assert total == ns
+    exp = orc.join_bruteforce(r, s)
+    assert (st.matches, st.checksum) == exp
+    a, b = s.copy(), np.zeros(ns, dtype=np.uint64)
+    pa, pb = C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)
+    smj.lib.avxsort_tuples(C.byref(pa), C.byref(pb), ns)
+    res = b if pb.value == b.ctypes.data else a
+    assert np.array_equal(res, np.sort(s))
+
+
+def test_reference_style_cli(smj):
+    """The sortmergejoins command line driver (src/main.c) on top of the library."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(smj.LIB_PATH), "sortmergejoins")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(smj.LIB_PATH), exe], check=True, capture_output=True)
+    env = dict(os.environ)
+    env.pop("SMJ_QUIET", None)
+    for algo, extra in (("m-way", []), ("m-pass", ["-n", "4"]), ("mpsm", ["-n", "4"]), ("m-way", ["-d"]),
+                        ("m-way", ["-s", "3000000"])):
+        out = subprocess.run([exe, "-a", algo, "-r", "1000000", "-s", "1000000"] + extra, capture_output=True,
+                             text=True, env=env, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        n_s = 3000000 if "-s" in extra else 1000000
+        assert f"Results = {n_s}. DONE." in out.stdout, out.stdout
+        assert "TUPLES-PER-SECOND" in out.stderr  # the reference's timing line, src/joins/joincommon.c:214-227
+    bad = subprocess.run([exe, "-n", "3", "-r", "1000", "-s", "1000"], capture_output=True, text=True, env=env)
+    assert "power of 2" in bad.stdout and bad.returncode != 0
