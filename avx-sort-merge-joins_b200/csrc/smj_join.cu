@@ -438,6 +438,45 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
         const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
         if (r0 == r1 || s0 == s1) continue;
         if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy hitters: k_big_bucket_join
+        // Fast path, R keys unique inside the bucket (the usual primary-key side): the slot holds
+        // the R item itself (stored complemented, 0 = empty), one exchange per R item and one load
+        // per S item.  A second R item on the same slot sends the bucket down the general path.
+        for (u32 i = lane; i < slots; i += 32) t_sum[i] = 0;
+        __syncwarp();
+        bool dup = false;
+        for (u64 i = r0 + lane; i < r1; i += 128) {  // 4 independent loads in flight per lane
+            u64 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = (i + 32 * u < r1) ? ld_stream(r + i + 32 * u) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i + 32 * u < r1) {
+                    const u32 slot = (u32)(x[u] >> lo_shift) & mask;
+                    dup |= atomicExch(&t_sum[slot], ~x[u]) != 0ull;
+                }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(SMJ_FULL_MASK, dup)) {
+            for (u64 j = s0 + lane; j < s1; j += 128) {
+                u64 y[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) y[u] = (j + 32 * u < s1) ? ld_stream(s + j + 32 * u) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j + 32 * u < s1) {
+                        const u64 v = t_sum[(u32)(y[u] >> lo_shift) & mask];
+                        if (v) {
+                            my_cnt += 1;
+                            my_cks += smj_cks_a(~v) * smj_cks_b(y[u]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        // General path: {count, sum A} per key slot
         for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;  // sums and counts
         __syncwarp();
         for (u64 i = r0 + lane; i < r1; i += 128) {  // 4 independent loads in flight per lane
