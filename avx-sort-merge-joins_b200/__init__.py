@@ -57,11 +57,12 @@ class smj_join_stats_t(C.Structure):  # include/smj_device.h
     _fields_ = [("matches", C.c_uint64), ("checksum", C.c_uint64), ("ms_h2d", C.c_float),
                 ("ms_partition", C.c_float), ("ms_sort", C.c_float), ("ms_merge", C.c_float),
                 ("ms_join", C.c_float), ("ms_total", C.c_float), ("launches", C.c_uint64),
-                ("hbm_bytes", C.c_uint64)]
+                ("hbm_bytes", C.c_uint64), ("path", C.c_uint32), ("repeats", C.c_uint32)]
 
 
 NUMA_RANDOM, NUMA_RING, NUMA_NEXT = 0, 1, 2
 ALGO_MWAY, ALGO_MPASS, ALGO_MPSM = 0, 1, 2
+PATH_GENERAL, PATH_MSD, PATH_MSD_OPT = 0, 1, 2
 
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p

@@ -147,6 +147,33 @@ __device__ __forceinline__ u64 warp_reduce_and(u64 v) {
 
 static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 
+// Key digits of the m-way join's two-level MSD partition, from the OR / AND of the items of R and
+// S (bits = {OR_R, AND_R, OR_S, AND_S}): key bits [lo, hi] vary; level 1 = 9 bits at shift1, level 2
+// = 9 bits at shift2, lbits key bits (at lo_shift) are left inside a bucket.  false when the key
+// domain does not suit the path (fewer than 19 or more than 31 varying bits).
+constexpr int SMJ_MSD_SAMPLE_WORDS = 16 + 2 * 512;  // host copy of the sample (smj_msd_sample)
+struct MsdPlan {
+    int lo, hi;
+    u32 shift1, shift2, lo_shift, lbits;
+};
+__host__ __device__ inline bool smj_msd_plan(const u64 *bits, MsdPlan *p) {
+    const u32 vor = (u32)((bits[0] | bits[2]) >> 32), vand = (u32)((bits[1] & bits[3]) >> 32);
+    const u32 v   = vor & ~vand;
+    if (v == 0) return false;
+    int hi = 31, lo = 0;
+    while (!((v >> hi) & 1u)) hi--;
+    while (!((v >> lo) & 1u)) lo++;
+    const int k = hi - lo + 1;
+    if (k < 19 || k > 31) return false;
+    p->lo       = lo;
+    p->hi       = hi;
+    p->lbits    = (u32)(k - 18);
+    p->shift1   = 32 + (u32)hi - 8;
+    p->shift2   = p->shift1 - 9;
+    p->lo_shift = 32 + (u32)lo;
+    return true;
+}
+
 // The join checksum (DESIGN.md / SURVEY.md 8d): sum over matched pairs of A(r)*B(s) mod 2^64.
 __host__ __device__ __forceinline__ u64 smj_cks_a(u64 r) {
     return (r >> 32) * 0x9E3779B97F4A7C15ull + (r & 0xffffffffull) * 0xC2B2AE3D27D4EB4Full + 1ull;

@@ -30,12 +30,22 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
                        u32 nruns, int mode);
 int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
                       u64 *offsets, u64 *exact_bits);
-int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_hist1, u64 *b, u32 shift2,
-                   u64 *offsets);
+int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
+                   u32 shift2, u64 *offsets);
 int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 *exact_bits);
 int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
                        const u64 *dest_offsets);
 int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
+int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *host);
+u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, u64 *start, u64 *limit, int shrink);
+u64 smj_msd_tile_items();
+u64 smj_msd_alloc2(u64 n);
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, const u64 *start,
+                       const u64 *limit, u64 dump, u64 *d_tab, u32 *d_flag, u32 kmask, u32 kref,
+                       u32 *d_kflag);
+int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
+                       u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink);
+int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
 
 namespace {
 
@@ -417,9 +427,11 @@ namespace {
 constexpr int BJ_WARPS = 8;
 
 __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__restrict__ r,
-                                                               const u64 *__restrict__ roffs,
+                                                               const u64 *__restrict__ rs_,
+                                                               const u64 *__restrict__ re_,
                                                                const u64 *__restrict__ s,
-                                                               const u64 *__restrict__ soffs,
+                                                               const u64 *__restrict__ ss_,
+                                                               const u64 *__restrict__ se_,
                                                                u32 nbuckets, u32 lo_shift, u32 lbits,
                                                                u64 big, u32 *next_bucket,
                                                                u64 *__restrict__ acc) {
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
         if (lane == 0) b = atomicAdd(next_bucket, 1u);
         b = __shfl_sync(SMJ_FULL_MASK, b, 0);
         if (b >= nbuckets) break;
-        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
         if (r0 == r1 || s0 == s1) continue;
         if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy hitters: k_big_bucket_join
         // Fast path, R keys unique inside the bucket (the usual primary-key side): the slot holds
@@ -579,9 +591,11 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
 // Same join for 11..13 remaining key bits (key domains up to 2^31): the 2^L-slot table no longer
 // fits a warp's share of shared memory, so a whole CTA owns a bucket.
 __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__ r,
-                                                         const u64 *__restrict__ roffs,
+                                                         const u64 *__restrict__ rs_,
+                                                         const u64 *__restrict__ re_,
                                                          const u64 *__restrict__ s,
-                                                         const u64 *__restrict__ soffs, u32 nbuckets,
+                                                         const u64 *__restrict__ ss_,
+                                                         const u64 *__restrict__ se_, u32 nbuckets,
                                                          u32 lo_shift, u32 lbits, u32 *next_bucket,
                                                          u64 *__restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__
         __syncthreads();
         const u32 b = s_b;
         if (b >= nbuckets) break;
-        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
         if (r0 == r1 || s0 == s1) continue;
         for (u32 i = threadIdx.x; i < slots * 3 / 2; i += 256) ((u64 *)t_sum)[i] = 0;
         __syncthreads();
@@ -640,13 +654,15 @@ __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__
 // listed by k_collect_big and joined by ALL warps of the grid together: every warp builds the
 // (small) R table of the bucket and takes an equal slice of its S side.
 namespace {
-__global__ void __launch_bounds__(256) k_collect_big(const u64 *__restrict__ roffs,
-                                                     const u64 *__restrict__ soffs, u32 nbuckets,
+__global__ void __launch_bounds__(256) k_collect_big(const u64 *__restrict__ rs_,
+                                                     const u64 *__restrict__ re_,
+                                                     const u64 *__restrict__ ss_,
+                                                     const u64 *__restrict__ se_, u32 nbuckets,
                                                      u64 big, u64 rmax, u32 *__restrict__ list,
                                                      u32 *__restrict__ info /* [0] count, [1] unsupported */) {
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbuckets) return;
-    const u64 nr = roffs[b + 1] - roffs[b], ns = soffs[b + 1] - soffs[b];
+    const u64 nr = re_[b] - rs_[b], ns = se_[b] - ss_[b];
     if (nr == 0 || ns == 0) return;
     if (nr > big || ns > big) {
         if (nr > rmax) atomicExch(&info[1], 1u);  // both sides heavy: leave it to the general path
@@ -655,9 +671,11 @@ __global__ void __launch_bounds__(256) k_collect_big(const u64 *__restrict__ rof
 }
 
 __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__restrict__ r,
-                                                                   const u64 *__restrict__ roffs,
+                                                                   const u64 *__restrict__ rs_,
+                                                                   const u64 *__restrict__ re_,
                                                                    const u64 *__restrict__ s,
-                                                                   const u64 *__restrict__ soffs,
+                                                                   const u64 *__restrict__ ss_,
+                                                                   const u64 *__restrict__ se_,
                                                                    const u32 *__restrict__ list,
                                                                    const u32 *__restrict__ info,
                                                                    u32 lo_shift, u32 lbits,
@@ -672,7 +690,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
     u64       my_cnt = 0, my_cks = 0;
     for (u32 q = 0; q < nbig; q++) {
         const u32 b  = list[q];
-        const u64 r0 = roffs[b], r1 = roffs[b + 1], s0 = soffs[b], s1 = soffs[b + 1];
+        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
         const u64 len = s1 - s0, j0 = s0 + (len * gw) / nw, j1 = s0 + (len * (gw + 1)) / nw;
         if (j0 == j1) continue;
         for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;
@@ -711,23 +729,32 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
 }
 }  // namespace
 
-// Join of the 2^18 second-level buckets (bR/offR, bS/offS as written by smj_msd_pass_b).
-// d_state (device, 8 x u64, initialised by the caller to {0, 0, 0, ~0, 0, ~0, 0, 0}):
-//   [1] bucket counter, [2..5] exact OR / AND of R and S (filled by the histogram passes),
-//   [6] = {number of heavy buckets, flag "a bucket is heavy on both sides"}.
-// h_state receives a copy (the call synchronises once).  *done = 0 when the buckets do not suit
-// the bucket kernels (the caller then takes the general sort + scan path).
-static int bucket_stage(SmjCtx *ctx, const u64 *bR, const u64 *offR, u64 nr, const u64 *bS,
-                        const u64 *offS, u64 ns, u32 lo_shift, u32 lbits, u64 *d_state, u64 *h_state,
-                        u32 *d_list, u64 *acc, int *done, PhaseTimer *tm, int *t_mid) {
-    constexpr u64 BIG = 1u << 16, RMAX = 1u << 16;  // bucket sizes: cooperative above BIG
-    const u32     nb2 = 512u * 512u;
-    *done             = 0;
-    SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, offR, offS, nb2, BIG, RMAX, d_list,
-               (u32 *)(d_state + 6));
-    SMJ_CHECK(cudaMemcpyAsync(h_state, d_state, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    if (tm && t_mid) *t_mid = tm->mark();
-    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+// Buckets of one relation after the second partitioning level: bucket q is items[starts[q] ..
+// ends[q]).  An exact pass B leaves them back to back (ends = starts + 1 of one offsets array), an
+// optimistic one in fixed slots.
+struct BucketSet {
+    const u64 *items, *starts, *ends;
+    u64        n;
+};
+
+// classification of the 2^18 bucket pairs: heavy ones (more than BIG tuples on a side) are listed
+// for the cooperative kernel; d_state[6] = {count, flag "heavy on both sides"}
+constexpr u64 BJ_BIG = 1u << 16, BJ_RMAX = 1u << 16;
+static int bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u64 *d_state, u32 *d_list) {
+    const u32 nb2 = 512u * 512u;
+    SMJ_CHECK(cudaMemsetAsync(d_state + 6, 0, 8, ctx->stream));
+    SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, R.starts, R.ends, S.starts, S.ends, nb2, BJ_BIG, BJ_RMAX,
+               d_list, (u32 *)(d_state + 6));
+    return 0;
+}
+
+// Join of the 2^18 bucket pairs.  h_state: host copy of d_state taken after bucket_collect
+// ([6] = heavy-bucket info).  *done = 0 when the buckets do not suit the bucket kernels (the caller
+// then takes the general sort + scan path).  d_state[1] is the bucket counter (zero on entry).
+static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
+                       u64 *d_state, const u64 *h_state, const u32 *d_list, u64 *acc, int *done) {
+    const u32 nb2 = 512u * 512u;
+    *done         = 0;
     const u32 nbig = (u32)(h_state[6] & 0xffffffffu), unsupported = (u32)(h_state[6] >> 32);
     u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
@@ -743,9 +770,9 @@ static int bucket_stage(SmjCtx *ctx, const u64 *bR, const u64 *offR, u64 nr, con
             smem_set_cta = smem;
         }
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / smem));
-        SMJ_ITEMS(ctx, nr + ns);
-        SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, bR, offR, bS, offS, nb2,
-                   lo_shift, lbits, d_next, acc);
+        SMJ_ITEMS(ctx, R.n + S.n);
+        SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, R.items, R.starts, R.ends,
+                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, d_next, acc);
         *done = 1;
         return 0;
     }
@@ -762,33 +789,16 @@ static int bucket_stage(SmjCtx *ctx, const u64 *bR, const u64 *offR, u64 nr, con
         smem_set = smem;
     }
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
-    SMJ_ITEMS(ctx, nr + ns);
-    SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS, offS, nb2,
-               lo_shift, lbits, BIG, d_next, acc);
+    SMJ_ITEMS(ctx, R.n + S.n);
+    SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts, R.ends,
+               S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
     if (nbig)
-        SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, bR, offR, bS,
-                   offS, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
+        SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts,
+                   R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
     *done = 1;
     return 0;
 }
 
-// The key digits of the MSD plan from the OR / AND of the keys of R and S (bits = {OR_R, AND_R,
-// OR_S, AND_S} of the items).  Returns false when the key domain does not suit the fast path.
-static bool msd_plan(const u64 *bits, int *lo, int *hi, u32 *shift1, u32 *shift2, u32 *lo_shift,
-                     u32 *lbits) {
-    const u32 vor = (u32)((bits[0] | bits[2]) >> 32), vand = (u32)((bits[1] & bits[3]) >> 32);
-    const u32 v   = vor & ~vand;
-    if (v == 0) return false;
-    *hi         = 31 - __builtin_clz(v);
-    *lo         = __builtin_ctz(v);
-    const int k = *hi - *lo + 1;
-    if (k < 19 || k > 31) return false;
-    *lbits    = (u32)(k - 18);
-    *shift1   = 32 + (u32)*hi - 8;
-    *shift2   = *shift1 - 9;
-    *lo_shift = 32 + (u32)*lo;
-    return true;
-}
 // no key bit outside [lo, hi] may vary in R or S (exact = {OR_R, AND_R, OR_S, AND_S})
 static bool msd_plan_holds(const u64 *exact, int lo, int hi) {
     const u32 xor_ = (u32)((exact[0] | exact[2]) >> 32), xand = (u32)((exact[1] & exact[3]) >> 32);
@@ -796,47 +806,150 @@ static bool msd_plan_holds(const u64 *exact, int lo, int hi) {
     return ((xor_ & ~xand) & ~range) == 0;
 }
 
+// d_state layout (16 x u64): [1] bucket counter, [2..5] exact OR / AND of R and S, [6] heavy-bucket
+// info, [8..11] overflow flags of the optimistic passes {R level 1, S level 1, R level 2, S level 2},
+// [12..13] first-level buckets of R / S whose second level was repeated exactly on the device,
+// [14..15] R / S hold a key outside the sampled key range (optimistic first pass)
+static const u64 MSD_STATE_INIT[16] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull,
+                                       0ull, 0ull, 0ull, 0ull,  0ull, 0ull,  0ull, 0ull};
+
+// One relation of the m-way fast path.  Optimistic: no histogram passes (sampled capacities, fixed
+// slots); exact: histogram + scatter per level.
+struct MsdRel {
+    const u64 *in;
+    u64        n;
+    u64       *a, *b;          // level-1 / level-2 outputs
+    u64        alloc1, alloc2; // capacities of a and b in items, dump areas excluded
+    u64       *starts, *ends;  // 2^18 (+1) entries each
+    u64       *d_tab, *d_counts;
+    bool       opt1, opt2;     // level 1 / level 2 ran optimistically
+    BucketSet set() const { return BucketSet{b, starts, opt2 ? ends : starts + 1, n}; }
+};
+
 // m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
 // fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
 // do not suit it; the caller then takes the general sort + scan path.
-static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *aR, u64 *bR, u64 *aS,
-                    u64 *bS, u64 *acc, int *used, PhaseTimer &tm, int &t_part, int &t_sort,
-                    int &t_join) {
+//
+// The partition passes run OPTIMISTICALLY: one sample of R and S gives the key range, the
+// first-level bin capacities and a skew test; both levels then scatter without a histogram pass
+// into regions with slack, the exact OR / AND of the keys is collected on the way.  Before the
+// join kernel is launched the host checks the overflow flags and the key range once; what did not
+// hold is repeated exactly (histogram first), so the result never depends on the guess.
+static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc, int *used,
+                    PhaseTimer &tm, int &t_part, int &t_sort, int &t_join, u64 *scratch_bytes,
+                    u32 *path, u32 *repeats) {
     *used = 0;
     if (nr + ns < (1u << 20)) return 0;  // 2^18 buckets only pay off on large inputs
-    u64 bits[4];
-    // The key range is guessed from a sample (5 us instead of a full read of R and S); the first
-    // histogram pass computes the exact OR / AND on the side and the guess is verified before the
-    // result is used.
-    int rc = smj_key_bits_sampled(ctx, r, nr, s, ns, bits);
+    const char *mode_env = getenv("SMJ_MSD_MODE");  // "exact" disables the optimistic passes
+    const int   mode     = (mode_env && mode_env[0] == 'e') ? 0 : 1;
+    // test hooks: SMJ_MSD_TEST=shrink1 / shrink2 under-sizes the first / second level regions so
+    // that the overflow -> exact repeat paths run on ordinary inputs
+    const char *hook    = getenv("SMJ_MSD_TEST");
+    const int   shrink1 = hook && !strcmp(hook, "shrink1"), shrink2 = hook && !strcmp(hook, "shrink2");
+    const u32 max_sectors = 1u << 18;
+    std::vector<u64> samp(SMJ_MSD_SAMPLE_WORDS);
+    int rc = smj_msd_sample(ctx, r, nr, s, ns, max_sectors, samp.data());
     if (rc) return rc;
-    int lo, hi;
-    u32 shift1, shift2, lo_shift, lbits;
-    if (!msd_plan(bits, &lo, &hi, &shift1, &shift2, &lo_shift, &lbits)) return 0;
-    const u32  nb2 = 512u * 512u;
+    MsdPlan pl;
+    if (!smj_msd_plan(samp.data(), &pl)) return 0;
+    const u32  nb2  = 512u * 512u;
+    const u64  tile = smj_msd_tile_items();
     SmjScratch sc(ctx);
-    u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
-    u64 *d_state = (u64 *)sc.get(64);
+    u64 *d_state = (u64 *)sc.get(128);
     u32 *d_list  = (u32 *)sc.get((size_t)nb2 * 4);
-    if (!offR || !offS || !d_state || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
-    const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d_state, init, 64, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = smj_msd_partition(ctx, r, nr, aR, bR, shift1, shift2, offR, d_state + 2))) return rc;
-    if ((rc = smj_msd_partition(ctx, s, ns, aS, bS, shift1, shift2, offS, d_state + 4))) return rc;
-    u64 h[8];
-    int done = 0, t_mid = -1;
-    if ((rc = bucket_stage(ctx, bR, offR, nr, bS, offS, ns, lo_shift, lbits, d_state, h, d_list, acc, &done,
-                           &tm, &t_mid)))
-        return rc;
+    if (!d_state || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
+    SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
+
+    // key bits outside [lo, hi] are constant in the sample: every key must carry the same value there
+    const u32 krange = (pl.hi == 31 ? 0xffffffffu : ((1u << (pl.hi + 1)) - 1)) & ~((1u << pl.lo) - 1);
+    const u32 kmask = ~krange, kref = (u32)((samp[1] & samp[3]) >> 32) & kmask;
+    MsdRel rel[2] = {{r, nr}, {s, ns}};
+    u64    h_start[2][512], h_limit[2][512];
+    for (int q = 0; q < 2; q++) {
+        MsdRel &x = rel[q];
+        // a heavy 18-bit bucket in the sample (expected count: a handful) means equal slots will
+        // not hold at the second level; the first level adapts its capacities to any skew
+        const u64 nsamp = samp[8 + q], maxsub = samp[6 + q];
+        const double expect = (double)nsamp / (double)nb2;
+        x.opt1 = mode && x.n >= (1u << 20);
+        x.opt2 = x.opt1 && (double)maxsub <= 4.0 * expect + 24.0;
+        x.alloc1 = x.n;
+        if (x.opt1) x.alloc1 = smj_msd_caps1(samp.data() + 16 + 512 * q, nsamp, x.n, h_start[q], h_limit[q], shrink1);
+        x.alloc2 = x.opt2 ? smj_msd_alloc2(x.n) : x.n;
+        x.a      = (u64 *)sc.get((std::max(x.alloc1, x.n) + tile) * 8);
+        x.b      = (u64 *)sc.get((std::max(x.alloc2, x.n) + tile) * 8);
+        x.starts = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
+        x.ends   = (u64 *)sc.get((size_t)nb2 * 8);
+        x.d_tab  = (u64 *)sc.get(3 * 512 * 8);
+        x.d_counts = (u64 *)sc.get(512 * 8);
+        if (!x.a || !x.b || !x.starts || !x.ends || !x.d_tab || !x.d_counts)
+            return smj_fail_msg("smjdev_join: out of device memory");
+    }
+    for (int q = 0; q < 2; q++) {
+        MsdRel &x = rel[q];
+        u32 *flags = (u32 *)(d_state + 8);  // one u64 slot per flag, low word used
+        if (x.opt1) {
+            if ((rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, h_start[q], h_limit[q], x.alloc1,
+                                         x.d_tab, flags + 2 * q, kmask, kref, flags + 12 + 2 * q)))
+                return rc;
+            if (x.opt2) {
+                if ((rc = smj_msd_pass_b_opt(ctx, x.a, x.n, x.d_tab, x.b, x.alloc2, pl.shift2, x.starts,
+                                             x.ends, x.d_counts, flags + 4 + 2 * q, d_state + 12 + q, shrink2)))
+                    return rc;
+            } else {
+                if ((rc = smj_msd_counts_opt(ctx, x.d_tab, x.d_counts))) return rc;
+                if ((rc = smj_msd_pass_b(ctx, x.a, x.n, x.d_counts, x.d_tab + 512, x.b, pl.shift2, x.starts)))
+                    return rc;
+            }
+        } else if ((rc = smj_msd_partition(ctx, x.in, x.n, x.a, x.b, pl.shift1, pl.shift2, x.starts,
+                                           d_state + 2 + 2 * q)))
+            return rc;
+    }
+    u64 h[16];
+    if ((rc = bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
+    SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    int t_mid = tm.mark();
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    // the sample missed key bits that vary (seen by an exact histogram pass or by the key check)
+    if (!msd_plan_holds(h + 2, pl.lo, pl.hi) || h[14] || h[15]) return 0;
+    bool redo = false;
+    *path     = (rel[0].opt1 || rel[1].opt1) ? SMJ_PATH_MSD_OPT : SMJ_PATH_MSD;
+    for (int q = 0; q < 2; q++) {
+        MsdRel &x = rel[q];
+        const bool over1 = x.opt1 && h[8 + q], over2 = x.opt2 && h[10 + q];
+        if (over1) {  // the whole relation again, exactly (a and b are large enough)
+            if ((rc = smj_msd_partition(ctx, x.in, x.n, x.a, x.b, pl.shift1, pl.shift2, x.starts, nullptr)))
+                return rc;
+            x.opt1 = x.opt2 = false;
+            redo = true;
+            *repeats += 1;
+        } else if (over2) {  // the slots did not fit b: level 2 again from the intact level-1 output
+            if ((rc = smj_msd_pass_b(ctx, x.a, x.n, x.d_counts, x.d_tab + 512, x.b, pl.shift2, x.starts)))
+                return rc;
+            x.opt2 = false;
+            redo   = true;
+            *repeats += 1;
+        } else if (x.opt2)
+            *repeats += (u32)h[12 + q];
+    }
+    if (redo) {
+        if ((rc = bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
+        SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
+        t_mid = tm.mark();
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     t_part = t_sort = t_mid;  // the in-partition sort is fused into the join kernel
-    if (!msd_plan_holds(h + 2, lo, hi)) {
-        // the sample missed key bits that do vary: whatever the bucket kernels added is void
+    int done = 0;
+    if ((rc = bucket_join(ctx, rel[0].set(), rel[1].set(), pl.lo_shift, pl.lbits, d_state, h, d_list, acc,
+                          &done)))
+        return rc;
+    if (!done) {
         SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
         return 0;
     }
-    if (!done) return 0;
     t_join = tm.mark();
     *used  = 1;
+    if (scratch_bytes) *scratch_bytes = sc.bytes;
     return 0;
 }
 
@@ -861,24 +974,31 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
     int t_part = t0, t_sort = t0, t_merge = t0, t_join = t0, rc = 0;
 
+    u64 msd_bytes = 0;
+    u32 path = SMJ_PATH_GENERAL, repeats = 0;
     if (nr && ns) {
-        u64 *aR = (u64 *)sc.get(nr * 8), *bR = (u64 *)sc.get(nr * 8);
-        u64 *aS = (u64 *)sc.get(ns * 8), *bS = (u64 *)sc.get(ns * 8);
-        if (!aR || !bR || !aS || !bS) return smj_fail_msg("smjdev_join: out of device memory");
+        u64 *aR = nullptr, *bR = nullptr, *aS = nullptr, *bS = nullptr;
+        auto ping_pong = [&]() {
+            aR = (u64 *)sc.get(nr * 8), bR = (u64 *)sc.get(nr * 8);
+            aS = (u64 *)sc.get(ns * 8), bS = (u64 *)sc.get(ns * 8);
+            return aR && bR && aS && bS;
+        };
         if (algo == SMJ_ALGO_MWAY) {
             // range partition + in-partition sort == a global key sort on one GPU: the sorted
             // partitions are disjoint key ranges, so no run merging is needed
             // (the reference's nthreads == 1 path, sortmergejoin_multiway.c:476-489)
             int used = 0;
-            const char *path = getenv("SMJ_MWAY_PATH");  // "lsd" forces the general path
-            if (!(path && path[0] == 'l')) {
-                if ((rc = mway_msd(ctx, r, nr, s, ns, aR, bR, aS, bS, acc, &used, tm, t_part, t_sort,
-                                   t_join)))
+            const char *force = getenv("SMJ_MWAY_PATH");  // "lsd" forces the general path
+            if (!(force && force[0] == 'l')) {
+                if ((rc = mway_msd(ctx, r, nr, s, ns, acc, &used, tm, t_part, t_sort, t_join, &msd_bytes,
+                                   &path, &repeats)))
                     return rc;
                 t_merge = t_sort;
             }
+            if (!used) path = SMJ_PATH_GENERAL;
             if (!used) {
                 u64 *sr = nullptr, *ss = nullptr;
+                if (!ping_pong()) return smj_fail_msg("smjdev_join: out of device memory");
                 SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
                 t_part = tm.mark();
                 if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
@@ -891,6 +1011,7 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             // sorted runs, then pairwise merge passes (sortmergejoin_multipass.c:410-708)
             std::vector<const u64 *> pr, ps;
             std::vector<u64>         lr, ls;
+            if (!ping_pong()) return smj_fail_msg("smjdev_join: out of device memory");
             t_part = tm.mark();
             if ((rc = sort_runs(ctx, r, aR, bR, nr, nruns, pr, lr))) return rc;
             if ((rc = sort_runs(ctx, s, aS, bS, ns, nruns, ps, ls))) return rc;
@@ -911,6 +1032,7 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             u64 *sr = nullptr;
             std::vector<const u64 *> ps;
             std::vector<u64>         ls;
+            if (!ping_pong()) return smj_fail_msg("smjdev_join: out of device memory");
             t_part = tm.mark();
             if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
             if ((rc = sort_runs(ctx, s, aS, bS, ns, nruns, ps, ls))) return rc;
@@ -934,7 +1056,9 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     stats->ms_join      = tm.ms(t_merge, t_join);
     stats->ms_total     = tm.ms(t0, t_end);
     stats->launches     = ctx->launches - launches0;
-    stats->hbm_bytes    = sc.bytes;
+    stats->hbm_bytes    = sc.bytes + msd_bytes;
+    stats->path         = path;
+    stats->repeats      = repeats;
     return 0;
 }
 
@@ -996,22 +1120,24 @@ extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512
     if (nr && ns) {
         u64 *bR = (u64 *)sc.get(nr * 8), *bS = (u64 *)sc.get(ns * 8);
         u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
-        u64 *d_h1 = (u64 *)sc.get(2 * 512 * 8), *d_state = (u64 *)sc.get(64);
+        u64 *d_h1 = (u64 *)sc.get(2 * 512 * 8), *d_state = (u64 *)sc.get(128);
         u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4);
         if (!bR || !bS || !offR || !offS || !d_h1 || !d_state || !d_list)
             return smj_fail_msg("smjdev_join_level1: out of device memory");
-        const u64 init[8] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull};
-        SMJ_CHECK(cudaMemcpyAsync(d_state, init, 64, cudaMemcpyHostToDevice, ctx->stream));
+        SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
         SMJ_CHECK(cudaMemcpyAsync(d_h1, rcounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
         SMJ_CHECK(cudaMemcpyAsync(d_h1 + 512, scounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
         int rc;
-        if ((rc = smj_msd_pass_b(ctx, r, nr, d_h1, bR, shift2, offR))) return rc;
-        if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, bS, shift2, offS))) return rc;
-        u64 h[8];
+        if ((rc = smj_msd_pass_b(ctx, r, nr, d_h1, nullptr, bR, shift2, offR))) return rc;
+        if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, nullptr, bS, shift2, offS))) return rc;
+        const BucketSet R = {bR, offR, offR + 1, nr}, S = {bS, offS, offS + 1, ns};
+        u64 h[16];
         int done = 0;
-        if ((rc = bucket_stage(ctx, bR, offR, nr, bS, offS, ns, lo_shift, lbits, d_state, h, d_list, acc,
-                               &done, &tm, &t_part)))
-            return rc;
+        if ((rc = bucket_collect(ctx, R, S, d_state, d_list))) return rc;
+        SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
+        t_part = tm.mark();
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+        if ((rc = bucket_join(ctx, R, S, lo_shift, lbits, d_state, h, d_list, acc, &done))) return rc;
         if (!done) {
             // heavy on both sides: general path on the same items (partitioning does not matter to it)
             u64 *aR = (u64 *)sc.get(nr * 8), *aS = (u64 *)sc.get(ns * 8), *sr = nullptr, *ss = nullptr;

@@ -15,6 +15,7 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -511,10 +512,60 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // AGG: rank through warp aggregation (match.any) instead of one atomic per lane; for bucket
 // functions with few bins (range partitioning over the GPUs), where per-lane atomics would all
 // hit the same few counters.
-template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false>
+// Bin capacity policies of the unstable pass.  With exact bin starts (a histogram pass ran first)
+// there is nothing to check (NoLimit).  The OPTIMISTIC passes of the m-way join run without a
+// histogram: every bin owns a region whose capacity was estimated from a sample, a tile whose
+// reservation does not fit stores that bin's items into a dump area instead and raises *flag; the
+// host then repeats the pass exactly (histogram first).  limit(b) = one past the last item index
+// bin b may use.
+struct NoLimit {
+    static constexpr bool on = false, keys = false;
+    __device__ __forceinline__ u64 operator()(u32) const { return ~0ull; }
+    __device__ __forceinline__ u64 dump_at() const { return 0; }
+    __device__ __forceinline__ void raise() const {}
+    __device__ __forceinline__ u32 key_bad(u64) const { return 0; }
+    __device__ __forceinline__ void raise_key() const {}
+};
+// first level: limit[b] from an array.  It also verifies the sampled key range on the way: every
+// key must agree with kref on the bit positions kmask (the positions the digit plan treats as
+// constant); one that does not raises *kflag and the host drops the plan.
+struct LimitArray {
+    static constexpr bool on = true, keys = true;
+    const u64 *lim;
+    u64        dump;  // item index of a TILE-sized dump area in out
+    u32       *flag;
+    u32        kmask, kref;
+    u32       *kflag;
+    __device__ __forceinline__ u64 operator()(u32 b) const { return lim[b]; }
+    __device__ __forceinline__ u64 dump_at() const { return dump; }
+    __device__ __forceinline__ void raise() const { *flag = 1u; }
+    __device__ __forceinline__ u32 key_bad(u64 x) const { return ((u32)(x >> 32) ^ kref) & kmask; }
+    __device__ __forceinline__ void raise_key() const { *kflag = 1u; }
+};
+// second level: the 512 sub-buckets of first-level bucket `bucket` are slots of cap2[bucket] items
+// from base2[bucket] on (read when needed: once per thread and tile); a slot may be used in full
+// except under the test hook that provokes overflows (shrink)
+struct LimitSlots {
+    static constexpr bool on = true, keys = false;
+    const u64 *base2, *cap2;
+    u32        bucket, shrink;
+    u64        dump;
+    u32       *flag;
+    __device__ __forceinline__ u64 operator()(u32 b) const {
+        const u64 cap = cap2[bucket];
+        return base2[bucket] + (u64)b * cap + (shrink ? cap / 4 : cap);
+    }
+    __device__ __forceinline__ u64 dump_at() const { return dump; }
+    __device__ __forceinline__ void raise() const { flag[bucket] = 1u; }
+    __device__ __forceinline__ u32 key_bad(u64) const { return 0; }
+    __device__ __forceinline__ void raise_key() const {}
+};
+
+template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit>
 __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
                                               const F &fn, u64 *cursors, u32 tile, u32 valid,
-                                              u64 *s_items, u32 *s_cnt, u64 *s_goff, u32 *s_wsum) {
+                                              u64 *s_items, u32 *s_cnt, u64 *s_goff, u32 *s_wsum,
+                                              const LIM &lim = LIM()) {
     constexpr int NB   = 1 << BITS;
     constexpr int TILE = THREADS * IPT;
     constexpr int BPT  = (NB + THREADS - 1) / THREADS;
@@ -528,6 +579,13 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
 #pragma unroll
     for (int j = 0; j < IPT; j++)
         item[j] = (FULL || j * THREADS + threadIdx.x < valid) ? ld_stream(src + j * THREADS) : ~0ull;
+    if (LIM::keys) {
+        u32 bad = 0;
+#pragma unroll
+        for (int j = 0; j < IPT; j++)
+            if (FULL || j * THREADS + threadIdx.x < valid) bad |= lim.key_bad(item[j]);
+        if (bad) lim.raise_key();
+    }
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
         u32 r = 0;  // rank inside the tile's bin; items past the end of the input take no part
@@ -560,7 +618,13 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
         cntb[q]     = (b < NB) ? s_cnt[b] : 0u;
         gbase[q]    = 0;
         tsum += cntb[q];
-        if (b <= last_bin && cntb[q]) gbase[q] = atomicAdd(&cursors[b], (u64)cntb[q]);
+        if (b <= last_bin && cntb[q]) {
+            gbase[q] = atomicAdd(&cursors[b], (u64)cntb[q]);
+            if (LIM::on && gbase[q] + cntb[q] > lim(b)) {  // does not fit: dump + tell the host
+                gbase[q] = lim.dump_at();
+                lim.raise();
+            }
+        }
     }
     u32 incl = tsum;
 #pragma unroll
@@ -605,10 +669,12 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
     }
 }
 
-template <int THREADS, int IPT, int BITS, class F, bool AGG>
+template <int THREADS, int IPT, int BITS, class F, bool AGG, class LIM>
 __global__ void __launch_bounds__(THREADS, 2)
-    k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, F fn,
-                        u64 *cursors /* [NB], initialised to the start of every bin */) {
+    k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n,
+                        const __grid_constant__ F fn,
+                        u64 *cursors /* [NB], initialised to the start of every bin */,
+                        const __grid_constant__ LIM lim) {
     constexpr int NB   = 1 << BITS;
     constexpr int TILE = THREADS * IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -621,28 +687,28 @@ __global__ void __launch_bounds__(THREADS, 2)
     const u32 tile   = blockIdx.x;
     const u64 remain = n - (u64)tile * TILE;
     if (remain >= (u64)TILE)
-        unstable_tile<THREADS, IPT, BITS, F, true, AGG>(in, out, fn, cursors, tile, (u32)TILE,
-                                                        s_items, s_cnt, s_goff, s_wsum);
+        unstable_tile<THREADS, IPT, BITS, F, true, AGG, LIM>(in, out, fn, cursors, tile, (u32)TILE,
+                                                             s_items, s_cnt, s_goff, s_wsum, lim);
     else
-        unstable_tile<THREADS, IPT, BITS, F, false, AGG>(in, out, fn, cursors, tile, (u32)remain,
-                                                         s_items, s_cnt, s_goff, s_wsum);
+        unstable_tile<THREADS, IPT, BITS, F, false, AGG, LIM>(in, out, fn, cursors, tile, (u32)remain,
+                                                              s_items, s_cnt, s_goff, s_wsum, lim);
 }
 
 // bases: [NB] start of every bin; it is used as the cursor array and is CONSUMED (on return
 // bases[b] is the end of bin b)
-template <int BITS, class F, bool AGG = false>
-int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases) {
+template <int BITS, class F, bool AGG = false, class LIM = NoLimit>
+int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim = LIM()) {
     constexpr int    THREADS = 512, IPT = 16, NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM    = (size_t)TILE * 8 + NB * 4 + NB * 8;
     static int       attr_gen = -1;
     if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F, AGG>,
+        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F, AGG, LIM>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_gen = ctx->generation;
     }
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F, AGG>), (unsigned)div_up(n, TILE),
-               THREADS, SMEM, in, out, n, fn, bases);
+    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F, AGG, LIM>), (unsigned)div_up(n, TILE),
+               THREADS, SMEM, in, out, n, fn, bases, lim);
     return 0;
 }
 
@@ -1012,13 +1078,16 @@ __global__ void __launch_bounds__(512) k_msd_hist1(const u64 *__restrict__ in, u
     }
 }
 
-// per pass-A bucket: first tile index and first item index (exclusive scans over the 512 buckets)
-__global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restrict__ hist1,
+// per pass-A bucket: first tile index (exclusive scan of the tile counts), first item index and
+// item count.  starts == null: the buckets lie back to back (exclusive scan of the counts).
+__global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restrict__ counts,
+                                                            const u64 *__restrict__ starts,
                                                             u64 *__restrict__ tile_prefix,
-                                                            u64 *__restrict__ bucket_start) {
+                                                            u64 *__restrict__ bucket_start,
+                                                            u64 *__restrict__ bucket_count) {
     __shared__ u64 s_t[MSD_NB], s_c[MSD_NB];
     const int      b = threadIdx.x;
-    const u64      c = hist1[b], t = (c + MSD_TILE - 1) / MSD_TILE;
+    const u64      c = counts[b], t = (c + MSD_TILE - 1) / MSD_TILE;
     s_t[b]           = t;
     s_c[b]           = c;
     __syncthreads();
@@ -1030,39 +1099,39 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restric
         __syncthreads();
     }
     tile_prefix[b]  = s_t[b] - t;
-    bucket_start[b] = s_c[b] - c;
-    if (b == MSD_NB - 1) {
-        tile_prefix[MSD_NB]  = s_t[b];
-        bucket_start[MSD_NB] = s_c[b];
-    }
+    bucket_start[b] = starts ? starts[b] : s_c[b] - c;
+    bucket_count[b] = c;
+    if (b == MSD_NB - 1) tile_prefix[MSD_NB] = s_t[b];
 }
 
 // Which pass-A bucket does tile `tile` belong to, and which items does it cover?  Called by all
 // MSD_THREADS (== number of buckets) threads of a CTA: thread b tests bucket b, so the lookup is
 // one coalesced load instead of a ten-step dependent binary search per tile.
 __device__ __forceinline__ void msd_locate(const u64 *__restrict__ tile_prefix,
-                                           const u64 *__restrict__ bucket_start, u64 tile,
+                                           const u64 *__restrict__ bucket_start,
+                                           const u64 *__restrict__ bucket_count, u64 tile,
                                            u32 *s_bucket, u64 *s_start, u32 *s_valid) {
     const u32 b  = threadIdx.x;
     const u64 t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
     if (b == 0) *s_valid = 0;  // stays 0 when the tile lies past the last bucket
     __syncthreads();
     if (t0 <= tile && tile < t1) {  // exactly one non-empty bucket matches
-        const u64 start = bucket_start[b] + (tile - t0) * (u64)MSD_TILE;
+        const u64 first = bucket_start[b], start = first + (tile - t0) * (u64)MSD_TILE;
         *s_bucket       = b;
         *s_start        = start;
-        *s_valid        = (u32)min((u64)MSD_TILE, bucket_start[b + 1] - start);
+        *s_valid        = (u32)min((u64)MSD_TILE, first + bucket_count[b] - start);
     }
 }
 
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict__ in,
                                                            const u64 *__restrict__ tile_prefix,
                                                            const u64 *__restrict__ bucket_start,
+                                                           const u64 *__restrict__ bucket_count,
                                                            FieldFn fn2, u64 *__restrict__ hist2) {
     __shared__ u32 sh[MSD_NB];
     __shared__ u32 s_bucket, s_valid;
     __shared__ u64 s_start;
-    msd_locate(tile_prefix, bucket_start, blockIdx.x, &s_bucket, &s_start, &s_valid);
+    msd_locate(tile_prefix, bucket_start, bucket_count, blockIdx.x, &s_bucket, &s_start, &s_valid);
     sh[threadIdx.x] = 0;
     __syncthreads();
     const u32 valid = s_valid;
@@ -1075,10 +1144,18 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict
     if (c) atomicAdd(&hist2[(u64)s_bucket * MSD_NB + threadIdx.x], (u64)c);
 }
 
+// OPT = false: exact pass (cursors2 start at the bucket offsets a histogram pass produced).
+// OPT = true: optimistic pass, no histogram: bucket b's 512 sub-buckets are equal slots of cap2[b]
+// items from base2[b] on (cursors2 start at the slot starts); a reservation that does not fit its
+// slot goes to the dump area and raises flag[bucket] (see LimitSlots); flagged buckets are
+// repartitioned exactly by the k_msd_fix_* kernels, on the device, without asking the host.
+template <bool OPT>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out,
                    const u64 *__restrict__ tile_prefix, const u64 *__restrict__ bucket_start,
-                   FieldFn fn2, u64 *cursors2 /* [512][512], initialised to the bucket starts */) {
+                   const u64 *__restrict__ bucket_count, const __grid_constant__ FieldFn fn2,
+                   u64 *cursors2 /* [512][512] */, const u64 *__restrict__ base2,
+                   const u64 *__restrict__ cap2, u64 dump, u32 *flag, int shrink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = (u64 *)smem_raw;
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
@@ -1086,18 +1163,278 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     __shared__ u32 s_wsum[32];
     __shared__ u32 s_bucket, s_valid;
     __shared__ u64 s_start;
-    msd_locate(tile_prefix, bucket_start, blockIdx.x, &s_bucket, &s_start, &s_valid);
+    msd_locate(tile_prefix, bucket_start, bucket_count, blockIdx.x, &s_bucket, &s_start, &s_valid);
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u32 valid = s_valid;
     if (valid == 0) return;
     u64 *cur = cursors2 + (u64)s_bucket * MSD_NB;
-    if (valid == (u32)MSD_TILE)
-        unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + s_start, out, fn2, cur, 0u, valid,
-                                                              s_items, s_cnt, s_goff, s_wsum);
-    else
-        unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + s_start, out, fn2, cur, 0u, valid,
-                                                               s_items, s_cnt, s_goff, s_wsum);
+    if (OPT) {
+        const LimitSlots lim = {base2, cap2, s_bucket, (u32)shrink, dump, flag};
+        if (valid == (u32)MSD_TILE)
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, LimitSlots>(
+                in + s_start, out, fn2, cur, 0u, valid, s_items, s_cnt, s_goff, s_wsum, lim);
+        else
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false, false, LimitSlots>(
+                in + s_start, out, fn2, cur, 0u, valid, s_items, s_cnt, s_goff, s_wsum, lim);
+    } else {
+        if (valid == (u32)MSD_TILE)
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + s_start, out, fn2, cur, 0u, valid,
+                                                                  s_items, s_cnt, s_goff, s_wsum);
+        else
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + s_start, out, fn2, cur, 0u, valid,
+                                                                   s_items, s_cnt, s_goff, s_wsum);
+    }
+}
+
+// ---- optimistic (histogram-free) partitioning: sample, capacities, slots ----------------------
+// One read of a jittered strided sample of R and S (32-byte sectors, at most max_sectors per
+// relation) gives (1) the OR / AND of the sampled keys -> the digit plan, computed by every CTA
+// after a grid barrier exactly as the host computes it, (2) the sampled first-level histogram ->
+// bin capacities of the first pass, (3) the largest sampled count of any 18-bit bucket -> a skew
+// detector for the second pass.  st (u64 words): [0..3] OR_R AND_R OR_S AND_S, [4] barrier,
+// [6..7] max bucket count R S, [8..9] items sampled R S, [16..528) hist R, [528..1040) hist S.
+constexpr int SAMP_CTAS = 192, SAMP_THREADS = 512, SAMP_SPT = 3, SAMP_WORDS = 16 + 2 * MSD_NB;
+constexpr u32 SAMP_MAX_SECTORS = SAMP_CTAS * SAMP_THREADS * SAMP_SPT;
+
+__global__ void __launch_bounds__(SAMP_THREADS)
+    k_msd_sample(const u64 *__restrict__ r, u64 nr, const u64 *__restrict__ s, u64 ns,
+                 u32 max_sectors, u64 *st, u32 *sub /* [2][2^18], zeroed */) {
+    __shared__ u32 s_h[MSD_NB];
+    const u32  rel  = blockIdx.y;
+    const u64 *in   = rel ? s : r;
+    const u64  n    = rel ? ns : nr;
+    const u64  nsec = n >> 2;
+    const u64  S    = min(nsec, (u64)max_sectors);
+    const u64  step = S ? nsec / S : 0;
+    u32        kor = 0, kand = ~0u;
+    u64        x[SAMP_SPT][4];  // this thread's sampled items: all loads in flight together
+    bool       ok[SAMP_SPT];
+    for (int i = threadIdx.x; i < MSD_NB; i += SAMP_THREADS) s_h[i] = 0;
+#pragma unroll
+    for (int k = 0; k < SAMP_SPT; k++) {
+        const u64 i = ((u64)k * SAMP_THREADS + threadIdx.x) * gridDim.x + blockIdx.x;
+        ok[k]       = i < S;
+        if (ok[k]) {
+            const u32 jit = ((u32)i * 2654435761u) >> 16;
+            const u64 sec = (i * nsec) / S + (((u64)jit * step) >> 16);
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[k][u] = in[sec * 4 + u];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SAMP_SPT; k++) {
+        if (ok[k]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                kor |= (u32)(x[k][u] >> 32);
+                kand &= (u32)(x[k][u] >> 32);
+            }
+        }
+    }
+    kor  = __reduce_or_sync(SMJ_FULL_MASK, kor);
+    kand = __reduce_and_sync(SMJ_FULL_MASK, kand);
+    if (lane_id() == 0) {
+        const u64 vor = (u64)kor << 32, vand = ((u64)kand << 32) | 0xffffffffull;
+        if (vor & ~ld_relaxed(st + 2 * rel)) atomicOr(st + 2 * rel, vor);
+        if (~vand & ld_relaxed(st + 2 * rel + 1)) atomicAnd(st + 2 * rel + 1, vand);
+    }
+    // grid barrier (cooperative launch: all CTAs are resident)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(st + 4, 1ull);
+        const u64 all = (u64)gridDim.x * gridDim.y;
+        while (ld_relaxed(st + 4) < all) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+    u64 bits[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) bits[q] = ld_relaxed(st + q);
+    MsdPlan pl;
+    if (!smj_msd_plan(bits, &pl)) return;
+    u32 mx = 0;
+#pragma unroll
+    for (int k = 0; k < SAMP_SPT; k++) {
+        if (ok[k]) {
+            u32 old[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                atomicAdd(&s_h[(u32)(x[k][u] >> pl.shift1) & (MSD_NB - 1)], 1u);
+                const u32 id = (u32)(x[k][u] >> pl.shift2) & (MSD_NB * MSD_NB - 1);
+                old[u]       = atomicAdd(&sub[(rel << 18) | id], 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) mx = max(mx, old[u] + 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSD_NB; i += SAMP_THREADS)
+        if (s_h[i]) atomicAdd(st + 16 + rel * MSD_NB + i, (u64)s_h[i]);
+    mx = __reduce_max_sync(SMJ_FULL_MASK, mx);
+    if (lane_id() == 0 && mx > ld_relaxed(st + 6 + rel)) atomicMax(st + 6 + rel, (u64)mx);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[8 + rel] = S * 4;
+}
+
+// Second-level layout of the optimistic pass, from the first pass's cursors: per first-level bucket
+// its item count (clipped to the capacity: an overflowing pass is repeated anyway), its tiles, and
+// the slot capacity cap2 = avg + 7 sqrt(avg) + slack of its 512 sub-buckets (a multiple of 4 items,
+// so every slot starts on a 32-byte sector).  Raises *flag and plans no tiles when the slots do
+// not fit alloc2 items.
+__global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restrict__ cur1,
+                                                            const u64 *__restrict__ start1,
+                                                            const u64 *__restrict__ limit1, u64 alloc2,
+                                                            u64 *__restrict__ tile_prefix,
+                                                            u64 *__restrict__ bucket_count,
+                                                            u64 *__restrict__ cap2,
+                                                            u64 *__restrict__ base2, u32 *flag) {
+    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB];
+    const int b   = threadIdx.x;
+    const u64 c   = min(cur1[b] - start1[b], limit1[b] - start1[b]);
+    const u64 t   = (c + MSD_TILE - 1) / MSD_TILE;
+    const u64 avg = (c + MSD_NB - 1) / MSD_NB;
+    const u64 cap = c ? ((avg + (u64)ceil(7.0 * sqrt((double)avg + 1.0)) + 8 + 3) & ~3ull) : 0ull;
+    s_t[b]        = t;
+    s_c[b]        = cap * MSD_NB;
+    __syncthreads();
+    for (int o = 1; o < MSD_NB; o <<= 1) {
+        u64 at = (b >= o) ? s_t[b - o] : 0, ac = (b >= o) ? s_c[b - o] : 0;
+        __syncthreads();
+        s_t[b] += at;
+        s_c[b] += ac;
+        __syncthreads();
+    }
+    const bool fits = s_c[MSD_NB - 1] <= alloc2;
+    tile_prefix[b]  = fits ? s_t[b] - t : 0;
+    bucket_count[b] = c;
+    cap2[b]         = cap;
+    base2[b]        = s_c[b] - cap * MSD_NB;
+    if (b == MSD_NB - 1) {
+        tile_prefix[MSD_NB] = fits ? s_t[b] : 0;
+        if (!fits) *flag = 1u;
+    }
+}
+
+// first-level bucket sizes from the table an optimistic pass A left (cursors, starts, limits)
+__global__ void __launch_bounds__(MSD_NB) k_msd_counts_opt(const u64 *__restrict__ tab,
+                                                           u64 *__restrict__ counts) {
+    const int b = threadIdx.x;
+    counts[b]   = min(tab[b] - tab[MSD_NB + b], tab[2 * MSD_NB + b] - tab[MSD_NB + b]);
+}
+
+// slot starts of all 2^18 sub-buckets: bucket starts for the join and initial cursors
+__global__ void __launch_bounds__(MSD_NB) k_msd_slots(const u64 *__restrict__ base2,
+                                                      const u64 *__restrict__ cap2,
+                                                      u64 *__restrict__ starts, u64 *__restrict__ cursors) {
+    const u64 v = base2[blockIdx.x] + (u64)threadIdx.x * cap2[blockIdx.x];
+    starts[blockIdx.x * MSD_NB + threadIdx.x]  = v;
+    cursors[blockIdx.x * MSD_NB + threadIdx.x] = v;
+}
+
+// ---- exact repeat of the second level for the flagged first-level buckets, all on the device ----
+// A first-level bucket whose items are not spread evenly over its 512 sub-buckets (the partly
+// filled bucket at the edge of a dense key domain, a locally clustered key range) overflows some
+// of its equal slots.  Its region still holds the whole bucket (512 slots >= its item count), so
+// the bucket is simply partitioned again, exactly, inside its own region: histogram of the
+// bucket, exclusive scan -> sub-bucket starts, scatter.  The cost is proportional to the flagged
+// buckets; with none flagged the three launches return at once.
+__device__ __forceinline__ u32 msd_flagged_list(const u32 *__restrict__ flag, u32 *s_list, u32 *s_wcnt) {
+    const u32 b = threadIdx.x, f = flag[b] != 0, warp = b >> 5, lane = b & 31;
+    const u32 m = __ballot_sync(SMJ_FULL_MASK, f);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    u32 base = 0, total = 0;
+    for (u32 w = 0; w < MSD_NB / 32; w++) {
+        const u32 c = s_wcnt[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (f) s_list[base + __popc(m & lanemask_lt())] = b;
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(MSD_THREADS) k_msd_fix_hist(const u64 *__restrict__ in,
+                                                              const u64 *__restrict__ bucket_start,
+                                                              const u64 *__restrict__ bucket_count,
+                                                              const u32 *__restrict__ flag, FieldFn fn2,
+                                                              u32 *__restrict__ hist2 /* [512][512], zeroed */) {
+    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32], sh[MSD_NB];
+    const u32 nflag = msd_flagged_list(flag, s_list, s_wcnt);
+    for (u32 q = 0; q < nflag; q++) {
+        const u32 b     = s_list[q];
+        const u64 first = bucket_start[b], cnt = bucket_count[b];
+        sh[threadIdx.x] = 0;
+        __syncthreads();
+        for (u64 t = blockIdx.x; t * MSD_TILE < cnt; t += gridDim.x) {
+            const u64 lo = t * MSD_TILE, hi = min(cnt, lo + MSD_TILE);
+            for (u64 i = lo + threadIdx.x; i < hi; i += MSD_THREADS)
+                atomicAdd(&sh[fn2(ld_stream(in + first + i))], 1u);
+        }
+        __syncthreads();
+        const u32 c = sh[threadIdx.x];
+        if (c) atomicAdd(&hist2[b * MSD_NB + threadIdx.x], c);
+        __syncthreads();
+    }
+}
+
+// one CTA per first-level bucket: for a flagged bucket the exact sub-bucket starts inside its
+// region (and the cursors); *nfixed counts the flagged buckets for the statistics
+__global__ void __launch_bounds__(MSD_NB) k_msd_fix_offsets(const u32 *__restrict__ flag,
+                                                            const u32 *__restrict__ hist2,
+                                                            const u64 *__restrict__ base2,
+                                                            u64 *__restrict__ starts,
+                                                            u64 *__restrict__ cursors, u64 *nfixed) {
+    const u32 b = blockIdx.x, d = threadIdx.x;
+    if (!flag[b]) return;
+    __shared__ u32 s_w[MSD_NB / 32];
+    const u32 c = hist2[b * MSD_NB + d], lane = d & 31, warp = d >> 5;
+    u32       incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u32 excl = incl - c;
+    for (u32 w = 0; w < warp; w++) excl += s_w[w];
+    const u64 v = base2[b] + excl;
+    starts[b * MSD_NB + d]  = v;
+    cursors[b * MSD_NB + d] = v;
+    if (d == 0) atomicAdd(nfixed, 1ull);
+}
+
+__global__ void __launch_bounds__(MSD_THREADS, 2)
+    k_msd_fix_scatter(const u64 *__restrict__ in, u64 *__restrict__ out,
+                      const u64 *__restrict__ bucket_start, const u64 *__restrict__ bucket_count,
+                      const u32 *__restrict__ flag, const __grid_constant__ FieldFn fn2, u64 *cursors2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_items = (u64 *)smem_raw;
+    u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
+    u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
+    __shared__ u32 s_wsum[32];
+    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32];
+    const u32 nflag = msd_flagged_list(flag, s_list, s_wcnt);
+    for (u32 q = 0; q < nflag; q++) {
+        const u32 b     = s_list[q];
+        const u64 first = bucket_start[b], cnt = bucket_count[b];
+        u64      *cur   = cursors2 + (u64)b * MSD_NB;
+        for (u64 t = blockIdx.x; t * MSD_TILE < cnt; t += gridDim.x) {
+            const u64 lo    = t * MSD_TILE;
+            const u32 valid = (u32)min((u64)MSD_TILE, cnt - lo);
+            __syncthreads();  // the previous tile is done with the staging area
+            s_cnt[threadIdx.x] = 0;
+            __syncthreads();
+            if (valid == (u32)MSD_TILE)
+                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + first + lo, out, fn2, cur, 0u,
+                                                                      valid, s_items, s_cnt, s_goff, s_wsum);
+            else
+                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + first + lo, out, fn2, cur, 0u,
+                                                                       valid, s_items, s_cnt, s_goff, s_wsum);
+        }
+    }
 }
 
 // exclusive scan of nb entries in two launches: per-block scan + block totals, then add the
@@ -1136,38 +1473,160 @@ __global__ void __launch_bounds__(1024) k_scan_add(u64 *__restrict__ out, u64 nb
 
 }  // namespace
 
-// Pass B of the MSD partition: `a` holds n items already partitioned by the first-level digit,
-// d_hist1 (device, 512 entries) the sizes of the first-level buckets laid out back to back in a.
-// Every bucket is partitioned by the 9-bit digit at shift2 into b.  offsets (device, 2^18 + 1
-// entries) receives the start of every second-level bucket in b (and n).
-int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_hist1, u64 *b, u32 shift2,
-                   u64 *offsets) {
-    const u32  NB2 = MSD_NB * MSD_NB;
-    SmjScratch sc(ctx);
-    u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get((MSD_NB + 1) * 8);
-    u64 *d_hist2 = (u64 *)sc.get((size_t)NB2 * 8), *d_cur2 = (u64 *)sc.get((size_t)NB2 * 8);
-    u64 *d_tot   = (u64 *)sc.get((NB2 / 1024) * 8);
-    if (!d_tpref || !d_bstart || !d_hist2 || !d_cur2 || !d_tot)
-        return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
-    SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
-    FieldFn f2 = {shift2, (u32)MSD_NB - 1};
-    SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_hist1, d_tpref, d_bstart);
-    const unsigned   max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
-    static int       attr_gen  = -1;
-    constexpr size_t SMEM      = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
+static int msd_scatter2_attr(SmjCtx *ctx) {
+    static int       attr_gen = -1;
+    constexpr size_t SMEM     = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
     if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM));
+        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SMEM));
+        SMJ_CHECK(cudaFuncSetAttribute(k_msd_fix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SMEM));
         attr_gen = ctx->generation;
     }
+    return 0;
+}
+constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
+
+// Pass B of the MSD partition: `a` holds n items already partitioned by the first-level digit,
+// d_counts (device, 512 entries) the sizes of the first-level buckets, d_starts (device, 512
+// entries, or null = back to back) where each begins in a.  Every bucket is partitioned by the
+// 9-bit digit at shift2 into b.  offsets (device, 2^18 + 1 entries) receives the start of every
+// second-level bucket in b (and n): bucket q is b[offsets[q] .. offsets[q + 1]).
+int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
+                   u32 shift2, u64 *offsets) {
+    const u32  NB2 = MSD_NB * MSD_NB;
+    SmjScratch sc(ctx);
+    u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get(MSD_NB * 8);
+    u64 *d_bcount = (u64 *)sc.get(MSD_NB * 8);
+    u64 *d_hist2 = (u64 *)sc.get((size_t)NB2 * 8), *d_cur2 = (u64 *)sc.get((size_t)NB2 * 8);
+    u64 *d_tot   = (u64 *)sc.get((NB2 / 1024) * 8);
+    if (!d_tpref || !d_bstart || !d_bcount || !d_hist2 || !d_cur2 || !d_tot)
+        return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
+    FieldFn f2 = {shift2, (u32)MSD_NB - 1};
+    SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_counts, d_starts, d_tpref, d_bstart, d_bcount);
+    const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, f2, d_hist2);
+    SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, d_bcount, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_scan_local, NB2 / 1024, 1024, 0, d_hist2, (u64)NB2, offsets, d_tot);
     SMJ_LAUNCH(ctx, k_scan_add, NB2 / 1024, 1024, 0, offsets, (u64)NB2, d_tot);
     SMJ_CHECK(cudaMemcpyAsync(d_cur2, offsets, (size_t)NB2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_scatter2, max_tiles, MSD_THREADS, SMEM, a, b, d_tpref, d_bstart, f2, d_cur2);
+    SMJ_LAUNCH(ctx, k_msd_scatter2<false>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tpref, d_bstart,
+               d_bcount, f2, d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, 0ull, (u32 *)nullptr, 0);
+    return 0;
+}
+
+// ---- optimistic passes -------------------------------------------------------------------------
+// Sample of R and S (see k_msd_sample).  host: SMJ_MSD_SAMPLE_WORDS u64.  Synchronises.
+int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *host) {
+    if (max_sectors > SAMP_MAX_SECTORS) max_sectors = SAMP_MAX_SECTORS;
+    SmjScratch sc(ctx);
+    u64 *d_st  = (u64 *)sc.get(SAMP_WORDS * 8);
+    u32 *d_sub = (u32 *)sc.get((size_t)2 * MSD_NB * MSD_NB * 4);
+    if (!d_st || !d_sub) return smj_fail_msg("smj_msd_sample: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_st, 0, SAMP_WORDS * 8, ctx->stream));
+    SMJ_CHECK(cudaMemsetAsync(d_sub, 0, (size_t)2 * MSD_NB * MSD_NB * 4, ctx->stream));
+    const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
+    SMJ_CHECK(cudaMemcpyAsync(d_st, init, 32, cudaMemcpyHostToDevice, ctx->stream));
+    // cooperative launch: the kernel contains a grid barrier, so the runtime must guarantee (or
+    // refuse) that all 2 x SAMP_CTAS CTAs are resident at once
+    void *args[] = {(void *)&r, (void *)&nr, (void *)&s, (void *)&ns, (void *)&max_sectors, (void *)&d_st,
+                    (void *)&d_sub};
+    if (ctx->profiling) smj_prof_before(ctx, "k_msd_sample");
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_msd_sample, dim3(SAMP_CTAS, 2),
+                                                dim3(SAMP_THREADS), args, 0, ctx->stream);
+    if (ctx->profiling) smj_prof_after(ctx);
+    ctx->next_items = 0;
+    ctx->launches++;
+    if (e != cudaSuccess) return smj_fail(e, "k_msd_sample", __FILE__, __LINE__);
+    SMJ_CHECK(cudaMemcpyAsync(host, d_st, SAMP_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// First-level bin regions from a sampled histogram (k of nsamp items fell into the bin):
+// capacity = (k + 7 sqrt(k) + slack) n / nsamp, i.e. the estimate plus seven standard deviations
+// of the sampling error, rounded up to 16 items.  start/limit: host arrays of 512 entries.
+// Returns the number of items the regions span.  shrink (tests only) halves the capacities.
+u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, u64 *start, u64 *limit, int shrink) {
+    const double scale = nsamp ? std::max(1.0, (double)n / (double)nsamp) : 1.0;
+    u64          tot   = 0;
+    for (int b = 0; b < MSD_NB; b++) {
+        const double k = (double)hist[b];
+        u64 cap = (u64)ceil((k + 7.0 * sqrt(k + 1.0) + 8.0) * scale);
+        if (shrink) cap = (u64)(k * scale * 0.5);  // test hook: bins that cannot hold their items
+        cap      = (cap + 15) & ~15ull;
+        start[b] = tot;
+        tot += cap;
+        limit[b] = tot;
+    }
+    return tot;
+}
+u64 smj_msd_tile_items() { return MSD_TILE; }
+// upper bound of the items the second-level slots of an n-item relation span (k_msd_level2_plan)
+u64 smj_msd_alloc2(u64 n) {
+    const double per = (double)n / (double)(MSD_NB * MSD_NB);
+    return n + (u64)((double)(MSD_NB * MSD_NB) * (7.0 * sqrt(per + 3.0) + 16.0)) + 4096;
+}
+
+// Optimistic pass A: in -> a, bin b into a[start[b] .. limit[b]) (host arrays), no histogram.
+// d_tab (device, 3 x 512 u64) receives {cursors = bin ends, starts, limits}; *d_flag is raised when
+// a bin overflowed (a then holds garbage in places; its dump area is a[dump .. dump + tile)).
+// Every key is checked against the sampled key range on the way: a key that differs from kref on
+// a bit position of kmask raises *d_kflag.
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, const u64 *start,
+                       const u64 *limit, u64 dump, u64 *d_tab, u32 *d_flag, u32 kmask, u32 kref,
+                       u32 *d_kflag) {
+    SMJ_CHECK(cudaMemcpyAsync(d_tab, start, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SMJ_CHECK(cudaMemcpyAsync(d_tab + MSD_NB, start, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SMJ_CHECK(cudaMemcpyAsync(d_tab + 2 * MSD_NB, limit, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n == 0) return 0;
+    FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
+    const LimitArray lim = {d_tab + 2 * MSD_NB, dump, d_flag, kmask, kref, d_kflag};
+    return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, a, n, f1, d_tab, lim);
+}
+
+int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts) {
+    SMJ_LAUNCH(ctx, k_msd_counts_opt, 1, MSD_NB, 0, d_tab, d_counts);
+    return 0;
+}
+
+// Optimistic pass B: a (as left by smj_msd_pass_a_opt, d_tab its table) -> b, every first-level
+// bucket into 512 equal slots, no histogram; buckets with an overflowing slot are repartitioned
+// exactly inside their region by the k_msd_fix_* kernels.  starts / ends (device, 2^18 entries
+// each): sub-bucket q is b[starts[q] .. ends[q]).  d_counts (device, 512) receives the
+// first-level bucket sizes.  alloc2 = items b can hold before its dump area b[alloc2 .. alloc2 +
+// tile).  *d_flag is raised when the slots do not fit alloc2 (nothing is partitioned then);
+// *d_nfixed (u64) counts the repartitioned buckets.
+int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
+                       u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink) {
+    SmjScratch sc(ctx);
+    u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_cap2 = (u64 *)sc.get(MSD_NB * 8);
+    u64 *d_base2 = (u64 *)sc.get(MSD_NB * 8);
+    u32 *d_bflag = (u32 *)sc.get(MSD_NB * 4), *d_hist2 = (u32 *)sc.get((size_t)MSD_NB * MSD_NB * 4);
+    if (!d_tpref || !d_cap2 || !d_base2 || !d_bflag || !d_hist2)
+        return smj_fail_msg("smj_msd_pass_b_opt: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_bflag, 0, MSD_NB * 4, ctx->stream));
+    SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)MSD_NB * MSD_NB * 4, ctx->stream));
+    FieldFn f2 = {shift2, (u32)MSD_NB - 1};
+    SMJ_LAUNCH(ctx, k_msd_level2_plan, 1, MSD_NB, 0, d_tab, d_tab + MSD_NB, d_tab + 2 * MSD_NB, alloc2, d_tpref,
+               d_counts, d_cap2, d_base2, d_flag);
+    SMJ_LAUNCH(ctx, k_msd_slots, MSD_NB, MSD_NB, 0, d_base2, d_cap2, starts, ends);
+    const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    if (msd_scatter2_attr(ctx)) return -1;
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tpref,
+               d_tab + MSD_NB, d_counts, f2, ends, d_base2, d_cap2, alloc2, d_bflag, shrink);
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 2, max_tiles);
+    SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
+    SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
+    SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,
+               d_bflag, f2, ends);
     return 0;
 }
 
@@ -1197,7 +1656,7 @@ int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shi
     SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist1, d_bases1);
     FieldFn f1 = {shift1, (u32)MSD_NB - 1};
     if (n && (rc = launch_unstable<9>(ctx, in, a, n, f1, d_bases1))) return rc;  // consumes d_bases1
-    return smj_msd_pass_b(ctx, a, n, d_hist1, b, shift2, offsets);
+    return smj_msd_pass_b(ctx, a, n, d_hist1, nullptr, b, shift2, offsets);
 }
 
 // Pass A of the MSD partition with caller-supplied destinations: bucket d of the 9-bit digit at

@@ -135,7 +135,14 @@ typedef struct smj_join_stats_t {
     float    ms_total;     /* first kernel -> result on host                            */
     uint64_t launches;     /* kernels launched by this call                             */
     uint64_t hbm_bytes;    /* peak scratch bytes allocated by this call                 */
+    uint32_t path;         /* SMJ_PATH_*: which pipeline produced the result            */
+    uint32_t repeats;      /* optimistic partition passes that overflowed and were
+                              repeated exactly (histogram first)                        */
 } smj_join_stats_t;
+/* m-way join: general = LSD sort of R and S + merge-path scan; msd = two-level MSD range
+ * partition + fused bucket join with histogram passes; msd_opt = the same with at least one
+ * histogram-free (sampled-capacity) partition pass.  m-pass / mpsm report SMJ_PATH_GENERAL. */
+enum { SMJ_PATH_GENERAL = 0, SMJ_PATH_MSD = 1, SMJ_PATH_MSD_OPT = 2 };
 
 /* Device-resident join: r/s are device arrays and are left unmodified.
  * nruns: number of sorted runs per relation for m-pass / mpsm (>=1; m-way ignores it). */

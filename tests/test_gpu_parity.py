@@ -353,6 +353,63 @@ def test_mway_fast_path_wrong_sample_guess(smj, orc):
     assert _device_mway(smj, r, s) == orc.join_bruteforce(r, s)
 
 
+def _device_mway_stats(smj, r, s):
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    st = smj.device_join(smj.ALGO_MWAY, dr, ds)
+    dr.free()
+    ds.free()
+    return st
+
+
+def test_mway_optimistic_partition_and_its_exact_repeats(smj, orc, monkeypatch):
+    """The histogram-free partition passes (sampled bin capacities, fixed second-level slots):
+    same count and checksum as the exact passes and as the oracle; when a region overflows (forced
+    here by under-sizing the regions, SMJ_MSD_TEST) the pass is repeated exactly and the result
+    does not change."""
+    n = 3_000_017
+    r, s = orc.gen_unique(n, 12345), orc.gen_fk(2 * n + 5, n, 7)
+    exp = orc.join_bruteforce(r, s)
+    st = _device_mway_stats(smj, r, s)
+    assert (st.matches, st.checksum) == exp
+    # only the partly filled first-level bucket at the top of the dense key domain (one per
+    # relation) may need its second level repeated
+    assert st.path == smj.PATH_MSD_OPT and st.repeats <= 2, st.repeats
+    monkeypatch.setenv("SMJ_MSD_MODE", "exact")
+    st = _device_mway_stats(smj, r, s)
+    assert (st.matches, st.checksum, st.path, st.repeats) == (*exp, smj.PATH_MSD, 0)
+    monkeypatch.delenv("SMJ_MSD_MODE")
+    for hook in ("shrink1", "shrink2"):
+        monkeypatch.setenv("SMJ_MSD_TEST", hook)
+        st = _device_mway_stats(smj, r, s)
+        assert (st.matches, st.checksum) == exp, hook
+        # shrink1: both relations overflow at level 1 and are repartitioned exactly by the host;
+        # shrink2: every first-level bucket is repartitioned exactly on the device
+        assert st.path == smj.PATH_MSD_OPT, hook
+        assert st.repeats == 2 if hook == "shrink1" else st.repeats > 500, (hook, st.repeats)
+    monkeypatch.delenv("SMJ_MSD_TEST")
+
+
+def test_mway_optimistic_partition_input_orders(smj, orc):
+    """Sampled capacities must hold for inputs that are not in random order: sorted, reverse
+    sorted, sorted blocks, and a relation too small to be sampled sparsely."""
+    n = 2_500_003
+    base = orc.gen_unique(n, 99)
+    s = orc.gen_fk(n + 11, n, 5)
+    exp = orc.join_bruteforce(base, s)
+    blocks = np.concatenate([np.sort(c) for c in np.array_split(base, 37)])
+    for name, r in (("sorted", np.sort(base)), ("reverse", np.sort(base)[::-1].copy()), ("blocks", blocks)):
+        st = _device_mway_stats(smj, r, s)
+        assert (st.matches, st.checksum) == exp, name
+        assert st.path == smj.PATH_MSD_OPT, name
+    # second-level skew that no single heavy key explains: S keys concentrated on one key range
+    rng = np.random.default_rng(5)
+    hot = rng.integers(1000, 1000 + 4096, size=n, dtype=np.uint64)
+    s2 = np.concatenate([s, (hot << np.uint64(32)) | np.arange(n, dtype=np.uint64)])
+    rng.shuffle(s2)
+    st = _device_mway_stats(smj, base, s2)
+    assert (st.matches, st.checksum) == orc.join_bruteforce(base, s2)
+
+
 # ------------------------------------------------------------------------------------ host memory paths
 def test_pageable_relations_use_the_staging_pipeline(smj, orc):
     """Relations in ordinary malloc'ed memory above the staging threshold (32 MiB): upload through
