@@ -15,6 +15,7 @@ struct SmjCtx {
     int          sm_count;
     cudaStream_t stream;      // stream all kernels are launched on
     cudaStream_t own_stream;  // the library's own stream (used when the caller sets none)
+    cudaStream_t copy_stream; // host->device copies that overlap kernels on `stream`
     u64          launches;    // kernels launched so far
     bool         ready;
     bool         profiling;   // smjdev_profile_begin(): CUDA events around every launch
@@ -27,6 +28,7 @@ void smj_prof_after(SmjCtx *ctx);
 SmjCtx *smj_ctx();                 // initialises lazily; nullptr on failure
 int     smj_fail(cudaError_t e, const char *what, const char *file, int line);
 int     smj_fail_msg(const char *msg);
+bool    smj_is_host_pointer(const void *p);  // mapped (pinned / registered) host memory
 
 #define SMJ_CHECK(expr)                                                        \
     do {                                                                       \

@@ -36,13 +36,16 @@ int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 
 int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
                        const u64 *dest_offsets);
 int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
-int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *host);
-u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, u64 *start, u64 *limit, int shrink);
+int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *d_st,
+                   u32 *d_sub, u64 *host);
+size_t smj_msd_sample_bytes(int which);
+u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, int shrink);
+int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc_r, u64 alloc_s, int shrink,
+                         u64 *tab_r, u64 *tab_s, u32 *d_flags);
 u64 smj_msd_tile_items();
 u64 smj_msd_alloc2(u64 n);
-int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, const u64 *start,
-                       const u64 *limit, u64 dump, u64 *d_tab, u32 *d_flag, u32 kmask, u32 kref,
-                       u32 *d_kflag);
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 dump, u64 *d_tab,
+                       u32 *d_flag, u32 kmask, u32 kref, u32 *d_kflag);
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
                        u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink);
 int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
@@ -426,7 +429,7 @@ extern "C" int smjdev_merge_join_ex(const uint64_t *r, uint64_t nr, const uint64
 namespace {
 constexpr int BJ_WARPS = 8;
 
-__global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__restrict__ r,
+__global__ void __launch_bounds__(BJ_WARPS * 32, 4) k_bucket_join(const u64 *__restrict__ r,
                                                                const u64 *__restrict__ rs_,
                                                                const u64 *__restrict__ re_,
                                                                const u64 *__restrict__ s,
@@ -442,40 +445,57 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
     u64 *t_sum = (u64 *)(smem_raw + (size_t)warp * slots * 12);
     u32 *t_cnt = (u32 *)(t_sum + slots);
     u64  my_cnt = 0, my_cks = 0;
+    constexpr u32 CHUNK = 4;  // buckets claimed per atomic: one round trip for 4 buckets' bounds
+    constexpr int UN    = 8;  // loads in flight per lane and relation
     while (true) {
-        u32 b = 0;
-        if (lane == 0) b = atomicAdd(next_bucket, 1u);
-        b = __shfl_sync(SMJ_FULL_MASK, b, 0);
-        if (b >= nbuckets) break;
-        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
+        u32 b0 = 0;
+        if (lane == 0) b0 = atomicAdd(next_bucket, CHUNK);
+        b0 = __shfl_sync(SMJ_FULL_MASK, b0, 0);
+        if (b0 >= nbuckets) break;
+        // lanes 0..15 fetch the 4 x {r0, r1, s0, s1} of the chunk in one go
+        u64 bound = 0;
+        {
+            const u32  k   = lane >> 2, which = lane & 3, bb = b0 + k;
+            const u64 *arr = which == 0 ? rs_ : which == 1 ? re_ : which == 2 ? ss_ : se_;
+            if (lane < 4 * CHUNK && bb < nbuckets) bound = arr[bb];
+        }
+#pragma unroll 1
+        for (u32 k = 0; k < CHUNK; k++) {
+        const u64 r0 = __shfl_sync(SMJ_FULL_MASK, bound, 4 * k), r1 = __shfl_sync(SMJ_FULL_MASK, bound, 4 * k + 1);
+        const u64 s0 = __shfl_sync(SMJ_FULL_MASK, bound, 4 * k + 2), s1 = __shfl_sync(SMJ_FULL_MASK, bound, 4 * k + 3);
         if (r0 == r1 || s0 == s1) continue;
         if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy hitters: k_big_bucket_join
         // Fast path, R keys unique inside the bucket (the usual primary-key side): the slot holds
         // the R item itself (stored complemented, 0 = empty), one exchange per R item and one load
         // per S item.  A second R item on the same slot sends the bucket down the general path.
+        // The first batches of R and of S are requested together, so a bucket of average size
+        // costs three DRAM round trips instead of one per 128 items.
+        u64 x[UN], y[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) x[u] = (r0 + lane + 32 * u < r1) ? ld_stream(r + r0 + lane + 32 * u) : 0ull;
+#pragma unroll
+        for (int u = 0; u < UN; u++) y[u] = (s0 + lane + 32 * u < s1) ? ld_stream(s + s0 + lane + 32 * u) : 0ull;
         for (u32 i = lane; i < slots; i += 32) t_sum[i] = 0;
         __syncwarp();
         bool dup = false;
-        for (u64 i = r0 + lane; i < r1; i += 128) {  // 4 independent loads in flight per lane
-            u64 x[4];
+        for (u64 i = r0 + lane;;) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) x[u] = (i + 32 * u < r1) ? ld_stream(r + i + 32 * u) : 0ull;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < UN; u++) {
                 if (i + 32 * u < r1) {
                     const u32 slot = (u32)(x[u] >> lo_shift) & mask;
                     dup |= atomicExch(&t_sum[slot], ~x[u]) != 0ull;
                 }
             }
+            i += 32 * UN;
+            if (i - lane >= r1) break;
+#pragma unroll
+            for (int u = 0; u < UN; u++) x[u] = (i + 32 * u < r1) ? ld_stream(r + i + 32 * u) : 0ull;
         }
         __syncwarp();
         if (!__any_sync(SMJ_FULL_MASK, dup)) {
-            for (u64 j = s0 + lane; j < s1; j += 128) {
-                u64 y[4];
+            for (u64 j = s0 + lane;;) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) y[u] = (j + 32 * u < s1) ? ld_stream(s + j + 32 * u) : 0ull;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < UN; u++) {
                     if (j + 32 * u < s1) {
                         const u64 v = t_sum[(u32)(y[u] >> lo_shift) & mask];
                         if (v) {
@@ -484,6 +504,10 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
                         }
                     }
                 }
+                j += 32 * UN;
+                if (j - lane >= s1) break;
+#pragma unroll
+                for (int u = 0; u < UN; u++) y[u] = (j + 32 * u < s1) ? ld_stream(s + j + 32 * u) : 0ull;
             }
             __syncwarp();
             continue;
@@ -522,6 +546,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_bucket_join(const u64 *__rest
             }
         }
         __syncwarp();
+        }
     }
     my_cnt = warp_reduce_add(my_cnt);
     my_cks = warp_reduce_add(my_cks);
@@ -596,8 +621,8 @@ __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__
                                                          const u64 *__restrict__ s,
                                                          const u64 *__restrict__ ss_,
                                                          const u64 *__restrict__ se_, u32 nbuckets,
-                                                         u32 lo_shift, u32 lbits, u32 *next_bucket,
-                                                         u64 *__restrict__ acc) {
+                                                         u32 lo_shift, u32 lbits, u64 big,
+                                                         u32 *next_bucket, u64 *__restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 slots = 1u << lbits, mask = slots - 1;
     u64 *t_sum = (u64 *)smem_raw;
@@ -613,6 +638,7 @@ __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__
         if (b >= nbuckets) break;
         const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
         if (r0 == r1 || s0 == s1) continue;
+        if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy: the host takes the general path
         for (u32 i = threadIdx.x; i < slots * 3 / 2; i += 256) ((u64 *)t_sum)[i] = 0;
         __syncthreads();
         for (u64 i = r0 + threadIdx.x; i < r1; i += 256) {
@@ -686,6 +712,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
     u64 *t_sum = (u64 *)(smem_raw + (size_t)warp * slots * 12);
     u32 *t_cnt = (u32 *)(t_sum + slots);
     const u64 gw = (u64)blockIdx.x * BJ_WARPS + warp, nw = (u64)gridDim.x * BJ_WARPS;
+    if (info[1]) return;  // a bucket heavy on both sides: the host takes the general path
     const u32 nbig = info[0];
     u64       my_cnt = 0, my_cks = 0;
     for (u32 q = 0; q < nbig; q++) {
@@ -748,18 +775,18 @@ static int bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u
     return 0;
 }
 
-// Join of the 2^18 bucket pairs.  h_state: host copy of d_state taken after bucket_collect
-// ([6] = heavy-bucket info).  *done = 0 when the buckets do not suit the bucket kernels (the caller
-// then takes the general sort + scan path).  d_state[1] is the bucket counter (zero on entry).
+// Join of the 2^18 bucket pairs, enqueued behind bucket_collect without asking the host: the
+// bucket kernel skips the heavy buckets, the cooperative kernel takes the listed ones (it returns
+// at once when there are none).  Whether the result may be used is decided afterwards from
+// d_state[6] (bucket_join_valid): a key that is heavy on BOTH sides, or any heavy bucket in a wide
+// key domain (lbits > 10), is left to the general sort + scan path.  d_state[1] is the bucket
+// counter (zero on entry).
 static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
-                       u64 *d_state, const u64 *h_state, const u32 *d_list, u64 *acc, int *done) {
+                       u64 *d_state, const u32 *d_list, u64 *acc) {
     const u32 nb2 = 512u * 512u;
-    *done         = 0;
-    const u32 nbig = (u32)(h_state[6] & 0xffffffffu), unsupported = (u32)(h_state[6] >> 32);
     u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
         // wide key domains (up to 2^31): one CTA per bucket, no cooperative heavy-hitter kernel
-        if (nbig) return 0;
         const size_t smem = (size_t)(1u << lbits) * 12;
         static size_t smem_set_cta = 0;
         static int    gen_cta      = -1;
@@ -772,11 +799,9 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / smem));
         SMJ_ITEMS(ctx, R.n + S.n);
         SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, R.items, R.starts, R.ends,
-                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, d_next, acc);
-        *done = 1;
+                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
         return 0;
     }
-    if (unsupported) return 0;  // a key that is heavy in R and in S: general path
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
     static size_t smem_set = 0;
     static int    smem_gen = -1;
@@ -792,11 +817,13 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
     SMJ_ITEMS(ctx, R.n + S.n);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts, R.ends,
                S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
-    if (nbig)
-        SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts,
-                   R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
-    *done = 1;
+    SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts,
+               R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
     return 0;
+}
+static bool bucket_join_valid(const u64 *h_state, u32 lbits) {
+    const u32 nbig = (u32)(h_state[6] & 0xffffffffu), unsupported = (u32)(h_state[6] >> 32);
+    return lbits > 10 ? nbig == 0 : unsupported == 0;
 }
 
 // no key bit outside [lo, hi] may vary in R or S (exact = {OR_R, AND_R, OR_S, AND_S})
@@ -813,11 +840,14 @@ static bool msd_plan_holds(const u64 *exact, int lo, int hi) {
 static const u64 MSD_STATE_INIT[16] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull,
                                        0ull, 0ull, 0ull, 0ull,  0ull, 0ull,  0ull, 0ull};
 
+struct Upload;
 // One relation of the m-way fast path.  Optimistic: no histogram passes (sampled capacities, fixed
 // slots); exact: histogram + scatter per level.
 struct MsdRel {
-    const u64 *in;
+    const u64 *in;             // device-resident input (the staging buffer of an upload)
     u64        n;
+    Upload    *up;             // non-null: `in` arrives chunk by chunk
+    const u64 *sample_from;    // what the sample kernel reads (the pinned host copy of an upload)
     u64       *a, *b;          // level-1 / level-2 outputs
     u64        alloc1, alloc2; // capacities of a and b in items, dump areas excluded
     u64       *starts, *ends;  // 2^18 (+1) entries each
@@ -826,18 +856,81 @@ struct MsdRel {
     BucketSet set() const { return BucketSet{b, starts, opt2 ? ends : starts + 1, n}; }
 };
 
+// A relation in pinned host memory on its way to HBM: copied chunk by chunk on the copy stream,
+// one event per chunk, so that the first partitioning pass can consume chunk k while chunk k + 1
+// is still crossing PCIe (the pass needs no histogram, hence no complete relation).
+struct Upload {
+    SmjCtx                  *ctx  = nullptr;
+    const u64               *host = nullptr;
+    u64                     *dev  = nullptr;
+    u64                      n = 0, chunk = 0;  // items, items per chunk
+    std::vector<cudaEvent_t> ev;                // ev[k]: chunk k has arrived (cached, not owned)
+    bool                     waited = false;
+    bool active() const { return host != nullptr; }
+    u64  nchunks() const { return ev.size(); }
+    // every later operation on ctx->stream sees the whole relation
+    int wait_all() {
+        if (active() && !waited && !ev.empty()) SMJ_CHECK(cudaStreamWaitEvent(ctx->stream, ev.back(), 0));
+        waited = true;
+        return 0;
+    }
+    ~Upload() { wait_all(); }  // the staging buffer is freed in stream order behind the copies
+};
+static cudaEvent_t upload_event(SmjCtx *ctx, size_t idx) {
+    static std::vector<cudaEvent_t> pool;
+    static int                      gen = -1;
+    if (gen != ctx->generation) {
+        pool.clear();  // events of another device: leaked on purpose (a handful, once)
+        gen = ctx->generation;
+    }
+    while (pool.size() <= idx) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        pool.push_back(e);
+    }
+    return pool[idx];
+}
+// starts the copies; ev_base: first index of this relation's events in the cache
+static int upload_begin(SmjCtx *ctx, SmjScratch &sc, const u64 *host, u64 n, size_t ev_base, Upload &up) {
+    constexpr u64 CHUNK = 8ull << 20;  // 8 Mi items = 64 MiB = 1024 scatter tiles
+    up.ctx   = ctx;
+    up.host  = host;
+    up.n     = n;
+    up.chunk = CHUNK;
+    up.dev   = (u64 *)sc.get(n * 8);
+    if (!up.dev) return smj_fail_msg("smjdev_join: out of device memory");
+    // the staging buffer comes from the stream-ordered pool of ctx->stream
+    cudaEvent_t e_alloc = upload_event(ctx, ev_base);
+    if (!e_alloc) return smj_fail_msg("smjdev_join: cudaEventCreate failed");
+    SMJ_CHECK(cudaEventRecord(e_alloc, ctx->stream));
+    SMJ_CHECK(cudaStreamWaitEvent(ctx->copy_stream, e_alloc, 0));
+    const u64 nch = div_up(n, CHUNK);
+    for (u64 k = 0; k < nch; k++) {
+        const u64   off = k * CHUNK, len = std::min(CHUNK, n - off);
+        cudaEvent_t e   = upload_event(ctx, ev_base + 1 + k);
+        if (!e) return smj_fail_msg("smjdev_join: cudaEventCreate failed");
+        SMJ_CHECK(cudaMemcpyAsync(up.dev + off, host + off, len * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SMJ_CHECK(cudaEventRecord(e, ctx->copy_stream));
+        up.ev.push_back(e);
+    }
+    return 0;
+}
+
 // m-way fast path: two-level MSD range partition of R and S by the same 18 key bits, then the
 // fused in-bucket counting sort + merge join.  *used = 0 when the key domain or the bucket sizes
-// do not suit it; the caller then takes the general sort + scan path.
+// do not suit it; the caller then takes the general sort + scan path.  On success h_acc = {count,
+// checksum} (the call has synchronised).
 //
 // The partition passes run OPTIMISTICALLY: one sample of R and S gives the key range, the
 // first-level bin capacities and a skew test; both levels then scatter without a histogram pass
-// into regions with slack, the exact OR / AND of the keys is collected on the way.  Before the
-// join kernel is launched the host checks the overflow flags and the key range once; what did not
-// hold is repeated exactly (histogram first), so the result never depends on the guess.
-static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc, int *used,
-                    PhaseTimer &tm, int &t_part, int &t_sort, int &t_join, u64 *scratch_bytes,
-                    u32 *path, u32 *repeats) {
+// into regions with slack, every key is checked against the sampled key range on the way, and the
+// join kernels are enqueued right behind.  Only then does the host look: overflow flags, key
+// range, heavy buckets.  What did not hold is repeated exactly (histogram first), so the result
+// never depends on the guess.  In the good case the host synchronises twice per join (sample,
+// result).
+static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upload *up_r, Upload *up_s,
+                    u64 *acc, int *used, PhaseTimer &tm, int &t_part, int &t_sort, int &t_join,
+                    u64 *scratch_bytes, u32 *path, u32 *repeats, u64 *h_acc) {
     *used = 0;
     if (nr + ns < (1u << 20)) return 0;  // 2^18 buckets only pay off on large inputs
     const char *mode_env = getenv("SMJ_MSD_MODE");  // "exact" disables the optimistic passes
@@ -846,25 +939,28 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
     // that the overflow -> exact repeat paths run on ordinary inputs
     const char *hook    = getenv("SMJ_MSD_TEST");
     const int   shrink1 = hook && !strcmp(hook, "shrink1"), shrink2 = hook && !strcmp(hook, "shrink2");
-    const u32 max_sectors = 1u << 18;
+    const u32   nb2     = 512u * 512u;
+    const u64   tile    = smj_msd_tile_items();
+    SmjScratch  sc(ctx);
+    u64 *d_state = (u64 *)sc.get(128), *d_st = (u64 *)sc.get(smj_msd_sample_bytes(0));
+    u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4), *d_sub = (u32 *)sc.get(smj_msd_sample_bytes(1));
+    if (!d_state || !d_list || !d_st || !d_sub) return smj_fail_msg("mway_msd: scratch allocation failed");
+    SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<u64> samp(SMJ_MSD_SAMPLE_WORDS);
-    int rc = smj_msd_sample(ctx, r, nr, s, ns, max_sectors, samp.data());
+    // an uploading relation is sampled where it is complete: in pinned host memory, over PCIe
+    // (a smaller sample: 2 MiB per relation next to the 64 MiB chunks of the upload)
+    const bool uploading = (up_r && up_r->active()) || (up_s && up_s->active());
+    const u64 *samp_r = (up_r && up_r->active()) ? up_r->host : r;
+    const u64 *samp_s = (up_s && up_s->active()) ? up_s->host : s;
+    int rc = smj_msd_sample(ctx, samp_r, nr, samp_s, ns, uploading ? 1u << 16 : 1u << 18, d_st, d_sub,
+                            samp.data());
     if (rc) return rc;
     MsdPlan pl;
     if (!smj_msd_plan(samp.data(), &pl)) return 0;
-    const u32  nb2  = 512u * 512u;
-    const u64  tile = smj_msd_tile_items();
-    SmjScratch sc(ctx);
-    u64 *d_state = (u64 *)sc.get(128);
-    u32 *d_list  = (u32 *)sc.get((size_t)nb2 * 4);
-    if (!d_state || !d_list) return smj_fail_msg("mway_msd: scratch allocation failed");
-    SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
-
     // key bits outside [lo, hi] are constant in the sample: every key must carry the same value there
     const u32 krange = (pl.hi == 31 ? 0xffffffffu : ((1u << (pl.hi + 1)) - 1)) & ~((1u << pl.lo) - 1);
     const u32 kmask = ~krange, kref = (u32)((samp[1] & samp[3]) >> 32) & kmask;
-    MsdRel rel[2] = {{r, nr}, {s, ns}};
-    u64    h_start[2][512], h_limit[2][512];
+    MsdRel rel[2] = {{r, nr, up_r, samp_r}, {s, ns, up_s, samp_s}};
     for (int q = 0; q < 2; q++) {
         MsdRel &x = rel[q];
         // a heavy 18-bit bucket in the sample (expected count: a handful) means equal slots will
@@ -873,8 +969,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         const double expect = (double)nsamp / (double)nb2;
         x.opt1 = mode && x.n >= (1u << 20);
         x.opt2 = x.opt1 && (double)maxsub <= 4.0 * expect + 24.0;
-        x.alloc1 = x.n;
-        if (x.opt1) x.alloc1 = smj_msd_caps1(samp.data() + 16 + 512 * q, nsamp, x.n, h_start[q], h_limit[q], shrink1);
+        x.alloc1 = x.opt1 ? smj_msd_caps1(samp.data() + 16 + 512 * q, nsamp, x.n, shrink1) : x.n;
         x.alloc2 = x.opt2 ? smj_msd_alloc2(x.n) : x.n;
         x.a      = (u64 *)sc.get((std::max(x.alloc1, x.n) + tile) * 8);
         x.b      = (u64 *)sc.get((std::max(x.alloc2, x.n) + tile) * 8);
@@ -885,12 +980,30 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
         if (!x.a || !x.b || !x.starts || !x.ends || !x.d_tab || !x.d_counts)
             return smj_fail_msg("smjdev_join: out of device memory");
     }
+    u32 *flags = (u32 *)(d_state + 8);  // one u64 slot per flag, low word used
+    if (rel[0].opt1 || rel[1].opt1)
+        if ((rc = smj_msd_caps1_tables(ctx, d_st, nr, ns, rel[0].alloc1, rel[1].alloc1, shrink1,
+                                       rel[0].opt1 ? rel[0].d_tab : nullptr,
+                                       rel[1].opt1 ? rel[1].d_tab : nullptr, flags)))
+            return rc;
     for (int q = 0; q < 2; q++) {
         MsdRel &x = rel[q];
-        u32 *flags = (u32 *)(d_state + 8);  // one u64 slot per flag, low word used
+        if (x.opt1 && x.up && x.up->active()) {
+            // the pass consumes the upload chunk by chunk (the bin cursors carry over)
+            for (u64 k = 0; k < x.up->nchunks(); k++) {
+                const u64 off = k * x.up->chunk, len = std::min(x.up->chunk, x.n - off);
+                SMJ_CHECK(cudaStreamWaitEvent(ctx->stream, x.up->ev[k], 0));
+                if ((rc = smj_msd_pass_a_opt(ctx, x.in + off, len, x.a, pl.shift1, x.alloc1, x.d_tab,
+                                             flags + 2 * q, kmask, kref, flags + 12 + 2 * q)))
+                    return rc;
+            }
+            x.up->waited = true;
+        } else if (x.up && (rc = x.up->wait_all()))
+            return rc;
         if (x.opt1) {
-            if ((rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, h_start[q], h_limit[q], x.alloc1,
-                                         x.d_tab, flags + 2 * q, kmask, kref, flags + 12 + 2 * q)))
+            if (!(x.up && x.up->active()) &&
+                (rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, x.alloc1, x.d_tab, flags + 2 * q, kmask,
+                                         kref, flags + 12 + 2 * q)))
                 return rc;
             if (x.opt2) {
                 if ((rc = smj_msd_pass_b_opt(ctx, x.a, x.n, x.d_tab, x.b, x.alloc2, pl.shift2, x.starts,
@@ -905,50 +1018,56 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64
                                            d_state + 2 + 2 * q)))
             return rc;
     }
-    u64 h[16];
-    if ((rc = bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
-    SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
-    int t_mid = tm.mark();
-    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-    // the sample missed key bits that vary (seen by an exact histogram pass or by the key check)
-    if (!msd_plan_holds(h + 2, pl.lo, pl.hi) || h[14] || h[15]) return 0;
-    bool redo = false;
-    *path     = (rel[0].opt1 || rel[1].opt1) ? SMJ_PATH_MSD_OPT : SMJ_PATH_MSD;
-    for (int q = 0; q < 2; q++) {
-        MsdRel &x = rel[q];
-        const bool over1 = x.opt1 && h[8 + q], over2 = x.opt2 && h[10 + q];
-        if (over1) {  // the whole relation again, exactly (a and b are large enough)
-            if ((rc = smj_msd_partition(ctx, x.in, x.n, x.a, x.b, pl.shift1, pl.shift2, x.starts, nullptr)))
-                return rc;
-            x.opt1 = x.opt2 = false;
-            redo = true;
-            *repeats += 1;
-        } else if (over2) {  // the slots did not fit b: level 2 again from the intact level-1 output
-            if ((rc = smj_msd_pass_b(ctx, x.a, x.n, x.d_counts, x.d_tab + 512, x.b, pl.shift2, x.starts)))
-                return rc;
-            x.opt2 = false;
-            redo   = true;
-            *repeats += 1;
-        } else if (x.opt2)
-            *repeats += (u32)h[12 + q];
-    }
-    if (redo) {
+    *path = (rel[0].opt1 || rel[1].opt1) ? SMJ_PATH_MSD_OPT : SMJ_PATH_MSD;
+    u64 h[18];
+    for (int attempt = 0;; attempt++) {
         if ((rc = bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
+        const int t_mid = tm.mark();
+        if ((rc = bucket_join(ctx, rel[0].set(), rel[1].set(), pl.lo_shift, pl.lbits, d_state, d_list, acc)))
+            return rc;
         SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
-        t_mid = tm.mark();
+        SMJ_CHECK(cudaMemcpyAsync(h + 16, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        const int t_done = tm.mark();
         SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+        t_part = t_sort = t_mid;  // the in-partition sort is fused into the join kernel
+        t_join = t_done;
+        // the sample missed key bits that vary (seen by an exact histogram pass or by the key check)
+        bool ok = msd_plan_holds(h + 2, pl.lo, pl.hi) && !h[14] && !h[15];
+        bool redo = false;
+        for (int q = 0; q < 2 && ok; q++) {
+            MsdRel &x = rel[q];
+            const bool over1 = x.opt1 && h[8 + q], over2 = x.opt2 && h[10 + q];
+            if (over1) {  // the whole relation again, exactly (a and b are large enough)
+                if ((rc = smj_msd_partition(ctx, x.in, x.n, x.a, x.b, pl.shift1, pl.shift2, x.starts, nullptr)))
+                    return rc;
+                x.opt1 = x.opt2 = false;
+                redo = true;
+                *repeats += 1;
+            } else if (over2) {  // the slots did not fit b: level 2 again from the intact level-1 output
+                if ((rc = smj_msd_pass_b(ctx, x.a, x.n, x.d_counts, x.d_tab + 512, x.b, pl.shift2, x.starts)))
+                    return rc;
+                x.opt2 = false;
+                redo   = true;
+                *repeats += 1;
+            }
+        }
+        if (ok && redo && attempt == 0) {  // join again on the repaired buckets
+            SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+            SMJ_CHECK(cudaMemsetAsync(d_state + 1, 0, 8, ctx->stream));
+            continue;
+        }
+        ok = ok && !redo && bucket_join_valid(h, pl.lbits);
+        if (!ok) {
+            SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+            return 0;
+        }
+        break;
     }
-    t_part = t_sort = t_mid;  // the in-partition sort is fused into the join kernel
-    int done = 0;
-    if ((rc = bucket_join(ctx, rel[0].set(), rel[1].set(), pl.lo_shift, pl.lbits, d_state, h, d_list, acc,
-                          &done)))
-        return rc;
-    if (!done) {
-        SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
-        return 0;
-    }
-    t_join = tm.mark();
-    *used  = 1;
+    for (int q = 0; q < 2; q++)
+        if (rel[q].opt2) *repeats += (u32)h[12 + q];
+    h_acc[0] = h[16];
+    h_acc[1] = h[17];
+    *used    = 1;
     if (scratch_bytes) *scratch_bytes = sc.bytes;
     return 0;
 }
@@ -974,8 +1093,27 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
     int t_part = t0, t_sort = t0, t_merge = t0, t_join = t0, rc = 0;
 
-    u64 msd_bytes = 0;
+    // pinned host relations are uploaded chunk by chunk on the copy stream (the m-way fast path
+    // overlaps its first partitioning pass with the transfer); everything else sees device arrays
+    Upload up_r, up_s;
+    cudaEvent_t h2d0 = nullptr, h2d1 = nullptr;
+    if (nr && ns && (smj_is_host_pointer(r) || smj_is_host_pointer(s))) {
+        SMJ_CHECK(cudaEventCreate(&h2d0));
+        SMJ_CHECK(cudaEventCreate(&h2d1));
+        SMJ_CHECK(cudaEventRecord(h2d0, ctx->copy_stream));
+        if (smj_is_host_pointer(r)) {
+            if ((rc = upload_begin(ctx, sc, r, nr, 0, up_r))) return rc;
+            r = up_r.dev;
+        }
+        if (smj_is_host_pointer(s)) {
+            if ((rc = upload_begin(ctx, sc, s, ns, 1 + div_up(nr, 8ull << 20), up_s))) return rc;
+            s = up_s.dev;
+        }
+        SMJ_CHECK(cudaEventRecord(h2d1, ctx->copy_stream));
+    }
+    u64 msd_bytes = 0, h_fast[2] = {0, 0};
     u32 path = SMJ_PATH_GENERAL, repeats = 0;
+    int fast_done = 0;
     if (nr && ns) {
         u64 *aR = nullptr, *bR = nullptr, *aS = nullptr, *bS = nullptr;
         auto ping_pong = [&]() {
@@ -990,14 +1128,16 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             int used = 0;
             const char *force = getenv("SMJ_MWAY_PATH");  // "lsd" forces the general path
             if (!(force && force[0] == 'l')) {
-                if ((rc = mway_msd(ctx, r, nr, s, ns, acc, &used, tm, t_part, t_sort, t_join, &msd_bytes,
-                                   &path, &repeats)))
+                if ((rc = mway_msd(ctx, r, nr, s, ns, &up_r, &up_s, acc, &used, tm, t_part, t_sort, t_join,
+                                   &msd_bytes, &path, &repeats, h_fast)))
                     return rc;
                 t_merge = t_sort;
             }
+            fast_done = used;
             if (!used) path = SMJ_PATH_GENERAL;
             if (!used) {
                 u64 *sr = nullptr, *ss = nullptr;
+                if (up_r.wait_all() || up_s.wait_all()) return -1;
                 if (!ping_pong()) return smj_fail_msg("smjdev_join: out of device memory");
                 SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
                 t_part = tm.mark();
@@ -1007,6 +1147,8 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
                 if ((rc = smj_merge_join_acc(ctx, sr, nr, ss, ns, acc))) return rc;
                 t_join = tm.mark();
             }
+        } else if (up_r.wait_all() || up_s.wait_all()) {
+            return -1;
         } else if (algo == SMJ_ALGO_MPASS) {
             // sorted runs, then pairwise merge passes (sortmergejoin_multipass.c:410-708)
             std::vector<const u64 *> pr, ps;
@@ -1044,10 +1186,19 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     } else {
         t_part = t_sort = t_merge = t_join = tm.mark();
     }
-    u64 h[2];
-    SMJ_CHECK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    const int t_end = tm.mark();
-    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    u64 h[2] = {h_fast[0], h_fast[1]};
+    int t_end = t_join;
+    if (!fast_done) {  // (the fast path has already synchronised and brought the result along)
+        SMJ_CHECK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        t_end = tm.mark();
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (h2d0) {
+        cudaEventSynchronize(h2d1);
+        cudaEventElapsedTime(&stats->ms_h2d, h2d0, h2d1);
+        cudaEventDestroy(h2d0);
+        cudaEventDestroy(h2d1);
+    }
     stats->matches      = h[0];
     stats->checksum     = h[1];
     stats->ms_partition = tm.ms(t0, t_part);
@@ -1132,12 +1283,12 @@ extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512
         if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, nullptr, bS, shift2, offS))) return rc;
         const BucketSet R = {bR, offR, offR + 1, nr}, S = {bS, offS, offS + 1, ns};
         u64 h[16];
-        int done = 0;
         if ((rc = bucket_collect(ctx, R, S, d_state, d_list))) return rc;
-        SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
         t_part = tm.mark();
+        if ((rc = bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
+        SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
         SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-        if ((rc = bucket_join(ctx, R, S, lo_shift, lbits, d_state, h, d_list, acc, &done))) return rc;
+        const int done = bucket_join_valid(h, lbits);
         if (!done) {
             // heavy on both sides: general path on the same items (partitioning does not matter to it)
             u64 *aR = (u64 *)sc.get(nr * 8), *aS = (u64 *)sc.get(ns * 8), *sr = nullptr, *ss = nullptr;

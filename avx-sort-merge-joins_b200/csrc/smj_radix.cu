@@ -15,6 +15,7 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <type_traits>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -561,24 +562,30 @@ struct LimitSlots {
     __device__ __forceinline__ void raise_key() const {}
 };
 
+// the tile's items, thread-strided: item[j] = src[j * THREADS + thread]
+template <int THREADS, int IPT, bool FULL>
+__device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__restrict__ src, u32 valid) {
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+        item[j] = (FULL || j * THREADS + threadIdx.x < valid) ? ld_stream(src + threadIdx.x + j * THREADS)
+                                                              : ~0ull;
+}
+
+// One tile whose items are already in registers (unstable_load).  s_cnt must be zero on entry and
+// is zero again on return (after a __syncthreads() of the caller).  next_src != null: the CTA's
+// next tile (a FULL one) is requested into item[] as soon as the registers are free, i.e. before
+// this tile is written out, so its DRAM latency hides behind the output phase.
 template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit>
-__device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
-                                              const F &fn, u64 *cursors, u32 tile, u32 valid,
-                                              u64 *s_items, u32 *s_cnt, u64 *s_goff, u32 *s_wsum,
-                                              const LIM &lim = LIM()) {
+__device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restrict__ out, const F &fn,
+                                                 u64 *cursors, u32 valid, u64 *s_items, u32 *s_cnt,
+                                                 u64 *s_goff, u32 *s_wsum, const LIM &lim,
+                                                 const u64 *__restrict__ next_src) {
     constexpr int NB   = 1 << BITS;
     constexpr int TILE = THREADS * IPT;
     constexpr int BPT  = (NB + THREADS - 1) / THREADS;
-    const u64 tile_start = (u64)tile * TILE;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 last_bin = fn.last_bin();
-
-    u64       item[IPT];
     u32       pos2[IPT / 2];
-    const u64 *src = in + tile_start + threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < IPT; j++)
-        item[j] = (FULL || j * THREADS + threadIdx.x < valid) ? ld_stream(src + j * THREADS) : ~0ull;
     if (LIM::keys) {
         u32 bad = 0;
 #pragma unroll
@@ -655,6 +662,8 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
         }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;  // ready for the next tile
+    if (next_src) unstable_load<THREADS, IPT, true>(item, next_src, (u32)TILE);
     if (FULL) {
 #pragma unroll 4
         for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
@@ -669,8 +678,20 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
     }
 }
 
-template <int THREADS, int IPT, int BITS, class F, bool AGG, class LIM>
-__global__ void __launch_bounds__(THREADS, 2)
+// one tile, not pipelined: in[0 .. valid) -> out
+template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit>
+__device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *__restrict__ out,
+                                              const F &fn, u64 *cursors, u32 valid, u64 *s_items,
+                                              u32 *s_cnt, u64 *s_goff, u32 *s_wsum,
+                                              const LIM &lim = LIM()) {
+    u64 item[IPT];
+    unstable_load<THREADS, IPT, FULL>(item, in, valid);
+    unstable_process<THREADS, IPT, BITS, F, FULL, AGG, LIM>(item, out, fn, cursors, valid, s_items, s_cnt,
+                                                            s_goff, s_wsum, lim, nullptr);
+}
+
+template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM>
+__global__ void __launch_bounds__(THREADS, MINB)
     k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n,
                         const __grid_constant__ F fn,
                         u64 *cursors /* [NB], initialised to the start of every bin */,
@@ -684,32 +705,56 @@ __global__ void __launch_bounds__(THREADS, 2)
     __shared__ u32 s_wsum[32];
     for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;
     __syncthreads();
-    const u32 tile   = blockIdx.x;
-    const u64 remain = n - (u64)tile * TILE;
-    if (remain >= (u64)TILE)
-        unstable_tile<THREADS, IPT, BITS, F, true, AGG, LIM>(in, out, fn, cursors, tile, (u32)TILE,
-                                                             s_items, s_cnt, s_goff, s_wsum, lim);
-    else
-        unstable_tile<THREADS, IPT, BITS, F, false, AGG, LIM>(in, out, fn, cursors, tile, (u32)remain,
-                                                              s_items, s_cnt, s_goff, s_wsum, lim);
+    // persistent CTAs: tile t, t + grid, ...; the next tile is in flight while this one is written
+    const u64 nfull = n / TILE;
+    u64       tile  = blockIdx.x;
+    if (tile < nfull) {
+        u64 item[IPT];
+        unstable_load<THREADS, IPT, true>(item, in + tile * TILE, (u32)TILE);
+        while (true) {
+            const u64  next = tile + gridDim.x;
+            const u64 *nsrc = next < nfull ? in + next * TILE : nullptr;
+            unstable_process<THREADS, IPT, BITS, F, true, AGG, LIM>(item, out, fn, cursors, (u32)TILE, s_items,
+                                                                    s_cnt, s_goff, s_wsum, lim, nsrc);
+            __syncthreads();
+            if (!nsrc) break;
+            tile = next;
+        }
+    }
+    if (n % TILE && blockIdx.x == nfull % gridDim.x)  // the ragged last tile
+        unstable_tile<THREADS, IPT, BITS, F, false, AGG, LIM>(in + nfull * TILE, out, fn, cursors,
+                                                              (u32)(n - nfull * TILE), s_items, s_cnt,
+                                                              s_goff, s_wsum, lim);
+}
+
+template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM>
+int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim) {
+    constexpr int    NB = 1 << BITS, TILE = THREADS * IPT;
+    constexpr size_t SMEM = (size_t)TILE * 8 + NB * 4 + NB * 8;
+    static int       attr_gen = -1;
+    if (attr_gen != ctx->generation) {
+        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_gen = ctx->generation;
+    }
+    // One CTA per tile: measured faster on HBM-resident input than persistent CTAs with the next
+    // tile in flight (0.49 vs 0.52 ms per 128 M items; the kernel is bound by the shared-memory
+    // pipe, not by load latency).  Persistent CTAs (the kernel supports any grid) pay off when the
+    // input is host memory read over PCIe, where a tile's load latency is several microseconds.
+    const bool     host_in = smj_is_host_pointer(in);
+    const unsigned grid = host_in ? (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB)
+                                  : (unsigned)div_up(n, TILE);
+    SMJ_ITEMS(ctx, n);
+    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>), grid, THREADS, SMEM, in, out,
+               n, fn, bases, lim);
+    return 0;
 }
 
 // bases: [NB] start of every bin; it is used as the cursor array and is CONSUMED (on return
 // bases[b] is the end of bin b)
 template <int BITS, class F, bool AGG = false, class LIM = NoLimit>
 int launch_unstable(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim = LIM()) {
-    constexpr int    THREADS = 512, IPT = 16, NB = 1 << BITS, TILE = THREADS * IPT;
-    constexpr size_t SMEM    = (size_t)TILE * 8 + NB * 4 + NB * 8;
-    static int       attr_gen = -1;
-    if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, BITS, F, AGG, LIM>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_gen = ctx->generation;
-    }
-    SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, BITS, F, AGG, LIM>), (unsigned)div_up(n, TILE),
-               THREADS, SMEM, in, out, n, fn, bases, lim);
-    return 0;
+    return launch_unstable_shape<512, 16, 2, BITS, F, AGG, LIM>(ctx, in, out, n, fn, bases, lim);
 }
 
 // Wide digits want big tiles: with 512 bins a 4096-item tile has only 8 items per bin to amortise
@@ -1104,44 +1149,46 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_tile_prefix(const u64 *__restric
     if (b == MSD_NB - 1) tile_prefix[MSD_NB] = s_t[b];
 }
 
-// Which pass-A bucket does tile `tile` belong to, and which items does it cover?  Called by all
-// MSD_THREADS (== number of buckets) threads of a CTA: thread b tests bucket b, so the lookup is
-// one coalesced load instead of a ten-step dependent binary search per tile.
-__device__ __forceinline__ void msd_locate(const u64 *__restrict__ tile_prefix,
-                                           const u64 *__restrict__ bucket_start,
-                                           const u64 *__restrict__ bucket_count, u64 tile,
-                                           u32 *s_bucket, u64 *s_start, u32 *s_valid) {
-    const u32 b  = threadIdx.x;
-    const u64 t0 = tile_prefix[b], t1 = tile_prefix[b + 1];
-    if (b == 0) *s_valid = 0;  // stays 0 when the tile lies past the last bucket
-    __syncthreads();
-    if (t0 <= tile && tile < t1) {  // exactly one non-empty bucket matches
-        const u64 first = bucket_start[b], start = first + (tile - t0) * (u64)MSD_TILE;
-        *s_bucket       = b;
-        *s_start        = start;
-        *s_valid        = (u32)min((u64)MSD_TILE, first + bucket_count[b] - start);
+// The tiles of pass B: tile t covers items [start, start + valid) of first-level bucket `bucket`
+// (a tile never straddles two buckets).  CTA b writes the entries of bucket b's tiles.
+struct __align__(16) MsdTile {
+    u64 start;
+    u32 bucket, valid;
+};
+__device__ __forceinline__ void msd_write_tiles(MsdTile *__restrict__ tiles, u32 b, u64 first_tile,
+                                                u64 start, u64 count) {
+    const u64 nt = (count + MSD_TILE - 1) / MSD_TILE;
+    for (u64 t = threadIdx.x; t < nt; t += blockDim.x) {
+        MsdTile e;
+        e.start  = start + t * MSD_TILE;
+        e.bucket = b;
+        e.valid  = (u32)min((u64)MSD_TILE, count - t * MSD_TILE);
+        tiles[first_tile + t] = e;
     }
+}
+__global__ void __launch_bounds__(256) k_msd_tile_table(const u64 *__restrict__ tile_prefix,
+                                                        const u64 *__restrict__ bucket_start,
+                                                        const u64 *__restrict__ bucket_count,
+                                                        MsdTile *__restrict__ tiles) {
+    const u32 b = blockIdx.x;
+    msd_write_tiles(tiles, b, tile_prefix[b], bucket_start[b], bucket_count[b]);
 }
 
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict__ in,
+                                                           const MsdTile *__restrict__ tiles,
                                                            const u64 *__restrict__ tile_prefix,
-                                                           const u64 *__restrict__ bucket_start,
-                                                           const u64 *__restrict__ bucket_count,
                                                            FieldFn fn2, u64 *__restrict__ hist2) {
     __shared__ u32 sh[MSD_NB];
-    __shared__ u32 s_bucket, s_valid;
-    __shared__ u64 s_start;
-    msd_locate(tile_prefix, bucket_start, bucket_count, blockIdx.x, &s_bucket, &s_start, &s_valid);
-    sh[threadIdx.x] = 0;
+    if (blockIdx.x >= tile_prefix[MSD_NB]) return;
+    const MsdTile ti = tiles[blockIdx.x];
+    sh[threadIdx.x]  = 0;
     __syncthreads();
-    const u32 valid = s_valid;
-    if (valid == 0) return;
-    const u64 *src = in + s_start;
+    const u64 *src = in + ti.start;
 #pragma unroll 4
-    for (u32 i = threadIdx.x; i < valid; i += MSD_THREADS) atomicAdd(&sh[fn2(ld_stream(src + i))], 1u);
+    for (u32 i = threadIdx.x; i < ti.valid; i += MSD_THREADS) atomicAdd(&sh[fn2(ld_stream(src + i))], 1u);
     __syncthreads();
     const u32 c = sh[threadIdx.x];
-    if (c) atomicAdd(&hist2[(u64)s_bucket * MSD_NB + threadIdx.x], (u64)c);
+    if (c) atomicAdd(&hist2[(u64)ti.bucket * MSD_NB + threadIdx.x], (u64)c);
 }
 
 // OPT = false: exact pass (cursors2 start at the bucket offsets a histogram pass produced).
@@ -1149,11 +1196,11 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict
 // items from base2[b] on (cursors2 start at the slot starts); a reservation that does not fit its
 // slot goes to the dump area and raises flag[bucket] (see LimitSlots); flagged buckets are
 // repartitioned exactly by the k_msd_fix_* kernels, on the device, without asking the host.
+// Persistent CTAs over the tile table; a full next tile is requested while this one is written.
 template <bool OPT>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
-    k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out,
-                   const u64 *__restrict__ tile_prefix, const u64 *__restrict__ bucket_start,
-                   const u64 *__restrict__ bucket_count, const __grid_constant__ FieldFn fn2,
+    k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
+                   const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
                    u64 *cursors2 /* [512][512] */, const u64 *__restrict__ base2,
                    const u64 *__restrict__ cap2, u64 dump, u32 *flag, int shrink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1161,34 +1208,46 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
     u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
     __shared__ u32 s_wsum[32];
-    __shared__ u32 s_bucket, s_valid;
-    __shared__ u64 s_start;
-    msd_locate(tile_prefix, bucket_start, bucket_count, blockIdx.x, &s_bucket, &s_start, &s_valid);
+    const u64 ntiles = tile_prefix[MSD_NB];
+    u64       t      = blockIdx.x;
+    if (t >= ntiles) return;
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const u32 valid = s_valid;
-    if (valid == 0) return;
-    u64 *cur = cursors2 + (u64)s_bucket * MSD_NB;
-    if (OPT) {
-        const LimitSlots lim = {base2, cap2, s_bucket, (u32)shrink, dump, flag};
-        if (valid == (u32)MSD_TILE)
-            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, LimitSlots>(
-                in + s_start, out, fn2, cur, 0u, valid, s_items, s_cnt, s_goff, s_wsum, lim);
-        else
-            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false, false, LimitSlots>(
-                in + s_start, out, fn2, cur, 0u, valid, s_items, s_cnt, s_goff, s_wsum, lim);
-    } else {
-        if (valid == (u32)MSD_TILE)
-            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + s_start, out, fn2, cur, 0u, valid,
-                                                                  s_items, s_cnt, s_goff, s_wsum);
-        else
-            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + s_start, out, fn2, cur, 0u, valid,
-                                                                   s_items, s_cnt, s_goff, s_wsum);
+    using Lim = typename std::conditional<OPT, LimitSlots, NoLimit>::type;
+    u64     item[MSD_IPT];
+    MsdTile ti   = tiles[t];
+    bool    have = false;  // item[] already holds tile t
+    while (true) {
+        const u64 tn  = t + gridDim.x;
+        MsdTile   nx  = ti;
+        bool      pre = false;
+        if (tn < ntiles) {
+            nx  = tiles[tn];
+            pre = nx.valid == (u32)MSD_TILE;
+        }
+        const u64 *nsrc = pre ? in + nx.start : nullptr;
+        u64       *cur  = cursors2 + (u64)ti.bucket * MSD_NB;
+        Lim        lim;
+        if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, dump, flag};
+        if (ti.valid == (u32)MSD_TILE) {
+            if (!have) unstable_load<MSD_THREADS, MSD_IPT, true>(item, in + ti.start, ti.valid);
+            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim>(
+                item, out, fn2, cur, ti.valid, s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
+        } else {
+            unstable_load<MSD_THREADS, MSD_IPT, false>(item, in + ti.start, ti.valid);
+            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, false, false, Lim>(
+                item, out, fn2, cur, ti.valid, s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
+        }
+        if (tn >= ntiles) break;
+        __syncthreads();
+        t    = tn;
+        ti   = nx;
+        have = pre;
     }
 }
 
 // ---- optimistic (histogram-free) partitioning: sample, capacities, slots ----------------------
-// One read of a jittered strided sample of R and S (32-byte sectors, at most max_sectors per
+// One read of a jittered strided sample of R and S (128-byte lines, at most max_sectors / 4 per
 // relation) gives (1) the OR / AND of the sampled keys -> the digit plan, computed by every CTA
 // after a grid barrier exactly as the host computes it, (2) the sampled first-level histogram ->
 // bin capacities of the first pass, (3) the largest sampled count of any 18-bit bucket -> a skew
@@ -1204,9 +1263,12 @@ __global__ void __launch_bounds__(SAMP_THREADS)
     const u32  rel  = blockIdx.y;
     const u64 *in   = rel ? s : r;
     const u64  n    = rel ? ns : nr;
-    const u64  nsec = n >> 2;
-    const u64  S    = min(nsec, (u64)max_sectors);
-    const u64  step = S ? nsec / S : 0;
+    // whole 128-byte lines (16 items) are sampled, four consecutive threads per line: a quarter
+    // of the distinct DRAM rows / TLB entries of isolated sectors for the same number of items
+    const u64  nline = n >> 4;
+    const u64  L     = min(nline, (u64)(max_sectors >> 2));
+    const u64  S     = L * 4;
+    const u64  step  = L ? nline / L : 0;
     u32        kor = 0, kand = ~0u;
     u64        x[SAMP_SPT][4];  // this thread's sampled items: all loads in flight together
     bool       ok[SAMP_SPT];
@@ -1216,8 +1278,9 @@ __global__ void __launch_bounds__(SAMP_THREADS)
         const u64 i = ((u64)k * SAMP_THREADS + threadIdx.x) * gridDim.x + blockIdx.x;
         ok[k]       = i < S;
         if (ok[k]) {
-            const u32 jit = ((u32)i * 2654435761u) >> 16;
-            const u64 sec = (i * nsec) / S + (((u64)jit * step) >> 16);
+            const u64 l   = i >> 2;
+            const u32 jit = ((u32)l * 2654435761u) >> 16;
+            const u64 sec = ((l * nline) / L + (((u64)jit * step) >> 16)) * 4 + (i & 3);
 #pragma unroll
             for (int u = 0; u < 4; u++) x[k][u] = in[sec * 4 + u];
         }
@@ -1277,26 +1340,65 @@ __global__ void __launch_bounds__(SAMP_THREADS)
     if (blockIdx.x == 0 && threadIdx.x == 0) st[8 + rel] = S * 4;
 }
 
+// First-level bin regions from the sampled histogram, on the device (the host computes the same
+// capacities, smj_msd_caps1, to size the buffer): tab[rel] = {cursors, starts, limits} x 512.
+// One CTA per relation.  Raises flag[2 * rel] when the regions do not fit alloc[rel] items.
+__device__ __host__ inline u64 msd_cap1(u64 k, double scale, int shrink) {
+    u64 cap = (u64)ceil(((double)k + 7.0 * sqrt((double)k + 1.0) + 8.0) * scale);
+    if (shrink) cap = (u64)((double)k * scale * 0.5);  // test hook: bins that cannot hold their items
+    return (cap + 15) & ~15ull;
+}
+__global__ void __launch_bounds__(MSD_NB) k_msd_caps1(const u64 *__restrict__ st, u64 nr, u64 ns,
+                                                      u64 alloc_r, u64 alloc_s, int shrink,
+                                                      u64 *__restrict__ tab_r, u64 *__restrict__ tab_s,
+                                                      u32 *flag) {
+    __shared__ u64 s_c[MSD_NB];
+    const u32 rel = blockIdx.x, b = threadIdx.x;
+    const u64 n = rel ? ns : nr, alloc = rel ? alloc_s : alloc_r, nsamp = st[8 + rel];
+    u64      *tab = rel ? tab_s : tab_r;
+    if (!tab) return;
+    const double scale = nsamp ? fmax(1.0, (double)n / (double)nsamp) : 1.0;
+    const u64    cap   = msd_cap1(st[16 + rel * MSD_NB + b], scale, shrink);
+    s_c[b]             = cap;
+    __syncthreads();
+    for (int o = 1; o < MSD_NB; o <<= 1) {
+        u64 ac = (b >= (u32)o) ? s_c[b - o] : 0;
+        __syncthreads();
+        s_c[b] += ac;
+        __syncthreads();
+    }
+    const u64 start     = s_c[b] - cap;
+    tab[b]              = start;
+    tab[MSD_NB + b]     = start;
+    tab[2 * MSD_NB + b] = s_c[b];
+    if (b == MSD_NB - 1 && s_c[b] > alloc) flag[2 * rel] = 1u;
+}
+
 // Second-level layout of the optimistic pass, from the first pass's cursors: per first-level bucket
 // its item count (clipped to the capacity: an overflowing pass is repeated anyway), its tiles, and
 // the slot capacity cap2 = avg + 7 sqrt(avg) + slack of its 512 sub-buckets (a multiple of 4 items,
-// so every slot starts on a 32-byte sector).  Raises *flag and plans no tiles when the slots do
-// not fit alloc2 items.
-__global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restrict__ cur1,
-                                                            const u64 *__restrict__ start1,
-                                                            const u64 *__restrict__ limit1, u64 alloc2,
+// so every slot starts on a 32-byte sector).  CTA b redoes the (cheap) scans and writes the slot
+// starts and initial cursors of bucket b's sub-buckets; CTA 0 also writes the per-bucket arrays.
+// Raises *flag and plans no tiles when the slots do not fit alloc2 items.
+__global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restrict__ tab1, u64 alloc2,
                                                             u64 *__restrict__ tile_prefix,
                                                             u64 *__restrict__ bucket_count,
                                                             u64 *__restrict__ cap2,
-                                                            u64 *__restrict__ base2, u32 *flag) {
-    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB];
+                                                            u64 *__restrict__ base2,
+                                                            u64 *__restrict__ starts,
+                                                            u64 *__restrict__ cursors,
+                                                            MsdTile *__restrict__ tiles, u32 *flag) {
+    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB], s_cap[MSD_NB], s_cnt1[MSD_NB];
     const int b   = threadIdx.x;
-    const u64 c   = min(cur1[b] - start1[b], limit1[b] - start1[b]);
+    const u64 st1 = tab1[MSD_NB + b];
+    const u64 c   = min(tab1[b] - st1, tab1[2 * MSD_NB + b] - st1);
     const u64 t   = (c + MSD_TILE - 1) / MSD_TILE;
     const u64 avg = (c + MSD_NB - 1) / MSD_NB;
     const u64 cap = c ? ((avg + (u64)ceil(7.0 * sqrt((double)avg + 1.0)) + 8 + 3) & ~3ull) : 0ull;
     s_t[b]        = t;
     s_c[b]        = cap * MSD_NB;
+    s_cap[b]      = cap;
+    s_cnt1[b]     = c;
     __syncthreads();
     for (int o = 1; o < MSD_NB; o <<= 1) {
         u64 at = (b >= o) ? s_t[b - o] : 0, ac = (b >= o) ? s_c[b - o] : 0;
@@ -1306,13 +1408,23 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restric
         __syncthreads();
     }
     const bool fits = s_c[MSD_NB - 1] <= alloc2;
-    tile_prefix[b]  = fits ? s_t[b] - t : 0;
-    bucket_count[b] = c;
-    cap2[b]         = cap;
-    base2[b]        = s_c[b] - cap * MSD_NB;
-    if (b == MSD_NB - 1) {
-        tile_prefix[MSD_NB] = fits ? s_t[b] : 0;
-        if (!fits) *flag = 1u;
+    if (blockIdx.x == 0) {
+        tile_prefix[b]  = fits ? s_t[b] - t : 0;
+        bucket_count[b] = c;
+        cap2[b]         = cap;
+        base2[b]        = s_c[b] - cap * MSD_NB;
+        if (b == MSD_NB - 1) {
+            tile_prefix[MSD_NB] = fits ? s_t[b] : 0;
+            if (!fits) *flag = 1u;
+        }
+    }
+    const u64 mycap = s_cap[blockIdx.x];
+    const u64 v     = s_c[blockIdx.x] - mycap * MSD_NB + (u64)b * mycap;
+    starts[blockIdx.x * MSD_NB + b]  = v;
+    cursors[blockIdx.x * MSD_NB + b] = v;
+    if (fits) {
+        const u64 mycnt = s_cnt1[blockIdx.x], myt = (mycnt + MSD_TILE - 1) / MSD_TILE;
+        msd_write_tiles(tiles, blockIdx.x, s_t[blockIdx.x] - myt, tab1[MSD_NB + blockIdx.x], mycnt);
     }
 }
 
@@ -1321,15 +1433,6 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_counts_opt(const u64 *__restrict
                                                            u64 *__restrict__ counts) {
     const int b = threadIdx.x;
     counts[b]   = min(tab[b] - tab[MSD_NB + b], tab[2 * MSD_NB + b] - tab[MSD_NB + b]);
-}
-
-// slot starts of all 2^18 sub-buckets: bucket starts for the join and initial cursors
-__global__ void __launch_bounds__(MSD_NB) k_msd_slots(const u64 *__restrict__ base2,
-                                                      const u64 *__restrict__ cap2,
-                                                      u64 *__restrict__ starts, u64 *__restrict__ cursors) {
-    const u64 v = base2[blockIdx.x] + (u64)threadIdx.x * cap2[blockIdx.x];
-    starts[blockIdx.x * MSD_NB + threadIdx.x]  = v;
-    cursors[blockIdx.x * MSD_NB + threadIdx.x] = v;
 }
 
 // ---- exact repeat of the second level for the flagged first-level buckets, all on the device ----
@@ -1417,6 +1520,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     __shared__ u32 s_wsum[32];
     __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32];
     const u32 nflag = msd_flagged_list(flag, s_list, s_wcnt);
+    s_cnt[threadIdx.x] = 0;
     for (u32 q = 0; q < nflag; q++) {
         const u32 b     = s_list[q];
         const u64 first = bucket_start[b], cnt = bucket_count[b];
@@ -1424,15 +1528,13 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
         for (u64 t = blockIdx.x; t * MSD_TILE < cnt; t += gridDim.x) {
             const u64 lo    = t * MSD_TILE;
             const u32 valid = (u32)min((u64)MSD_TILE, cnt - lo);
-            __syncthreads();  // the previous tile is done with the staging area
-            s_cnt[threadIdx.x] = 0;
-            __syncthreads();
+            __syncthreads();  // the previous tile is done with the staging area, s_cnt is zero
             if (valid == (u32)MSD_TILE)
-                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + first + lo, out, fn2, cur, 0u,
-                                                                      valid, s_items, s_cnt, s_goff, s_wsum);
+                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + first + lo, out, fn2, cur, valid,
+                                                                      s_items, s_cnt, s_goff, s_wsum);
             else
-                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + first + lo, out, fn2, cur, 0u,
-                                                                       valid, s_items, s_cnt, s_goff, s_wsum);
+                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + first + lo, out, fn2, cur, valid,
+                                                                       s_items, s_cnt, s_goff, s_wsum);
         }
     }
 }
@@ -1508,27 +1610,28 @@ int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const 
     FieldFn f2 = {shift2, (u32)MSD_NB - 1};
     SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_counts, d_starts, d_tpref, d_bstart, d_bcount);
     const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
+    if (!d_tiles) return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
+    SMJ_LAUNCH(ctx, k_msd_tile_table, MSD_NB, 256, 0, d_tpref, d_bstart, d_bcount, d_tiles);
+    const unsigned grid2 = max_tiles;  // one CTA per tile (see launch_unstable_shape)
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tpref, d_bstart, d_bcount, f2, d_hist2);
+    SMJ_LAUNCH(ctx, k_msd_hist2, max_tiles, MSD_THREADS, 0, a, d_tiles, d_tpref, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_scan_local, NB2 / 1024, 1024, 0, d_hist2, (u64)NB2, offsets, d_tot);
     SMJ_LAUNCH(ctx, k_scan_add, NB2 / 1024, 1024, 0, offsets, (u64)NB2, d_tot);
     SMJ_CHECK(cudaMemcpyAsync(d_cur2, offsets, (size_t)NB2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_scatter2<false>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tpref, d_bstart,
-               d_bcount, f2, d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, 0ull, (u32 *)nullptr, 0);
+    SMJ_LAUNCH(ctx, k_msd_scatter2<false>, grid2, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2,
+               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, 0ull, (u32 *)nullptr, 0);
     return 0;
 }
 
 // ---- optimistic passes -------------------------------------------------------------------------
 // Sample of R and S (see k_msd_sample).  host: SMJ_MSD_SAMPLE_WORDS u64.  Synchronises.
-int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *host) {
+int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *d_st,
+                   u32 *d_sub, u64 *host) {
     if (max_sectors > SAMP_MAX_SECTORS) max_sectors = SAMP_MAX_SECTORS;
-    SmjScratch sc(ctx);
-    u64 *d_st  = (u64 *)sc.get(SAMP_WORDS * 8);
-    u32 *d_sub = (u32 *)sc.get((size_t)2 * MSD_NB * MSD_NB * 4);
-    if (!d_st || !d_sub) return smj_fail_msg("smj_msd_sample: scratch allocation failed");
     SMJ_CHECK(cudaMemsetAsync(d_st, 0, SAMP_WORDS * 8, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_sub, 0, (size_t)2 * MSD_NB * MSD_NB * 4, ctx->stream));
     const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
@@ -1548,24 +1651,25 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+size_t smj_msd_sample_bytes(int which) {
+    return which == 0 ? (size_t)SAMP_WORDS * 8 : (size_t)2 * MSD_NB * MSD_NB * 4;
+}
 
 // First-level bin regions from a sampled histogram (k of nsamp items fell into the bin):
 // capacity = (k + 7 sqrt(k) + slack) n / nsamp, i.e. the estimate plus seven standard deviations
-// of the sampling error, rounded up to 16 items.  start/limit: host arrays of 512 entries.
-// Returns the number of items the regions span.  shrink (tests only) halves the capacities.
-u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, u64 *start, u64 *limit, int shrink) {
+// of the sampling error, rounded up to 16 items.  Returns the number of items the regions span
+// (what k_msd_caps1 lays out on the device).  shrink (tests only) halves the capacities.
+u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, int shrink) {
     const double scale = nsamp ? std::max(1.0, (double)n / (double)nsamp) : 1.0;
     u64          tot   = 0;
-    for (int b = 0; b < MSD_NB; b++) {
-        const double k = (double)hist[b];
-        u64 cap = (u64)ceil((k + 7.0 * sqrt(k + 1.0) + 8.0) * scale);
-        if (shrink) cap = (u64)(k * scale * 0.5);  // test hook: bins that cannot hold their items
-        cap      = (cap + 15) & ~15ull;
-        start[b] = tot;
-        tot += cap;
-        limit[b] = tot;
-    }
+    for (int b = 0; b < MSD_NB; b++) tot += msd_cap1(hist[b], scale, shrink);
     return tot;
+}
+// device tables of both relations (null = relation not partitioned optimistically)
+int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc_r, u64 alloc_s, int shrink,
+                         u64 *tab_r, u64 *tab_s, u32 *d_flags) {
+    SMJ_LAUNCH(ctx, k_msd_caps1, 2, MSD_NB, 0, d_st, nr, ns, alloc_r, alloc_s, shrink, tab_r, tab_s, d_flags);
+    return 0;
 }
 u64 smj_msd_tile_items() { return MSD_TILE; }
 // upper bound of the items the second-level slots of an n-item relation span (k_msd_level2_plan)
@@ -1574,20 +1678,17 @@ u64 smj_msd_alloc2(u64 n) {
     return n + (u64)((double)(MSD_NB * MSD_NB) * (7.0 * sqrt(per + 3.0) + 16.0)) + 4096;
 }
 
-// Optimistic pass A: in -> a, bin b into a[start[b] .. limit[b]) (host arrays), no histogram.
-// d_tab (device, 3 x 512 u64) receives {cursors = bin ends, starts, limits}; *d_flag is raised when
-// a bin overflowed (a then holds garbage in places; its dump area is a[dump .. dump + tile)).
-// Every key is checked against the sampled key range on the way: a key that differs from kref on
-// a bit position of kmask raises *d_kflag.
-int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, const u64 *start,
-                       const u64 *limit, u64 dump, u64 *d_tab, u32 *d_flag, u32 kmask, u32 kref,
-                       u32 *d_kflag) {
-    SMJ_CHECK(cudaMemcpyAsync(d_tab, start, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    SMJ_CHECK(cudaMemcpyAsync(d_tab + MSD_NB, start, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    SMJ_CHECK(cudaMemcpyAsync(d_tab + 2 * MSD_NB, limit, MSD_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
+// Optimistic pass A: in -> a, bin b into a[start[b] .. limit[b]), no histogram.  d_tab (device,
+// 3 x 512 u64 = {cursors, starts, limits}, laid out by k_msd_caps1; the cursors end up as the bin
+// ends); *d_flag is raised when a bin overflowed (a then holds garbage in places; its dump area is
+// a[dump .. dump + tile)).  Every key is checked against the sampled key range on the way: a key
+// that differs from kref on a bit position of kmask raises *d_kflag.
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 dump, u64 *d_tab,
+                       u32 *d_flag, u32 kmask, u32 kref, u32 *d_kflag) {
     if (n == 0) return 0;
     FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
     const LimitArray lim = {d_tab + 2 * MSD_NB, dump, d_flag, kmask, kref, d_kflag};
+    // (tile shapes 256x16, 512x12, 384x16 and 1024x8 were measured: 512x16 with 2 CTAs per SM wins)
     return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, a, n, f1, d_tab, lim);
 }
 
@@ -1614,15 +1715,16 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     SMJ_CHECK(cudaMemsetAsync(d_bflag, 0, MSD_NB * 4, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)MSD_NB * MSD_NB * 4, ctx->stream));
     FieldFn f2 = {shift2, (u32)MSD_NB - 1};
-    SMJ_LAUNCH(ctx, k_msd_level2_plan, 1, MSD_NB, 0, d_tab, d_tab + MSD_NB, d_tab + 2 * MSD_NB, alloc2, d_tpref,
-               d_counts, d_cap2, d_base2, d_flag);
-    SMJ_LAUNCH(ctx, k_msd_slots, MSD_NB, MSD_NB, 0, d_base2, d_cap2, starts, ends);
     const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
+    MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
+    if (!d_tiles) return smj_fail_msg("smj_msd_pass_b_opt: scratch allocation failed");
+    SMJ_LAUNCH(ctx, k_msd_level2_plan, MSD_NB, MSD_NB, 0, d_tab, alloc2, d_tpref, d_counts, d_cap2, d_base2,
+               starts, ends, d_tiles, d_flag);
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 2, max_tiles);
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tpref,
-               d_tab + MSD_NB, d_counts, f2, ends, d_base2, d_cap2, alloc2, d_bflag, shrink);
-    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 2, max_tiles);
+    SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
+               d_base2, d_cap2, alloc2, d_bflag, shrink);
     SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,

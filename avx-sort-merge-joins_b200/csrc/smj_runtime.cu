@@ -65,12 +65,14 @@ static int ctx_init_locked(int device) {
     if (device >= ndev) return smj_fail_msg("smjdev_init: device index out of range");
     SMJ_CHECK(cudaSetDevice(device));
     if (g_ctx.ready && g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
+    if (g_ctx.ready && g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
     cudaDeviceProp prop;
     SMJ_CHECK(cudaGetDeviceProperties(&prop, device));
     g_ctx.device   = device;
     g_ctx.generation++;
     g_ctx.sm_count = prop.multiProcessorCount;
     SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
+    SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     g_ctx.stream = g_ctx.own_stream;
     // keep freed scratch in the pool: cudaMallocAsync then costs microseconds, not a driver call
     cudaMemPool_t pool;
@@ -79,6 +81,15 @@ static int ctx_init_locked(int device) {
     SMJ_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     g_ctx.ready = true;
     return 0;
+}
+
+bool smj_is_host_pointer(const void *p) {
+    cudaPointerAttributes attr;
+    if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
 }
 
 SmjCtx *smj_ctx() {

@@ -42,12 +42,14 @@ static int is_device_ptr(const void *p) {
     return k == 2 || k == 3;
 }
 
-/* returns 0 on success; copy != 0 uploads the contents */
+/* returns 0 on success; copy != 0 uploads the contents.  copy == 2 (joins): a pinned host buffer is
+ * handed to the device layer as it is: smjdev_join uploads it chunk by chunk on its copy stream and
+ * starts partitioning while the transfer is still running. */
 static int stage_in(devbuf_t *b, const void *p, uint64_t n, int copy) {
     b->d     = NULL;
     b->owned = 0;
     if (n == 0) return 0;
-    if (is_device_ptr(p)) {
+    if (is_device_ptr(p) || (copy == 2 && smjdev_pointer_kind(p) == 1 && !getenv("SMJ_NO_OVERLAP"))) {
         b->d = (uint64_t *)p;
         return 0;
     }
@@ -104,8 +106,8 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
     memset(&dr, 0, sizeof(dr));
     memset(&ds, 0, sizeof(ds));
     failed = smjdev_init(-1) || smjdev_event_create(&e0) || smjdev_event_create(&e1) ||
-             smjdev_event_record(e0) || stage_in(&dr, relR->tuples, relR->num_tuples, 1) ||
-             stage_in(&ds, relS->tuples, relS->num_tuples, 1) || smjdev_event_record(e1) ||
+             smjdev_event_record(e0) || stage_in(&dr, relR->tuples, relR->num_tuples, 2) ||
+             stage_in(&ds, relS->tuples, relS->num_tuples, 2) || smjdev_event_record(e1) ||
              /* m-pass / mpsm work on NTHREADS sorted runs per relation, like the reference's threads */
              smjdev_join(algo, dr.d, relR->num_tuples, ds.d, relS->num_tuples, nthreads, &st);
     if (!failed && (dr.owned || ds.owned)) smjdev_event_elapsed_ms(e0, e1, &ms_h2d);
@@ -117,7 +119,7 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
         smj_fatal(name); /* exits unless SMJ_NO_EXIT */
         return NULL;
     }
-    st.ms_h2d = ms_h2d;
+    if (dr.owned || ds.owned) st.ms_h2d += ms_h2d; /* (pinned relations: measured by smjdev_join) */
     gettimeofday(&end, NULL);
 
     g_last_stats = st;

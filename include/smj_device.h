@@ -144,7 +144,10 @@ typedef struct smj_join_stats_t {
  * histogram-free (sampled-capacity) partition pass.  m-pass / mpsm report SMJ_PATH_GENERAL. */
 enum { SMJ_PATH_GENERAL = 0, SMJ_PATH_MSD = 1, SMJ_PATH_MSD_OPT = 2 };
 
-/* Device-resident join: r/s are device arrays and are left unmodified.
+/* Join of two relations in device memory or in PINNED host memory (left unmodified).  A pinned
+ * host relation is uploaded in 64 MiB chunks on a separate copy stream; the m-way path runs its
+ * first partitioning pass on every chunk as it arrives, so partitioning hides behind the PCIe
+ * transfer (stats->ms_h2d = duration of the copies).
  * nruns: number of sorted runs per relation for m-pass / mpsm (>=1; m-way ignores it). */
 int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                 int nruns, smj_join_stats_t *stats);

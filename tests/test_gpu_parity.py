@@ -410,6 +410,60 @@ def test_mway_optimistic_partition_input_orders(smj, orc):
     assert (st.matches, st.checksum) == orc.join_bruteforce(base, s2)
 
 
+def test_join_pinned_host_relations_overlap_upload(smj, orc, monkeypatch):
+    """Pinned host relations go to smjdev_join as they are: uploaded in 64 MiB chunks on the copy
+    stream while the first partitioning pass consumes the chunks (several chunks per relation
+    here).  Same result as the device-resident join and the oracle, for every algorithm, through
+    the device layer and through sortmergejoin_multiway()."""
+    nr, ns = 17_000_001, 9_000_001
+    r, s = orc.gen_unique(nr, 12345), orc.gen_fk(ns, nr, 7)
+    exp = orc.join_bruteforce(r, s)
+    assert exp[0] == ns
+    lib = smj.lib
+    hr, hs = lib.smjdev_host_alloc(nr * 8), lib.smjdev_host_alloc(ns * 8)
+    assert hr and hs
+    C.memmove(hr, r.ctypes.data, nr * 8)
+    C.memmove(hs, s.ctypes.data, ns * 8)
+    try:
+        for algo, nruns in ((smj.ALGO_MWAY, 1), (smj.ALGO_MPASS, 4), (smj.ALGO_MPSM, 2)):
+            st = smj.smj_join_stats_t()
+            smj.check(lib.smjdev_join(algo, hr, nr, hs, ns, nruns, C.byref(st)), "smjdev_join")
+            assert (st.matches, st.checksum) == exp, algo
+            assert st.ms_h2d > 0
+            if algo == smj.ALGO_MWAY:
+                assert st.path == smj.PATH_MSD_OPT
+        # mixed: R on the device, S pinned; and the exact passes (the upload is awaited first)
+        dr = smj.DeviceBuffer.from_host(r)
+        st = smj.smj_join_stats_t()
+        smj.check(lib.smjdev_join(smj.ALGO_MWAY, dr.ptr, nr, hs, ns, 1, C.byref(st)), "smjdev_join")
+        assert (st.matches, st.checksum) == exp
+        monkeypatch.setenv("SMJ_MSD_MODE", "exact")
+        smj.check(lib.smjdev_join(smj.ALGO_MWAY, hr, nr, hs, ns, 1, C.byref(st)), "smjdev_join")
+        assert (st.matches, st.checksum, st.path) == (*exp, smj.PATH_MSD)
+        monkeypatch.delenv("SMJ_MSD_MODE")
+        monkeypatch.setenv("SMJ_MSD_TEST", "shrink1")  # overflow -> exact repeat from the uploaded copy
+        smj.check(lib.smjdev_join(smj.ALGO_MWAY, hr, nr, hs, ns, 1, C.byref(st)), "smjdev_join")
+        assert (st.matches, st.checksum, st.repeats) == (*exp, 2)
+        monkeypatch.delenv("SMJ_MSD_TEST")
+        dr.free()
+        # the reference-facing entry point with the same pinned buffers
+        cfg = smj.joinconfig_t(1, 128, 0, 0, 20 * 1024 * 1024, smj.NUMA_NEXT)
+        relr, rels = smj.relation_t(hr, nr), smj.relation_t(hs, ns)
+        res = lib.sortmergejoin_multiway(C.byref(relr), C.byref(rels), C.byref(cfg))
+        assert res and res.contents.totalresults == ns
+        hst = smj.smj_join_stats_t()
+        lib.smj_last_join_stats(C.byref(hst))
+        assert (hst.matches, hst.checksum) == exp and hst.ms_h2d > 0
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+        libc.free(C.cast(res, C.c_void_p))
+        assert np.array_equal(np.ctypeslib.as_array(C.cast(hr, C.POINTER(C.c_uint64)), shape=(nr,)), r)
+    finally:
+        lib.smjdev_host_free(hr)
+        lib.smjdev_host_free(hs)
+
+
 # ------------------------------------------------------------------------------------ host memory paths
 def test_pageable_relations_use_the_staging_pipeline(smj, orc):
     """Relations in ordinary malloc'ed memory above the staging threshold (32 MiB): upload through
