@@ -626,8 +626,10 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
         gbase[q]    = 0;
         tsum += cntb[q];
         if (b <= last_bin && cntb[q]) {
-            gbase[q] = atomicAdd(&cursors[b], (u64)cntb[q]);
-            if (LIM::on && gbase[q] + cntb[q] > lim(b)) {  // does not fit: dump + tell the host
+            // the limit is requested before the atomic, so that the two round trips to L2 overlap
+            const u64 limit = LIM::on ? lim(b) : ~0ull;
+            gbase[q]        = atomicAdd(&cursors[b], (u64)cntb[q]);
+            if (LIM::on && gbase[q] + cntb[q] > limit) {  // does not fit: dump + raise the flag
                 gbase[q] = lim.dump_at();
                 lim.raise();
             }
@@ -1269,14 +1271,17 @@ __global__ void __launch_bounds__(SAMP_THREADS)
     const u64  L     = min(nline, (u64)(max_sectors >> 2));
     const u64  S     = L * 4;
     const u64  step  = L ? nline / L : 0;
+    const u32  per_cta = ((u32)((S + gridDim.x - 1) / gridDim.x) + 3u) & ~3u;  // <= SAMP_THREADS * SAMP_SPT
     u32        kor = 0, kand = ~0u;
     u64        x[SAMP_SPT][4];  // this thread's sampled items: all loads in flight together
     bool       ok[SAMP_SPT];
     for (int i = threadIdx.x; i < MSD_NB; i += SAMP_THREADS) s_h[i] = 0;
 #pragma unroll
     for (int k = 0; k < SAMP_SPT; k++) {
-        const u64 i = ((u64)k * SAMP_THREADS + threadIdx.x) * gridDim.x + blockIdx.x;
-        ok[k]       = i < S;
+        // CTA c samples the c-th part of the relation: an SM touches a few pages, not all of them
+        const u32 w = (u32)k * SAMP_THREADS + threadIdx.x;
+        const u64 i = (u64)blockIdx.x * per_cta + w;
+        ok[k]       = w < per_cta && i < S;
         if (ok[k]) {
             const u64 l   = i >> 2;
             const u32 jit = ((u32)l * 2654435761u) >> 16;
