@@ -225,8 +225,8 @@ def run_single_gpu(args, smj) -> dict:
     prof = parse_profile(buf.value.decode())
     total_kernel_ms = sum(p["ms"] for p in prof.values()) or 1.0
     top = max(prof, key=lambda k: prof[k]["ms"])
-    bytes_per_item = {"k_onesweep": 16, "k_msd_scatter2": 16, "k_msd_hist2": 8, "k_bucket_join": 8,
-                      "k_mj_tile": 8, "k_hist_digits": 8, "k_bits_reduce": 8}
+    bytes_per_item = {"k_onesweep": 16, "k_msd_scatter2": 16, "k_msd_hist2": 8, "k_msd_hist1": 8,
+                      "k_bucket_join": 8, "k_mj_tile": 8, "k_hist_digits": 8, "k_bits_reduce": 8}
     bpi = next((v for k, v in bytes_per_item.items() if k in top), 16)
     peak, peak_src = measured_peak()
     achieved = bpi * prof[top]["items"] / (prof[top]["ms"] * 1e-3) / 1e9 if prof[top]["ms"] else 0.0
@@ -234,8 +234,8 @@ def run_single_gpu(args, smj) -> dict:
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        for kname, rec in tj.get("kernels", {}).items():
-            if kname in top and rec.get("items"):
+        for kname, rec in sorted(tj.get("kernels", {}).items(), key=lambda kv: len(kv[0])):
+            if kname in top and rec.get("items"):  # the longest matching name wins
                 traffic = rec["dram_bytes_per_launch"] * (prof[top]["items"] / prof[top]["launches"]) / rec["items"]
     except Exception:
         traffic = None
