@@ -63,6 +63,7 @@ class smj_join_stats_t(C.Structure):  # include/smj_device.h
 NUMA_RANDOM, NUMA_RING, NUMA_NEXT = 0, 1, 2
 ALGO_MWAY, ALGO_MPASS, ALGO_MPSM = 0, 1, 2
 PATH_GENERAL, PATH_MSD, PATH_MSD_OPT = 0, 1, 2
+OUT_S_TUPLE, OUT_RID_PAIR = 0, 1
 
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
@@ -110,6 +111,7 @@ SIGNATURES = {
     "smjdev_merge_join_acc": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, _vp]),
     "smjdev_join": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, C.c_int,
                               C.POINTER(smj_join_stats_t)]),
+    "smjdev_join_materialize": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_int, _vp, C.c_uint64, _u64p]),
     "smjdev_range_partition": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32,
                                          _vp]),
     "smjdev_sample_key_bits": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, _u64p]),
@@ -137,6 +139,8 @@ SIGNATURES = {
                                                       C.POINTER(joinconfig_t)]),
     "sortmergejoin_mpsm": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
                                                  C.POINTER(joinconfig_t)]),
+    "sortmergejoin_multiway_materialize": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
+                                                                 C.POINTER(joinconfig_t)]),
     "sortmergejoin_initrun": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
                                                     C.POINTER(joinconfig_t), _vp]),
     "smj_last_join_stats": (C.c_int, [C.POINTER(smj_join_stats_t)]),

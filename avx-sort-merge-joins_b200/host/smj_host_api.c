@@ -177,6 +177,52 @@ result_t *sortmergejoin_mpsm(relation_t *relR, relation_t *relS, joinconfig_t *j
     return join_common(SMJ_ALGO_MPSM, relR, relS, joincfg, "sortmergejoin_mpsm");
 }
 
+/* JOIN_MATERIALIZE (src/joins/joincommon.c:256-278): count first, then emit into a device buffer
+ * of exactly that size and bring it home */
+result_t *sortmergejoin_multiway_materialize(relation_t *relR, relation_t *relS,
+                                             joinconfig_t *joincfg) {
+    devbuf_t  dr, ds;
+    uint64_t  count = 0, written = 0;
+    uint64_t *d_out = NULL;
+    tuple_t  *h_out = NULL;
+    int       nthreads = joincfg->NTHREADS > 0 ? joincfg->NTHREADS : 1;
+    int       failed;
+    if ((joincfg->NTHREADS & (joincfg->NTHREADS - 1)) != 0) {
+        fprintf(stdout, "[ERROR] m-way sort-merge join runs with a power of 2 #threads.\n");
+        return 0;
+    }
+    memset(&dr, 0, sizeof(dr));
+    memset(&ds, 0, sizeof(ds));
+    failed = smjdev_init(-1) || stage_in(&dr, relR->tuples, relR->num_tuples, 1) ||
+             stage_in(&ds, relS->tuples, relS->num_tuples, 1) ||
+             smjdev_join_materialize(dr.d, relR->num_tuples, ds.d, relS->num_tuples, SMJ_OUT_S_TUPLE, NULL, 0,
+                                     &count);
+    if (!failed && count) {
+        d_out  = (uint64_t *)smjdev_malloc(count * sizeof(uint64_t));
+        h_out  = (tuple_t *)malloc(count * sizeof(tuple_t));
+        failed = !d_out || !h_out ||
+                 smjdev_join_materialize(dr.d, relR->num_tuples, ds.d, relS->num_tuples, SMJ_OUT_S_TUPLE, d_out,
+                                         count, &written) ||
+                 written != count || smjdev_download(h_out, d_out, count * sizeof(uint64_t));
+    }
+    if (d_out) smjdev_free(d_out);
+    stage_free(&dr);
+    stage_free(&ds);
+    if (failed) {
+        free(h_out);
+        smj_fatal("sortmergejoin_multiway_materialize");
+        return NULL;
+    }
+    result_t *res   = (result_t *)malloc(sizeof(result_t));
+    res->resultlist = (threadresult_t *)calloc((size_t)nthreads, sizeof(threadresult_t));
+    for (int i = 0; i < nthreads; i++) res->resultlist[i].threadid = (uint32_t)i;
+    res->resultlist[0].nresults = (int64_t)count;
+    res->resultlist[0].results  = h_out;
+    res->totalresults           = (int64_t)count;
+    res->nthreads               = nthreads;
+    return res;
+}
+
 result_t *sortmergejoin_initrun(relation_t *relR, relation_t *relS, joinconfig_t *joincfg,
                                 void *(*jointhread)(void *)) {
     (void)jointhread;

@@ -46,6 +46,15 @@ result_t *sortmergejoin_mpsm(relation_t *relR, relation_t *relS, joinconfig_t *j
 result_t *sortmergejoin_initrun(relation_t *relR, relation_t *relS, joinconfig_t *joincfg,
                                 void *(*jointhread)(void *));
 
+/* The reference's JOIN_MATERIALIZE build of the same entry point (src/joins/joincommon.c:256-278
+ * emits one tuple <S.key, S.payload> per matching pair into per-thread chained buffers; that build
+ * does not compile in the reference, tuple_buffer.h is missing, so it is a separate function here
+ * instead of a compile-time switch).  result->resultlist[0].results is a malloc()ed tuple_t array
+ * of result->totalresults tuples in unspecified order; the caller frees it, resultlist and
+ * result. */
+result_t *sortmergejoin_multiway_materialize(relation_t *relR, relation_t *relS,
+                                             joinconfig_t *joincfg);
+
 /* Extension (not in the reference): statistics of the calling thread's last join, including the
  * checksum over matched (key, R-payload, S-payload) triples.  Returns 0 if there was a join. */
 int smj_last_join_stats(smj_join_stats_t *out);

@@ -152,6 +152,18 @@ enum { SMJ_PATH_GENERAL = 0, SMJ_PATH_MSD = 1, SMJ_PATH_MSD_OPT = 2 };
 int smjdev_join(int algo, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                 int nruns, smj_join_stats_t *stats);
 
+/* The join with its result written out (the reference's JOIN_MATERIALIZE build,
+ * src/joins/joincommon.c:256-278, appends <S.key, S.payload> per matching pair to per-thread
+ * chained buffers).  r/s: device arrays, left unmodified.  out: device array of `capacity` 64-bit
+ * items or NULL (count only).  *count (host) receives the number of matching pairs; at most
+ * `capacity` of them are written, in unspecified order.  Synchronises. */
+enum {
+    SMJ_OUT_S_TUPLE  = 0, /* the reference's layout: the S tuple, once per matching R tuple */
+    SMJ_OUT_RID_PAIR = 1  /* R.payload << 32 | S.payload (row-id pair)                      */
+};
+int smjdev_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                            int layout, uint64_t *out, uint64_t capacity, uint64_t *count);
+
 int smjdev_join_level1(const uint64_t *r, const uint64_t *rcounts512, const uint64_t *s,
                        const uint64_t *scounts512, uint32_t shift1, uint32_t lo_bit,
                        smj_join_stats_t *stats);

@@ -361,6 +361,43 @@ void orc_join_bruteforce(const uint64_t *r, uint64_t nr, const uint64_t *s, uint
     free(ss);
 }
 
+/* reference src/joins/joincommon.c:239-312 with JOIN_MATERIALIZE (:256-278): the loop emits
+ * <S.key, S.payload> once per matching (r, s) pair; layout 1 emits the row-id pair instead */
+uint64_t orc_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                              int layout, uint64_t *out, uint64_t cap) {
+    uint64_t *rs = (uint64_t *)malloc((nr ? nr : 1) * 8), *ss = (uint64_t *)malloc((ns ? ns : 1) * 8);
+    uint64_t  i = 0, j = 0, matches = 0;
+    memcpy(rs, r, nr * 8);
+    memcpy(ss, s, ns * 8);
+    orc_sort(rs, nr);
+    orc_sort(ss, ns);
+    while (i < nr && j < ns) {
+        const uint32_t kr = (uint32_t)(rs[i] >> 32), ks = (uint32_t)(ss[j] >> 32);
+        if (kr < ks)
+            i++;
+        else if (kr > ks)
+            j++;
+        else {
+            uint64_t jj;
+            do {
+                jj = j;
+                do {
+                    if (out && matches < cap)
+                        out[matches] = layout == 0 ? ss[jj]
+                                                   : ((rs[i] & 0xffffffffull) << 32) | (ss[jj] & 0xffffffffull);
+                    matches++;
+                    jj++;
+                } while (jj < ns && (uint32_t)(ss[jj] >> 32) == kr);
+                i++;
+            } while (i < nr && (uint32_t)(rs[i] >> 32) == ks);
+            j = jj;
+        }
+    }
+    free(rs);
+    free(ss);
+    return matches;
+}
+
 /* The reference's m-way pipeline, its threads run one after the other:
  *   joincommon.c:105-139           chunking of R and S over the threads
  *   sortmergejoin_multiway.c:331-386 partitioning_phase (bit-shift rule :372-376)

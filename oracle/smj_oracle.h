@@ -57,6 +57,13 @@ void orc_join_bruteforce(const uint64_t *r, uint64_t nr, const uint64_t *s, uint
 int orc_join_mway(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns, int nthreads,
                   int fanout, uint64_t *count, uint64_t *checksum);
 
+/* the join result written out: reference src/joins/joincommon.c:256-278 (JOIN_MATERIALIZE) emits
+ * <S.key, S.payload> for every matching pair; layout 1 emits R.payload << 32 | S.payload instead.
+ * Sorts copies of r and s, then the literal loop.  out may be NULL (count only); at most cap items
+ * are written, in the loop's order.  Returns the number of matching pairs. */
+uint64_t orc_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                              int layout, uint64_t *out, uint64_t cap);
+
 /* deterministic generators (the reference's are seeded from time(), generator.c:136-139) */
 void orc_gen_unique(uint64_t *out, uint64_t n, uint64_t seed);                  /* keys = perm of 1..n */
 void orc_gen_fk(uint64_t *out, uint64_t n, uint32_t maxkey, uint64_t seed);     /* keys in 1..maxkey  */

@@ -85,6 +85,8 @@ class Oracle:
         L.orc_merge_join_interpolation.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64]
         L.orc_merge_join_interpolation.restype = C.c_uint64
         L.orc_join_mway.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
+        L.orc_join_materialize.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, C.c_int, _vp, C.c_uint64]
+        L.orc_join_materialize.restype = C.c_uint64
         L.orc_gen_unique.argtypes = [_vp, C.c_uint64, C.c_uint64]
         L.orc_gen_fk.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_uint64]
 
@@ -149,6 +151,16 @@ class Oracle:
 
     def join_bruteforce(self, r, s):
         return self._cc(self.lib.orc_join_bruteforce, r, s)
+
+    def join_materialize(self, r, s, layout: int = 0) -> np.ndarray:
+        """the join result written out (joincommon.c:256-278), in the reference loop's order"""
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        n = self.lib.orc_join_materialize(_p(r), r.size, _p(s), s.size, layout, None, 0)
+        out = np.empty(n, dtype=np.uint64)
+        got = self.lib.orc_join_materialize(_p(r), r.size, _p(s), s.size, layout, _p(out), n)
+        assert got == n
+        return out
 
     def join_mway(self, r, s, nthreads: int, fanout: int):
         r = np.ascontiguousarray(r, dtype=np.uint64)

@@ -464,6 +464,72 @@ def test_join_pinned_host_relations_overlap_upload(smj, orc, monkeypatch):
         lib.smjdev_host_free(hs)
 
 
+# ------------------------------------------------------------------------------------ materialisation
+def _materialize(smj, r, s, layout):
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    cnt = C.c_uint64(0)
+    smj.check(smj.lib.smjdev_join_materialize(dr.ptr, r.size, ds.ptr, s.size, layout, None, 0, C.byref(cnt)))
+    out = smj.DeviceBuffer(max(cnt.value, 1))
+    cnt2 = C.c_uint64(0)
+    smj.check(smj.lib.smjdev_join_materialize(dr.ptr, r.size, ds.ptr, s.size, layout, out.ptr, cnt.value,
+                                              C.byref(cnt2)))
+    assert cnt2.value == cnt.value
+    res = out.to_host(cnt.value, 0) if cnt.value else np.zeros(0, dtype=np.uint64)
+    for b in (dr, ds, out):
+        b.free()
+    return res
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_join_materialize(smj, orc, layout):
+    """smjdev_join_materialize against the oracle's restatement of the JOIN_MATERIALIZE loop
+    (joincommon.c:256-278): same multiset of emitted tuples, for unique / foreign-key / duplicate /
+    heavy-run / disjoint / empty inputs."""
+    for name, r, s in _join_cases(orc):
+        if name == "all_equal":
+            r, s = r[:300], s[:500]
+        exp = orc.join_materialize(r, s, layout)
+        got = _materialize(smj, r, s, layout)
+        assert got.size == exp.size == orc.join_bruteforce(r, s)[0], name
+        assert np.array_equal(np.sort(got), np.sort(exp)), name
+    # long R runs (duplicates in R beyond the shared-memory staging) and a larger foreign-key join
+    rng = np.random.default_rng(3)
+    r = ol.rand_items(rng, 200_000, 40)
+    s = ol.rand_items(rng, 3_000, 50)
+    assert np.array_equal(np.sort(_materialize(smj, r, s, layout)), np.sort(orc.join_materialize(r, s, layout)))
+    r, s = orc.gen_unique(1 << 20, 5), orc.gen_fk((1 << 21) + 7, 1 << 20, 9)
+    got = _materialize(smj, r, s, layout)
+    assert got.size == s.size
+    assert np.array_equal(np.sort(got), np.sort(orc.join_materialize(r, s, layout)))
+
+
+def test_join_materialize_host_api(smj, orc):
+    """sortmergejoin_multiway_materialize: resultlist[0].results holds totalresults tuples
+    <S.key, S.payload>, malloc()ed, freed by the caller; partial output when the buffer is small."""
+    r, s = orc.gen_unique(50_000, 1), orc.gen_fk(120_001, 50_000, 2)
+    cfg = smj.joinconfig_t(2, 128, 0, 0, 20 * 1024 * 1024, smj.NUMA_NEXT)
+    res = smj.lib.sortmergejoin_multiway_materialize(C.byref(smj.rel(r)), C.byref(smj.rel(s)), C.byref(cfg))
+    assert res and res.contents.totalresults == s.size and res.contents.nthreads == 2
+    tr = res.contents.resultlist[0]
+    assert tr.nresults == s.size
+    got = np.ctypeslib.as_array(C.cast(tr.results, C.POINTER(C.c_uint64)), shape=(s.size,)).copy()
+    assert np.array_equal(np.sort(got), np.sort(s))  # every S tuple has exactly one partner
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(tr.results, C.c_void_p))
+    libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+    libc.free(C.cast(res, C.c_void_p))
+    # capacity smaller than the result: the count is complete, the output is cut
+    dr, ds, out = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s), smj.DeviceBuffer(1000)
+    cnt = C.c_uint64(0)
+    smj.check(smj.lib.smjdev_join_materialize(dr.ptr, r.size, ds.ptr, s.size, 0, out.ptr, 1000, C.byref(cnt)))
+    assert cnt.value == s.size
+    part = out.to_host()
+    assert np.all(np.isin(part, s))
+    for b in (dr, ds, out):
+        b.free()
+
+
 # ------------------------------------------------------------------------------------ host memory paths
 def test_pageable_relations_use_the_staging_pipeline(smj, orc):
     """Relations in ordinary malloc'ed memory above the staging threshold (32 MiB): upload through

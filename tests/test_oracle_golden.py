@@ -44,3 +44,28 @@ def test_join_golden(orc):
     assert orc.join_mway(R, S, 2, 128) == orc.join_mway(R, S, 4, 64) == orc.join_bruteforce(R, S)
     assert orc.join_bruteforce(D1, D2)[0] == int(G["join_DD_mway_2"]) == int(G["join_DD_mpass_2"])
     assert orc.join_mway(D1, D2, 2, 128) == orc.join_bruteforce(D1, D2)
+
+
+def test_oracle_join_materialize_against_numpy():
+    """orc_join_materialize (joincommon.c:256-278 restated): the emitted tuples are the S tuples,
+    once per matching R tuple; the row-id layout pairs every matching (R.payload, S.payload)."""
+    import oracle_lib as ol
+    orc = ol.oracle()
+    rng = np.random.default_rng(11)
+    r = ol.rand_items(rng, 3000, 400)
+    s = ol.rand_items(rng, 5000, 500)
+    cnt, _ = orc.join_bruteforce(r, s)
+    kr, ks = (r >> np.uint64(32)).astype(np.int64), (s >> np.uint64(32)).astype(np.int64)
+    mult = np.bincount(kr, minlength=512)
+    expect = np.sort(np.repeat(s, mult[ks]))
+    got = orc.join_materialize(r, s, 0)
+    assert got.size == cnt == int(mult[ks].sum())
+    assert np.array_equal(np.sort(got), expect)
+    pairs = orc.join_materialize(r, s, 1)
+    lo32 = np.uint64(0xFFFFFFFF)
+    brute = np.sort(np.array([((a & lo32) << np.uint64(32)) | (b & lo32)
+                              for a in r[:300] for b in s[(s >> np.uint64(32)) == (a >> np.uint64(32))]], dtype=np.uint64))
+    sub = orc.join_materialize(r[:300], s, 1)
+    assert np.array_equal(np.sort(sub), brute)
+    assert pairs.size == cnt
+    assert orc.join_materialize(r[:0], s, 0).size == 0 and orc.join_materialize(r, s[:0], 1).size == 0
