@@ -32,9 +32,12 @@ int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shi
                       u64 *offsets, u64 *exact_bits);
 int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
                    u32 shift2, u64 *offsets);
+int smj_msd_pass_b_seg(SmjCtx *ctx, const u64 *a, u64 n, u32 nseg, const u64 *d_seg, u64 *b, u32 shift2,
+                       u64 *offsets);
 int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 *exact_bits);
 int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
                        const u64 *dest_offsets);
+int smj_msd_scatter_local(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, const u64 *d_hist512, u64 *out);
 int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
 int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *d_st,
                    u32 *d_sub, u64 *host);
@@ -44,8 +47,8 @@ int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc
                          u64 *tab_r, u64 *tab_s, u32 *d_flags);
 u64 smj_msd_tile_items();
 u64 smj_msd_alloc2(u64 n);
-int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 dump, u64 *d_tab,
-                       u32 *d_flag, u32 kmask, u32 kref, u32 *d_kflag);
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
+                       u32 kmask, u32 kref, u32 *d_kflag);
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
                        u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink);
 int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
@@ -849,7 +852,7 @@ struct MsdRel {
     Upload    *up;             // non-null: `in` arrives chunk by chunk
     const u64 *sample_from;    // what the sample kernel reads (the pinned host copy of an upload)
     u64       *a, *b;          // level-1 / level-2 outputs
-    u64        alloc1, alloc2; // capacities of a and b in items, dump areas excluded
+    u64        alloc1, alloc2; // capacities of a and b in items
     u64       *starts, *ends;  // 2^18 (+1) entries each
     u64       *d_tab, *d_counts;
     bool       opt1, opt2;     // level 1 / level 2 ran optimistically
@@ -940,7 +943,6 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     const char *hook    = getenv("SMJ_MSD_TEST");
     const int   shrink1 = hook && !strcmp(hook, "shrink1"), shrink2 = hook && !strcmp(hook, "shrink2");
     const u32   nb2     = 512u * 512u;
-    const u64   tile    = smj_msd_tile_items();
     SmjScratch  sc(ctx);
     u64 *d_state = (u64 *)sc.get(128), *d_st = (u64 *)sc.get(smj_msd_sample_bytes(0));
     u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4), *d_sub = (u32 *)sc.get(smj_msd_sample_bytes(1));
@@ -963,16 +965,15 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     MsdRel rel[2] = {{r, nr, up_r, samp_r}, {s, ns, up_s, samp_s}};
     for (int q = 0; q < 2; q++) {
         MsdRel &x = rel[q];
-        // a heavy 18-bit bucket in the sample (expected count: a handful) means equal slots will
-        // not hold at the second level; the first level adapts its capacities to any skew
-        const u64 nsamp = samp[8 + q], maxsub = samp[6 + q];
-        const double expect = (double)nsamp / (double)nb2;
+        // equal slots at the second level are trusted only for relations whose sample shows no
+        // duplicate keys (see k_msd_sample); the first level adapts its capacities to any skew
+        const u64 nsamp = samp[8 + q], dups = samp[6 + q];
         x.opt1 = mode && x.n >= (1u << 20);
-        x.opt2 = x.opt1 && (double)maxsub <= 4.0 * expect + 24.0;
+        x.opt2 = x.opt1 && dups <= 16;
         x.alloc1 = x.opt1 ? smj_msd_caps1(samp.data() + 16 + 512 * q, nsamp, x.n, shrink1) : x.n;
         x.alloc2 = x.opt2 ? smj_msd_alloc2(x.n) : x.n;
-        x.a      = (u64 *)sc.get((std::max(x.alloc1, x.n) + tile) * 8);
-        x.b      = (u64 *)sc.get((std::max(x.alloc2, x.n) + tile) * 8);
+        x.a      = (u64 *)sc.get(std::max(x.alloc1, x.n) * 8);
+        x.b      = (u64 *)sc.get(std::max(x.alloc2, x.n) * 8);
         x.starts = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
         x.ends   = (u64 *)sc.get((size_t)nb2 * 8);
         x.d_tab  = (u64 *)sc.get(3 * 512 * 8);
@@ -993,7 +994,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
             for (u64 k = 0; k < x.up->nchunks(); k++) {
                 const u64 off = k * x.up->chunk, len = std::min(x.up->chunk, x.n - off);
                 SMJ_CHECK(cudaStreamWaitEvent(ctx->stream, x.up->ev[k], 0));
-                if ((rc = smj_msd_pass_a_opt(ctx, x.in + off, len, x.a, pl.shift1, x.alloc1, x.d_tab,
+                if ((rc = smj_msd_pass_a_opt(ctx, x.in + off, len, x.a, pl.shift1, x.d_tab,
                                              flags + 2 * q, kmask, kref, flags + 12 + 2 * q)))
                     return rc;
             }
@@ -1002,7 +1003,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
             return rc;
         if (x.opt1) {
             if (!(x.up && x.up->active()) &&
-                (rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, x.alloc1, x.d_tab, flags + 2 * q, kmask,
+                (rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, x.d_tab, flags + 2 * q, kmask,
                                          kref, flags + 12 + 2 * q)))
                 return rc;
             if (x.opt2) {
@@ -1244,9 +1245,35 @@ extern "C" int smjdev_msd_scatter(const uint64_t *in, uint64_t n, uint32_t shift
                               (const u64 *)dest_offsets512);
 }
 
+extern "C" int smjdev_msd_scatter_local(const uint64_t *in, uint64_t n, uint32_t shift1,
+                                        const uint64_t *hist512_dev, uint64_t *out) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (shift1 < 32 || shift1 > 55) return smj_fail_msg("smjdev_msd_scatter_local: digit outside the key");
+    return smj_msd_scatter_local(ctx, (const u64 *)in, n, shift1, (const u64 *)hist512_dev, (u64 *)out);
+}
+
+// common body of smjdev_join_level1 / smjdev_join_level1_seg: nseg == 0 -> counts512 describe 512
+// back-to-back buckets, else seg = {start[nseg], count[nseg], bucket[nseg]} (host arrays)
+static int join_level1(const uint64_t *r_, const uint64_t *rcounts512, uint32_t nseg_r, const uint64_t *rseg,
+                       const uint64_t *s_, const uint64_t *scounts512, uint32_t nseg_s, const uint64_t *sseg,
+                       uint32_t shift1, uint32_t lo_bit, smj_join_stats_t *stats);
+
 extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512, const uint64_t *s_,
                                   const uint64_t *scounts512, uint32_t shift1, uint32_t lo_bit,
                                   smj_join_stats_t *stats) {
+    return join_level1(r_, rcounts512, 0, nullptr, s_, scounts512, 0, nullptr, shift1, lo_bit, stats);
+}
+extern "C" int smjdev_join_level1_seg(const uint64_t *r_, uint32_t nseg_r, const uint64_t *rseg,
+                                      const uint64_t *s_, uint32_t nseg_s, const uint64_t *sseg,
+                                      uint32_t shift1, uint32_t lo_bit, smj_join_stats_t *stats) {
+    if (!nseg_r || !nseg_s || !rseg || !sseg) return smj_fail_msg("smjdev_join_level1_seg: no segments");
+    return join_level1(r_, nullptr, nseg_r, rseg, s_, nullptr, nseg_s, sseg, shift1, lo_bit, stats);
+}
+
+static int join_level1(const uint64_t *r_, const uint64_t *rcounts512, uint32_t nseg_r, const uint64_t *rseg,
+                       const uint64_t *s_, const uint64_t *scounts512, uint32_t nseg_s, const uint64_t *sseg,
+                       uint32_t shift1, uint32_t lo_bit, smj_join_stats_t *stats) {
     SmjCtx *ctx = smj_ctx();
     if (!ctx) return -1;
     if (!stats) return smj_fail_msg("smjdev_join_level1: stats must not be NULL");
@@ -1255,9 +1282,14 @@ extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512
     const u64 *r = (const u64 *)r_, *s = (const u64 *)s_;
     memset(stats, 0, sizeof(*stats));
     u64 nr = 0, ns = 0;
-    for (int b = 0; b < 512; b++) {
-        nr += rcounts512[b];
-        ns += scounts512[b];
+    if (nseg_r) {
+        for (u32 i = 0; i < nseg_r; i++) nr += rseg[nseg_r + i];
+        for (u32 i = 0; i < nseg_s; i++) ns += sseg[nseg_s + i];
+    } else {
+        for (int b = 0; b < 512; b++) {
+            nr += rcounts512[b];
+            ns += scounts512[b];
+        }
     }
     const u64  launches0 = ctx->launches;
     const u32  shift2 = shift1 - 9, lo_shift = 32 + lo_bit, lbits = shift2 - lo_shift, nb2 = 512u * 512u;
@@ -1276,11 +1308,20 @@ extern "C" int smjdev_join_level1(const uint64_t *r_, const uint64_t *rcounts512
         if (!bR || !bS || !offR || !offS || !d_h1 || !d_state || !d_list)
             return smj_fail_msg("smjdev_join_level1: out of device memory");
         SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
-        SMJ_CHECK(cudaMemcpyAsync(d_h1, rcounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
-        SMJ_CHECK(cudaMemcpyAsync(d_h1 + 512, scounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
         int rc;
-        if ((rc = smj_msd_pass_b(ctx, r, nr, d_h1, nullptr, bR, shift2, offR))) return rc;
-        if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, nullptr, bS, shift2, offS))) return rc;
+        if (nseg_r) {
+            u64 *d_segr = (u64 *)sc.get((size_t)nseg_r * 24), *d_segs = (u64 *)sc.get((size_t)nseg_s * 24);
+            if (!d_segr || !d_segs) return smj_fail_msg("smjdev_join_level1: out of device memory");
+            SMJ_CHECK(cudaMemcpyAsync(d_segr, rseg, (size_t)nseg_r * 24, cudaMemcpyHostToDevice, ctx->stream));
+            SMJ_CHECK(cudaMemcpyAsync(d_segs, sseg, (size_t)nseg_s * 24, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = smj_msd_pass_b_seg(ctx, r, nr, nseg_r, d_segr, bR, shift2, offR))) return rc;
+            if ((rc = smj_msd_pass_b_seg(ctx, s, ns, nseg_s, d_segs, bS, shift2, offS))) return rc;
+        } else {
+            SMJ_CHECK(cudaMemcpyAsync(d_h1, rcounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
+            SMJ_CHECK(cudaMemcpyAsync(d_h1 + 512, scounts512, 512 * 8, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = smj_msd_pass_b(ctx, r, nr, d_h1, nullptr, bR, shift2, offR))) return rc;
+            if ((rc = smj_msd_pass_b(ctx, s, ns, d_h1 + 512, nullptr, bS, shift2, offS))) return rc;
+        }
         const BucketSet R = {bR, offR, offR + 1, nr}, S = {bS, offS, offS + 1, ns};
         u64 h[16];
         if ((rc = bucket_collect(ctx, R, S, d_state, d_list))) return rc;

@@ -515,14 +515,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // hit the same few counters.
 // Bin capacity policies of the unstable pass.  With exact bin starts (a histogram pass ran first)
 // there is nothing to check (NoLimit).  The OPTIMISTIC passes of the m-way join run without a
-// histogram: every bin owns a region whose capacity was estimated from a sample, a tile whose
-// reservation does not fit stores that bin's items into a dump area instead and raises *flag; the
-// host then repeats the pass exactly (histogram first).  limit(b) = one past the last item index
+// histogram: every bin owns a region whose capacity was estimated from a sample; a tile whose
+// reservation does not fit does not store that bin's items at all and raises a flag, and the pass
+// (or the bucket) is repeated exactly, histogram first.  limit(b) = one past the last item index
 // bin b may use.
 struct NoLimit {
     static constexpr bool on = false, keys = false;
     __device__ __forceinline__ u64 operator()(u32) const { return ~0ull; }
-    __device__ __forceinline__ u64 dump_at() const { return 0; }
     __device__ __forceinline__ void raise() const {}
     __device__ __forceinline__ u32 key_bad(u64) const { return 0; }
     __device__ __forceinline__ void raise_key() const {}
@@ -533,12 +532,10 @@ struct NoLimit {
 struct LimitArray {
     static constexpr bool on = true, keys = true;
     const u64 *lim;
-    u64        dump;  // item index of a TILE-sized dump area in out
     u32       *flag;
     u32        kmask, kref;
     u32       *kflag;
     __device__ __forceinline__ u64 operator()(u32 b) const { return lim[b]; }
-    __device__ __forceinline__ u64 dump_at() const { return dump; }
     __device__ __forceinline__ void raise() const { *flag = 1u; }
     __device__ __forceinline__ u32 key_bad(u64 x) const { return ((u32)(x >> 32) ^ kref) & kmask; }
     __device__ __forceinline__ void raise_key() const { *kflag = 1u; }
@@ -550,13 +547,11 @@ struct LimitSlots {
     static constexpr bool on = true, keys = false;
     const u64 *base2, *cap2;
     u32        bucket, shrink;
-    u64        dump;
     u32       *flag;
     __device__ __forceinline__ u64 operator()(u32 b) const {
         const u64 cap = cap2[bucket];
         return base2[bucket] + (u64)b * cap + (shrink ? cap / 4 : cap);
     }
-    __device__ __forceinline__ u64 dump_at() const { return dump; }
     __device__ __forceinline__ void raise() const { flag[bucket] = 1u; }
     __device__ __forceinline__ u32 key_bad(u64) const { return 0; }
     __device__ __forceinline__ void raise_key() const {}
@@ -629,8 +624,8 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
             // the limit is requested before the atomic, so that the two round trips to L2 overlap
             const u64 limit = LIM::on ? lim(b) : ~0ull;
             gbase[q]        = atomicAdd(&cursors[b], (u64)cntb[q]);
-            if (LIM::on && gbase[q] + cntb[q] > limit) {  // does not fit: dump + raise the flag
-                gbase[q] = lim.dump_at();
+            if (LIM::on && gbase[q] + cntb[q] > limit) {  // does not fit: store nothing, raise the flag
+                gbase[q] = ~0ull;
                 lim.raise();
             }
         }
@@ -650,7 +645,7 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
         const u32 b = threadIdx.x * BPT + q;
         if (b < NB) {
             s_cnt[b]  = excl;  // tile position of the bin's first item
-            s_goff[b] = gbase[q] - (u64)excl;
+            s_goff[b] = (LIM::on && gbase[q] == ~0ull) ? ~0ull : gbase[q] - (u64)excl;
         }
         excl += cntb[q];
     }
@@ -669,13 +664,13 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
     if (FULL) {
 #pragma unroll 4
         for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
-            u64 x = s_items[i];
-            st_stream(out + s_goff[fn(x)] + i, x);
+            const u64 x = s_items[i], g = s_goff[fn(x)];
+            if (!LIM::on || g != ~0ull) st_stream(out + g + i, x);
         }
     } else {
         for (u32 i = threadIdx.x; i < valid; i += THREADS) {
-            u64 x = s_items[i];
-            st_stream(out + s_goff[fn(x)] + i, x);
+            const u64 x = s_items[i], g = s_goff[fn(x)];
+            if (!LIM::on || g != ~0ull) st_stream(out + g + i, x);
         }
     }
 }
@@ -1176,6 +1171,53 @@ __global__ void __launch_bounds__(256) k_msd_tile_table(const u64 *__restrict__ 
     msd_write_tiles(tiles, b, tile_prefix[b], bucket_start[b], bucket_count[b]);
 }
 
+// Tile table from SEGMENTS: segment i = items [start[i], start[i] + count[i]) of first-level
+// bucket bucket[i].  A bucket may come in several segments (multi-GPU: one per source rank).
+// One CTA; seg = {start[nseg], count[nseg], bucket[nseg]}; ntiles_at[MSD_NB] receives the total.
+constexpr int SEG_THREADS = 1024, SEG_PER = 8, SEG_MAX = SEG_THREADS * SEG_PER;
+__global__ void __launch_bounds__(SEG_THREADS) k_msd_seg_tiles(const u64 *__restrict__ seg, u32 nseg,
+                                                               MsdTile *__restrict__ tiles,
+                                                               u64 *__restrict__ ntiles_at) {
+    __shared__ u64 s_w[SEG_THREADS / 32];
+    u64 t[SEG_PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < SEG_PER; q++) {
+        const u32 i = threadIdx.x * SEG_PER + q;
+        t[q]        = i < nseg ? (seg[nseg + i] + MSD_TILE - 1) / MSD_TILE : 0;
+        sum += t[q];
+    }
+    u64       incl = sum;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 v = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+        if (lane >= (u32)o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u64 excl = incl - sum, total = 0;
+    for (u32 w = 0; w < SEG_THREADS / 32; w++) {
+        if (w < warp) excl += s_w[w];
+        total += s_w[w];
+    }
+    if (threadIdx.x == 0) ntiles_at[MSD_NB] = total;
+#pragma unroll
+    for (int q = 0; q < SEG_PER; q++) {
+        const u32 i = threadIdx.x * SEG_PER + q;
+        if (i < nseg) {
+            const u64 start = seg[i], count = seg[nseg + i];
+            for (u64 k = 0; k < t[q]; k++) {
+                MsdTile e;
+                e.start  = start + k * MSD_TILE;
+                e.bucket = (u32)seg[2 * nseg + i];
+                e.valid  = (u32)min((u64)MSD_TILE, count - k * MSD_TILE);
+                tiles[excl + k] = e;
+            }
+        }
+        excl += t[q];
+    }
+}
+
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict__ in,
                                                            const MsdTile *__restrict__ tiles,
                                                            const u64 *__restrict__ tile_prefix,
@@ -1204,7 +1246,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
                    const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
                    u64 *cursors2 /* [512][512] */, const u64 *__restrict__ base2,
-                   const u64 *__restrict__ cap2, u64 dump, u32 *flag, int shrink) {
+                   const u64 *__restrict__ cap2, u32 *flag, int shrink) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = (u64 *)smem_raw;
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
@@ -1230,7 +1272,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
         const u64 *nsrc = pre ? in + nx.start : nullptr;
         u64       *cur  = cursors2 + (u64)ti.bucket * MSD_NB;
         Lim        lim;
-        if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, dump, flag};
+        if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, flag};
         if (ti.valid == (u32)MSD_TILE) {
             if (!have) unstable_load<MSD_THREADS, MSD_IPT, true>(item, in + ti.start, ti.valid);
             unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim>(
@@ -1252,15 +1294,21 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
 // One read of a jittered strided sample of R and S (128-byte lines, at most max_sectors / 4 per
 // relation) gives (1) the OR / AND of the sampled keys -> the digit plan, computed by every CTA
 // after a grid barrier exactly as the host computes it, (2) the sampled first-level histogram ->
-// bin capacities of the first pass, (3) the largest sampled count of any 18-bit bucket -> a skew
-// detector for the second pass.  st (u64 words): [0..3] OR_R AND_R OR_S AND_S, [4] barrier,
-// [6..7] max bucket count R S, [8..9] items sampled R S, [16..528) hist R, [528..1040) hist S.
+// bin capacities of the first pass, (3) the number of sampled keys seen twice (a lossy hash table:
+// atomicExch of the key, a hit when the previous occupant was the same key) -> whether the
+// relation has duplicate keys at all.  Equal slots at the second level are only trusted for
+// relations without duplicates; with duplicates the key frequencies may be skewed in ways a
+// sample cannot see (Zipf 0.4 over 128 M keys overflows most first-level buckets although its
+// hottest key shows up nine times in 2^20 samples), and the exact second level costs 3 % more.
+// st (u64 words): [0..3] OR_R AND_R OR_S AND_S, [4] barrier, [6..7] duplicate keys seen R S,
+// [8..9] items sampled R S, [16..528) hist R, [528..1040) hist S.
+constexpr int SAMP_TAB_BITS = 20;  // hash table slots per relation
 constexpr int SAMP_CTAS = 192, SAMP_THREADS = 512, SAMP_SPT = 3, SAMP_WORDS = 16 + 2 * MSD_NB;
 constexpr u32 SAMP_MAX_SECTORS = SAMP_CTAS * SAMP_THREADS * SAMP_SPT;
 
 __global__ void __launch_bounds__(SAMP_THREADS)
     k_msd_sample(const u64 *__restrict__ r, u64 nr, const u64 *__restrict__ s, u64 ns,
-                 u32 max_sectors, u64 *st, u32 *sub /* [2][2^18], zeroed */) {
+                 u32 max_sectors, u64 *st, u32 *tab /* [2][2^SAMP_TAB_BITS], zeroed */) {
     __shared__ u32 s_h[MSD_NB];
     const u32  rel  = blockIdx.y;
     const u64 *in   = rel ? s : r;
@@ -1322,7 +1370,7 @@ __global__ void __launch_bounds__(SAMP_THREADS)
     for (int q = 0; q < 4; q++) bits[q] = ld_relaxed(st + q);
     MsdPlan pl;
     if (!smj_msd_plan(bits, &pl)) return;
-    u32 mx = 0;
+    u32 dups = 0;
 #pragma unroll
     for (int k = 0; k < SAMP_SPT; k++) {
         if (ok[k]) {
@@ -1330,18 +1378,19 @@ __global__ void __launch_bounds__(SAMP_THREADS)
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 atomicAdd(&s_h[(u32)(x[k][u] >> pl.shift1) & (MSD_NB - 1)], 1u);
-                const u32 id = (u32)(x[k][u] >> pl.shift2) & (MSD_NB * MSD_NB - 1);
-                old[u]       = atomicAdd(&sub[(rel << 18) | id], 1u);
+                const u32 key = (u32)(x[k][u] >> 32);
+                const u32 h   = (key * 2654435761u) >> (32 - SAMP_TAB_BITS);
+                old[u]        = atomicExch(&tab[(rel << SAMP_TAB_BITS) | h], key + 1u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) mx = max(mx, old[u] + 1u);
+            for (int u = 0; u < 4; u++) dups += old[u] == (u32)(x[k][u] >> 32) + 1u;
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < MSD_NB; i += SAMP_THREADS)
         if (s_h[i]) atomicAdd(st + 16 + rel * MSD_NB + i, (u64)s_h[i]);
-    mx = __reduce_max_sync(SMJ_FULL_MASK, mx);
-    if (lane_id() == 0 && mx > ld_relaxed(st + 6 + rel)) atomicMax(st + 6 + rel, (u64)mx);
+    dups = __reduce_add_sync(SMJ_FULL_MASK, dups);
+    if (lane_id() == 0 && dups) atomicAdd(st + 6 + rel, (u64)dups);
     if (blockIdx.x == 0 && threadIdx.x == 0) st[8 + rel] = S * 4;
 }
 
@@ -1463,23 +1512,47 @@ __device__ __forceinline__ u32 msd_flagged_list(const u32 *__restrict__ flag, u3
     return total;
 }
 
+// the tiles of all flagged buckets as one index space: s_tp[q] = first tile of the q-th flagged
+// bucket, returns the total; (bucket, tile) of a flat index by binary search in s_tp
+__device__ __forceinline__ u32 msd_flagged_tiles(const u64 *__restrict__ bucket_count, const u32 *s_list,
+                                                 u32 nflag, u32 *s_tp) {
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (u32 q = 0; q < nflag; q++) {
+            s_tp[q] = acc;
+            acc += (u32)((bucket_count[s_list[q]] + MSD_TILE - 1) / MSD_TILE);
+        }
+        s_tp[nflag] = acc;
+    }
+    __syncthreads();
+    return s_tp[nflag];
+}
+__device__ __forceinline__ u32 msd_flat_find(const u32 *s_tp, u32 nflag, u32 f) {
+    u32 lo = 0, hi = nflag;  // s_tp[lo] <= f < s_tp[hi]
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (s_tp[mid] <= f) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(MSD_THREADS) k_msd_fix_hist(const u64 *__restrict__ in,
                                                               const u64 *__restrict__ bucket_start,
                                                               const u64 *__restrict__ bucket_count,
                                                               const u32 *__restrict__ flag, FieldFn fn2,
                                                               u32 *__restrict__ hist2 /* [512][512], zeroed */) {
-    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32], sh[MSD_NB];
+    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32], sh[MSD_NB], s_tp[MSD_NB + 1];
     const u32 nflag = msd_flagged_list(flag, s_list, s_wcnt);
-    for (u32 q = 0; q < nflag; q++) {
-        const u32 b     = s_list[q];
+    if (nflag == 0) return;
+    const u32 total = msd_flagged_tiles(bucket_count, s_list, nflag, s_tp);
+    for (u32 f = blockIdx.x; f < total; f += gridDim.x) {
+        const u32 q = msd_flat_find(s_tp, nflag, f), b = s_list[q];
         const u64 first = bucket_start[b], cnt = bucket_count[b];
+        const u64 lo = (u64)(f - s_tp[q]) * MSD_TILE, hi = min(cnt, lo + MSD_TILE);
         sh[threadIdx.x] = 0;
         __syncthreads();
-        for (u64 t = blockIdx.x; t * MSD_TILE < cnt; t += gridDim.x) {
-            const u64 lo = t * MSD_TILE, hi = min(cnt, lo + MSD_TILE);
-            for (u64 i = lo + threadIdx.x; i < hi; i += MSD_THREADS)
-                atomicAdd(&sh[fn2(ld_stream(in + first + i))], 1u);
-        }
+        for (u64 i = lo + threadIdx.x; i < hi; i += MSD_THREADS)
+            atomicAdd(&sh[fn2(ld_stream(in + first + i))], 1u);
         __syncthreads();
         const u32 c = sh[threadIdx.x];
         if (c) atomicAdd(&hist2[b * MSD_NB + threadIdx.x], c);
@@ -1523,24 +1596,24 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
     u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
     __shared__ u32 s_wsum[32];
-    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32];
+    __shared__ u32 s_list[MSD_NB], s_wcnt[MSD_NB / 32], s_tp[MSD_NB + 1];
     const u32 nflag = msd_flagged_list(flag, s_list, s_wcnt);
+    if (nflag == 0) return;
+    const u32 total = msd_flagged_tiles(bucket_count, s_list, nflag, s_tp);
     s_cnt[threadIdx.x] = 0;
-    for (u32 q = 0; q < nflag; q++) {
-        const u32 b     = s_list[q];
+    for (u32 f = blockIdx.x; f < total; f += gridDim.x) {
+        const u32 q = msd_flat_find(s_tp, nflag, f), b = s_list[q];
         const u64 first = bucket_start[b], cnt = bucket_count[b];
+        const u64 lo    = (u64)(f - s_tp[q]) * MSD_TILE;
+        const u32 valid = (u32)min((u64)MSD_TILE, cnt - lo);
         u64      *cur   = cursors2 + (u64)b * MSD_NB;
-        for (u64 t = blockIdx.x; t * MSD_TILE < cnt; t += gridDim.x) {
-            const u64 lo    = t * MSD_TILE;
-            const u32 valid = (u32)min((u64)MSD_TILE, cnt - lo);
-            __syncthreads();  // the previous tile is done with the staging area, s_cnt is zero
-            if (valid == (u32)MSD_TILE)
-                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + first + lo, out, fn2, cur, valid,
-                                                                      s_items, s_cnt, s_goff, s_wsum);
-            else
-                unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + first + lo, out, fn2, cur, valid,
-                                                                       s_items, s_cnt, s_goff, s_wsum);
-        }
+        __syncthreads();  // the previous tile is done with the staging area, s_cnt is zero
+        if (valid == (u32)MSD_TILE)
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, true>(in + first + lo, out, fn2, cur, valid,
+                                                                  s_items, s_cnt, s_goff, s_wsum);
+        else
+            unstable_tile<MSD_THREADS, MSD_IPT, 9, FieldFn, false>(in + first + lo, out, fn2, cur, valid,
+                                                                   s_items, s_cnt, s_goff, s_wsum);
     }
 }
 
@@ -1601,23 +1674,26 @@ constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB *
 // entries, or null = back to back) where each begins in a.  Every bucket is partitioned by the
 // 9-bit digit at shift2 into b.  offsets (device, 2^18 + 1 entries) receives the start of every
 // second-level bucket in b (and n): bucket q is b[offsets[q] .. offsets[q + 1]).
-int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
-                   u32 shift2, u64 *offsets) {
+static int msd_pass_b_common(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts,
+                             u32 nseg, const u64 *d_seg, u64 *b, u32 shift2, u64 *offsets) {
     const u32  NB2 = MSD_NB * MSD_NB;
     SmjScratch sc(ctx);
     u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get(MSD_NB * 8);
     u64 *d_bcount = (u64 *)sc.get(MSD_NB * 8);
     u64 *d_hist2 = (u64 *)sc.get((size_t)NB2 * 8), *d_cur2 = (u64 *)sc.get((size_t)NB2 * 8);
     u64 *d_tot   = (u64 *)sc.get((NB2 / 1024) * 8);
-    if (!d_tpref || !d_bstart || !d_bcount || !d_hist2 || !d_cur2 || !d_tot)
+    const unsigned max_tiles = (unsigned)(n / MSD_TILE + std::max<u32>(MSD_NB, nseg));
+    MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
+    if (!d_tpref || !d_bstart || !d_bcount || !d_hist2 || !d_cur2 || !d_tot || !d_tiles)
         return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
     SMJ_CHECK(cudaMemsetAsync(d_hist2, 0, (size_t)NB2 * 8, ctx->stream));
     FieldFn f2 = {shift2, (u32)MSD_NB - 1};
-    SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_counts, d_starts, d_tpref, d_bstart, d_bcount);
-    const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
-    MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
-    if (!d_tiles) return smj_fail_msg("smj_msd_pass_b: scratch allocation failed");
-    SMJ_LAUNCH(ctx, k_msd_tile_table, MSD_NB, 256, 0, d_tpref, d_bstart, d_bcount, d_tiles);
+    if (d_seg) {
+        SMJ_LAUNCH(ctx, k_msd_seg_tiles, 1, SEG_THREADS, 0, d_seg, nseg, d_tiles, d_tpref);
+    } else {
+        SMJ_LAUNCH(ctx, k_msd_tile_prefix, 1, MSD_NB, 0, d_counts, d_starts, d_tpref, d_bstart, d_bcount);
+        SMJ_LAUNCH(ctx, k_msd_tile_table, MSD_NB, 256, 0, d_tpref, d_bstart, d_bcount, d_tiles);
+    }
     const unsigned grid2 = max_tiles;  // one CTA per tile (see launch_unstable_shape)
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
@@ -1628,8 +1704,22 @@ int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const 
     SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<false>, grid2, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2,
-               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, 0ull, (u32 *)nullptr, 0);
+               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0);
     return 0;
+}
+
+int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
+                   u32 shift2, u64 *offsets) {
+    return msd_pass_b_common(ctx, a, n, d_counts, d_starts, 0, nullptr, b, shift2, offsets);
+}
+
+// Pass B over SEGMENTS: the n items of `a` lie in nseg segments, d_seg (device) = {start[nseg],
+// count[nseg], bucket[nseg]}; the segments of one first-level bucket need not be adjacent (after a
+// multi-GPU exchange every source rank contributes one segment per bucket).
+int smj_msd_pass_b_seg(SmjCtx *ctx, const u64 *a, u64 n, u32 nseg, const u64 *d_seg, u64 *b, u32 shift2,
+                       u64 *offsets) {
+    if (nseg == 0 || nseg > (u32)SEG_MAX) return smj_fail_msg("smj_msd_pass_b_seg: bad segment count");
+    return msd_pass_b_common(ctx, a, n, nullptr, nullptr, nseg, d_seg, b, shift2, offsets);
 }
 
 // ---- optimistic passes -------------------------------------------------------------------------
@@ -1638,7 +1728,7 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
                    u32 *d_sub, u64 *host) {
     if (max_sectors > SAMP_MAX_SECTORS) max_sectors = SAMP_MAX_SECTORS;
     SMJ_CHECK(cudaMemsetAsync(d_st, 0, SAMP_WORDS * 8, ctx->stream));
-    SMJ_CHECK(cudaMemsetAsync(d_sub, 0, (size_t)2 * MSD_NB * MSD_NB * 4, ctx->stream));
+    SMJ_CHECK(cudaMemsetAsync(d_sub, 0, ((size_t)2 << SAMP_TAB_BITS) * 4, ctx->stream));
     const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
     SMJ_CHECK(cudaMemcpyAsync(d_st, init, 32, cudaMemcpyHostToDevice, ctx->stream));
     // cooperative launch: the kernel contains a grid barrier, so the runtime must guarantee (or
@@ -1657,7 +1747,7 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
     return 0;
 }
 size_t smj_msd_sample_bytes(int which) {
-    return which == 0 ? (size_t)SAMP_WORDS * 8 : (size_t)2 * MSD_NB * MSD_NB * 4;
+    return which == 0 ? (size_t)SAMP_WORDS * 8 : ((size_t)2 << SAMP_TAB_BITS) * 4;
 }
 
 // First-level bin regions from a sampled histogram (k of nsamp items fell into the bin):
@@ -1685,14 +1775,14 @@ u64 smj_msd_alloc2(u64 n) {
 
 // Optimistic pass A: in -> a, bin b into a[start[b] .. limit[b]), no histogram.  d_tab (device,
 // 3 x 512 u64 = {cursors, starts, limits}, laid out by k_msd_caps1; the cursors end up as the bin
-// ends); *d_flag is raised when a bin overflowed (a then holds garbage in places; its dump area is
-// a[dump .. dump + tile)).  Every key is checked against the sampled key range on the way: a key
+// ends); *d_flag is raised when a bin overflowed (its items are then missing from a).  Every key is
+// checked against the sampled key range on the way: a key
 // that differs from kref on a bit position of kmask raises *d_kflag.
-int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 dump, u64 *d_tab,
-                       u32 *d_flag, u32 kmask, u32 kref, u32 *d_kflag) {
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
+                       u32 kmask, u32 kref, u32 *d_kflag) {
     if (n == 0) return 0;
     FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
-    const LimitArray lim = {d_tab + 2 * MSD_NB, dump, d_flag, kmask, kref, d_kflag};
+    const LimitArray lim = {d_tab + 2 * MSD_NB, d_flag, kmask, kref, d_kflag};
     // (tile shapes 256x16, 512x12, 384x16 and 1024x8 were measured: 512x16 with 2 CTAs per SM wins)
     return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, a, n, f1, d_tab, lim);
 }
@@ -1706,8 +1796,7 @@ int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts) {
 // bucket into 512 equal slots, no histogram; buckets with an overflowing slot are repartitioned
 // exactly inside their region by the k_msd_fix_* kernels.  starts / ends (device, 2^18 entries
 // each): sub-bucket q is b[starts[q] .. ends[q]).  d_counts (device, 512) receives the
-// first-level bucket sizes.  alloc2 = items b can hold before its dump area b[alloc2 .. alloc2 +
-// tile).  *d_flag is raised when the slots do not fit alloc2 (nothing is partitioned then);
+// first-level bucket sizes.  alloc2 = items b can hold.  *d_flag is raised when the slots do not fit alloc2 (nothing is partitioned then);
 // *d_nfixed (u64) counts the repartitioned buckets.
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
                        u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink) {
@@ -1725,11 +1814,11 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     if (!d_tiles) return smj_fail_msg("smj_msd_pass_b_opt: scratch allocation failed");
     SMJ_LAUNCH(ctx, k_msd_level2_plan, MSD_NB, MSD_NB, 0, d_tab, alloc2, d_tpref, d_counts, d_cap2, d_base2,
                starts, ends, d_tiles, d_flag);
-    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 2, max_tiles);
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 4, max_tiles);
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
-               d_base2, d_cap2, alloc2, d_bflag, shrink);
+               d_base2, d_cap2, d_bflag, shrink);
     SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,
@@ -1784,6 +1873,19 @@ int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const
     SMJ_CHECK(cudaMemcpyAsync(d_cur, h_cur, RADIX_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
     FieldFn f1 = {shift1, (u32)MSD_NB - 1};
     return launch_unstable<9>(ctx, in, (u64 *)nullptr, n, f1, d_cur);
+}
+
+// Pass A into a LOCAL buffer laid out bucket-major (bucket d starts at the exclusive prefix of
+// hist512, a DEVICE array as smj_msd_hist1 leaves it): nothing goes through the host, so the pass
+// can be enqueued while the histograms of the ranks are still being all-gathered.
+int smj_msd_scatter_local(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, const u64 *d_hist512, u64 *out) {
+    if (n == 0) return 0;
+    SmjScratch sc(ctx);
+    u64 *d_cur = (u64 *)sc.get(RADIX_NB * 8);
+    if (!d_cur) return smj_fail_msg("smj_msd_scatter_local: scratch");
+    SMJ_LAUNCH(ctx, k_bases_multi, 1, RADIX_NB, 0, d_hist512, d_cur);
+    FieldFn f1 = {shift1, (u32)MSD_NB - 1};
+    return launch_unstable<9>(ctx, in, out, n, f1, d_cur);
 }
 
 // Same from a strided sample of about 2^16 items per relation (a guess, to be verified).

@@ -205,6 +205,38 @@ int smjdev_memset(void *dst, int value, size_t bytes) {
     if (bytes) SMJ_CHECK(cudaMemsetAsync(dst, value, bytes, c->stream));
     return 0;
 }
+// Bulk exchange with the copy engines: copies enqueued between smjdev_exchange_begin() and
+// smjdev_exchange_end() run on the library's copy stream behind everything enqueued on the compute
+// stream so far, and the compute stream continues only when they are done.  dst / src may be peer
+// GPUs' buffers (smjdev_ipc_open): a contiguous copy crosses NVLink at ~735 GB/s on B200, about
+// twice what scattered stores from the SMs reach.
+static cudaEvent_t g_xev[2] = {nullptr, nullptr};
+static int exchange_events(void) {
+    for (auto &e : g_xev)
+        if (!e) SMJ_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+int smjdev_exchange_begin(void) {
+    SmjCtx *c = smj_ctx();
+    if (!c || exchange_events()) return -1;
+    SMJ_CHECK(cudaEventRecord(g_xev[0], c->stream));
+    SMJ_CHECK(cudaStreamWaitEvent(c->copy_stream, g_xev[0], 0));
+    return 0;
+}
+int smjdev_exchange_copy(void *dst, const void *src, size_t bytes) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (bytes) SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->copy_stream));
+    return 0;
+}
+int smjdev_exchange_end(void) {
+    SmjCtx *c = smj_ctx();
+    if (!c || exchange_events()) return -1;
+    SMJ_CHECK(cudaEventRecord(g_xev[1], c->copy_stream));
+    SMJ_CHECK(cudaStreamWaitEvent(c->stream, g_xev[1], 0));
+    return 0;
+}
+
 int smjdev_pointer_kind(const void *p) {
     if (!smj_ctx()) return -1;
     cudaPointerAttributes attr;

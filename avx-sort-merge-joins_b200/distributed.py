@@ -128,6 +128,55 @@ def msd_layout(hist: np.ndarray, rank: int):
     return owner, offs, mine
 
 
+def msd_layout_dma(hist: np.ndarray, rank: int):
+    """Layout of the copy-engine exchange.  hist[src][rel][512] as in msd_layout; buckets are given
+    to ranks in the same contiguous runs.  Every rank scatters its slice bucket-major into a LOCAL
+    send buffer, so the buckets of one owner are one contiguous range there, and copies that range
+    into the owner's receive buffer, which is therefore laid out source-major: for every source
+    rank one block holding its items of the owner's buckets, bucket by bucket.  Returns a dict:
+      owner[512], first[W + 1]       bucket b belongs to rank owner[b]; rank p owns first[p]..first[p+1]-1
+      send_off[rel][512]             where bucket b starts in THIS rank's send buffer
+      self_off[rel]                  where this rank's own block starts in its own receive buffer
+      copies                         [(rel, dst rank, first item in the send buffer, items, item offset
+                                       in dst's receive buffer)] for every other rank
+      segs[rel] = (start, count, bucket) arrays: the segments of this rank's receive buffer
+      recv[rel]                      items this rank receives (its own included)"""
+    hist = np.asarray(hist, dtype=np.int64)
+    world = hist.shape[0]
+    tot = hist.sum(axis=0)
+    load = tot.sum(axis=0)
+    prefix = np.cumsum(load) - load
+    owner = np.minimum(((2 * prefix + load) * world) // max(2 * int(load.sum()), 1), world - 1)
+    owner = np.maximum.accumulate(owner)
+    first = np.searchsorted(owner, np.arange(world + 1), side="left")
+    first[world] = 512
+    csum = np.concatenate([np.zeros((world, 2, 1), dtype=np.int64), np.cumsum(hist, axis=2)], axis=2)
+    # blk[p][g][rel] = items source g sends to owner p; blockstart = exclusive prefix over g
+    blk = np.stack([csum[:, :, first[p + 1]] - csum[:, :, first[p]] for p in range(world)])
+    blockstart = np.cumsum(blk, axis=1) - blk
+    send_off = csum[rank][:, :512]
+    copies = [(rel, p, int(send_off[rel][first[p]]) if first[p] < 512 else 0, int(blk[p][rank][rel]),
+               int(blockstart[p][rank][rel]))
+              for rel in range(2) for p in range(world) if p != rank and blk[p][rank][rel] > 0]
+    lo, hi = int(first[rank]), int(first[rank + 1])
+    segs = []
+    for rel in range(2):
+        st, ct, bk = [], [], []
+        for g in range(world):
+            c = hist[g][rel][lo:hi]
+            inner = np.cumsum(c) - c
+            st.append(blockstart[rank][g][rel] + inner)
+            ct.append(c)
+            bk.append(np.arange(lo, hi, dtype=np.int64))
+        st, ct, bk = (np.concatenate(x) if x else np.zeros(0, dtype=np.int64) for x in (st, ct, bk))
+        keep = ct > 0
+        segs.append((st[keep], ct[keep], bk[keep]))
+    self_off = [int(blockstart[rank][rank][rel]) for rel in range(2)]
+    recv = [int(blk[rank][:, rel].sum()) for rel in range(2)]
+    return {"owner": owner, "first": first, "send_off": send_off, "self_off": self_off, "copies": copies,
+            "segs": segs, "recv": recv}
+
+
 class P2PExchange:
     """Receive buffers for R and S on every GPU, mapped into every process with CUDA IPC.  With it
     DistributedJoin.step_p2p partitions and exchanges in ONE kernel per relation: the scatter
@@ -309,6 +358,110 @@ class DistributedJoin:
         out = res.cpu().numpy().view(np.uint64)
         sent = 8 * int(hist[self.rank][:, owner != self.rank].sum())
         return int(out[0]), int(out[1]), sent
+
+    def step_msd_dma(self, r, nr: int, s, ns: int, px: "P2PExchange"):
+        """The m-way join across GPUs with a COPY-ENGINE exchange: pass A of the MSD partition
+        scatters every rank's slice bucket-major into a local send buffer, so the buckets of one
+        owner are one contiguous range; that range is copied into the owner's receive buffer with
+        one cudaMemcpyAsync over NVLink on the copy stream, and every rank finishes the buckets it
+        owns from the segments it received (smjdev_join_level1_seg).  Contiguous copies cross
+        NVLink at ~700 GB/s per direction where the scattered 128-byte stores of step_msd reach
+        ~350.  The local scatters need only the LOCAL histograms, on the device: they are enqueued
+        behind the all-gather of the histograms and run while the host waits for it and computes
+        the layout."""
+        e, lib, smj, W = self.e, self.e.lib, self.e.smj, self.world
+        dev = e.device
+        sends = [e.empty(nr), e.empty(ns)]
+
+        def scatter_local(loc, shift1):
+            smj.check(lib.smjdev_msd_scatter_local(r.data_ptr(), nr, shift1, loc[0:512].data_ptr(),
+                                                   sends[0].data_ptr()), "msd_scatter_local")
+            smj.check(lib.smjdev_msd_scatter_local(s.data_ptr(), ns, shift1, loc[512:1024].data_ptr(),
+                                                   sends[1].data_ptr()), "msd_scatter_local")
+
+        pre = self._msd_plan_and_hist(r, nr, s, ns, overlap=scatter_local)
+        if pre is None:
+            return self.step_p2p(r, nr, s, ns, self._fallback, px)
+        lo, hi, shift1, hist = pre
+        lay = msd_layout_dma(hist, self.rank)
+        for rel in range(2):
+            if lay["recv"][rel] > px.cap[rel]:
+                raise RuntimeError(f"receive buffer too small: {lay['recv'][rel]} > {px.cap[rel]}")
+        first = lay["first"]
+        smj.check(lib.smjdev_exchange_begin(), "exchange_begin")
+        # rank g sends to g+1, g+2, ... (mod W): at any moment every receiver has one sender
+        order = sorted(lay["copies"], key=lambda c: (c[0], (c[1] - self.rank) % W))
+        for rel in range(2):
+            for (crel, p, src, cnt, dst) in order:
+                if crel == rel:
+                    smj.check(lib.smjdev_exchange_copy(C.c_void_p(px.ptrs[rel][p] + 8 * dst),
+                                                       C.c_void_p(sends[rel].data_ptr() + 8 * src), 8 * cnt),
+                              "exchange_copy")
+            own_n = int(hist[self.rank][rel][first[self.rank]:first[self.rank + 1]].sum())
+            if own_n:  # this rank's own buckets: a local copy
+                src = int(lay["send_off"][rel][first[self.rank]])
+                smj.check(lib.smjdev_exchange_copy(C.c_void_p(px.local[rel] + 8 * lay["self_off"][rel]),
+                                                   C.c_void_p(sends[rel].data_ptr() + 8 * src), 8 * own_n),
+                          "exchange_copy")
+        smj.check(lib.smjdev_exchange_end(), "exchange_end")
+        dist.all_reduce(self._token(dev), op=dist.ReduceOp.SUM)  # every rank's copies have landed
+        st = smj.smj_join_stats_t()
+        (rs, rc, rb), (ss, sc_, sb) = lay["segs"]
+        if rs.size and ss.size:
+            rseg = np.ascontiguousarray(np.concatenate([rs, rc, rb]), dtype=np.uint64)
+            sseg = np.ascontiguousarray(np.concatenate([ss, sc_, sb]), dtype=np.uint64)
+            smj.check(lib.smjdev_join_level1_seg(px.local[0], rs.size, rseg.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 px.local[1], ss.size, sseg.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 shift1, lo, C.byref(st)), "join_level1_seg")
+        res = e.result_tensor(st.matches, st.checksum)
+        dist.all_reduce(res, op=dist.ReduceOp.SUM)  # also: nobody copies into a buffer still in use
+        out = res.cpu().numpy().view(np.uint64)
+        del sends
+        sent = 8 * sum(c[3] for c in lay["copies"])
+        return int(out[0]), int(out[1]), sent
+
+    def _msd_plan_and_hist(self, r, nr: int, s, ns: int, overlap=None):
+        """Steps 1-2 of the MSD exchanges: the digit plan from the sampled OR/AND of all ranks and
+        the all-gathered first-level histograms (with the exact OR/AND that verifies the plan).
+        overlap(loc, shift1): called after the all-gather has been ENQUEUED and before the host
+        waits for it, with the device tensor of the local histograms (R at 0:512, S at 512:1024).
+        Returns (lo, hi, shift1, hist[W][2][512]) or None (then self._fallback holds splitters)."""
+        e, lib, smj, W = self.e, self.e.lib, self.e.smj, self.world
+        dev = e.device
+        b4 = (C.c_uint64 * 4)()
+        smj.check(lib.smjdev_sample_key_bits(r.data_ptr(), nr, s.data_ptr(), ns, b4), "sample_key_bits")
+        mine = torch.from_numpy(np.array(list(b4) + [nr, ns], dtype=np.uint64).view(np.int64)).to(dev)
+        allm = [torch.empty_like(mine) for _ in range(W)]
+        dist.all_gather(allm, mine)
+        m = torch.stack(allm).cpu().numpy().view(np.uint64)
+        self._fallback = self._fallback_splitters(m)
+        fold = lambda col, op: int(op.reduce(m[:, col]))
+        sizes_ok = int(m[:, 4].sum() + m[:, 5].sum()) >= (1 << 20) and m[:, 4].sum() > 0 and m[:, 5].sum() > 0
+        plan = msd_plan(fold(0, np.bitwise_or), fold(1, np.bitwise_and), fold(2, np.bitwise_or),
+                        fold(3, np.bitwise_and)) if sizes_ok else None
+        if plan is None:
+            return None
+        lo, hi, shift1 = plan
+        loc = torch.zeros(2 * 512 + 4, dtype=torch.int64, device=dev)
+        loc[1025], loc[1027] = -1, -1  # AND accumulators start at ~0
+        smj.check(lib.smjdev_msd_hist(r.data_ptr(), nr, shift1, loc[0:512].data_ptr(), loc[1024:1026].data_ptr()), "msd_hist")
+        smj.check(lib.smjdev_msd_hist(s.data_ptr(), ns, shift1, loc[512:1024].data_ptr(), loc[1026:1028].data_ptr()), "msd_hist")
+        alll = torch.empty(W, loc.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(alll, loc)
+        if getattr(self, "_pin", None) is None or self._pin.shape != alll.shape:
+            self._pin = torch.empty(alll.shape, dtype=torch.int64).pin_memory()
+        self._pin.copy_(alll, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        if overlap is not None:
+            overlap(loc, shift1)  # work that needs only local data runs while the host waits
+        ev.synchronize()
+        a = self._pin.numpy().copy()
+        ex = a[:, 1024:1028].view(np.uint64)
+        if not msd_plan_holds(int(np.bitwise_or.reduce(ex[:, 0])), int(np.bitwise_and.reduce(ex[:, 1])),
+                              int(np.bitwise_or.reduce(ex[:, 2])), int(np.bitwise_and.reduce(ex[:, 3])), lo, hi):
+            return None
+        return lo, hi, shift1, a[:, :1024].reshape(W, 2, 512)
 
     def _fallback_splitters(self, m: np.ndarray) -> np.ndarray:
         """Equal-width splitters over the sampled key range (used when step_msd cannot apply)."""

@@ -36,7 +36,13 @@ def run(args, smj):
     splitters = dj_mod.uniform_splitters(n, world)  # keys are a permutation of 1..n
 
     # fused partition + exchange over peer memory (default); SMJ_EXCHANGE=nccl uses the all-to-all
-    mode = os.environ.get("SMJ_EXCHANGE", "msd")  # msd (default) | p2p | nccl
+    # msd (default: the pass-A scatter kernel stores into the owners' buffers) | dma (copy engines)
+    # | p2p (range partition fused with the exchange) | nccl (all-to-all).  Measured on B200
+    # (128M x 128M): N=2 msd 3.27 ms, dma 3.26-3.46 ms; N=8 msd 2.00 ms, dma 2.28 ms.
+    # auto: dma when a rank sends at least 1 GB per step (config 5: 14.7 ms against 17.0 ms), else msd
+    mode = os.environ.get("SMJ_EXCHANGE", "auto")
+    if mode == "auto":
+        mode = "dma" if 2 * count * 8 * (world - 1) / world >= 1e9 else "msd"
     use_p2p = mode != "nccl"
     px = None
     if use_p2p:
@@ -44,6 +50,8 @@ def run(args, smj):
         px = dj_mod.P2PExchange(eng, rank, world, cap, cap)
 
     def one_step(rr, ss):
+        if mode == "dma":
+            return dj.step_msd_dma(rr, count, ss, count, px)
         if mode == "msd":
             return dj.step_msd(rr, count, ss, count, px)
         if use_p2p:
@@ -86,6 +94,20 @@ def run(args, smj):
     assert cnt == n
 
     # ---- end to end: each rank's slices start in pinned host memory
+    if os.environ.get("SMJ_BENCH_NO_E2E"):  # very large --size: the pinned copies do not fit the host
+        e2e_steps, e2e_s = 0, float("nan")
+    else:
+        e2e_steps, e2e_s = _e2e(args, r, s, count, dev, one_step, sync_all, n)
+    line = _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kernel_ms, prof, clocks,
+                 e2e_s, e2e_steps, launches, cnt, cks)
+    if px is not None:
+        px.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return line
+
+
+def _e2e(args, r, s, count, dev, one_step, sync_all, n):
     hr = torch.empty(count, dtype=torch.int64).pin_memory()
     hs = torch.empty(count, dtype=torch.int64).pin_memory()
     hr.copy_(r[:count])
@@ -101,8 +123,11 @@ def run(args, smj):
     sync_all()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+    return e2e_steps, float(e2e_s.item())
 
+
+def _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kernel_ms, prof, clocks, e2e_s,
+          e2e_steps, launches, cnt, cks):
     line = None
     if rank == 0:
         peak, peak_src = B.measured_peak()
@@ -112,8 +137,13 @@ def run(args, smj):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"sortmergejoins -a m-way, |R|=|S|={n} 8-byte tuples, uniform unique keys "
-                                   f"(BASELINE.json configs[0]), relations spread evenly over {world} GPUs",
-                       "parallelism": (f"first MSD partitioning pass fused with the exchange (the scatter kernel stores "
+                                   + ("(BASELINE.json configs[0])" if n == 128_000_000 else
+                                      "(BASELINE.json configs[4], scale-out)" if n == 2_000_000_000 else "")
+                                   + f", relations spread evenly over {world} GPUs",
+                       "parallelism": (f"first MSD partitioning pass into a bucket-major send buffer, contiguous bucket "
+                                       f"ranges copied to their owners over NVLink by the copy engines (overlapping "
+                                       f"the scatter of the other relation) over {world} GPUs" if mode == "dma" else
+                                       f"first MSD partitioning pass fused with the exchange (the scatter kernel stores "
                                        f"into the bucket owners' buffers over NVLink, CUDA IPC) over {world} GPUs"
                                        if mode == "msd" else
                                        f"range partition fused with the exchange (scatter kernel stores into peer receive "
@@ -126,9 +156,10 @@ def run(args, smj):
                        "rank0_kernel_ms_per_step": kernel_ms,
                        "rank0_kernels": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}},
             "clocks": clocks,
-            "e2e": {"value": 2 * n / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": 2 * n * 8,
-                    "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                    "api": "DistributedJoin.step on per-rank pinned host slices"},
+            "e2e": ({"value": 2 * n / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": 2 * n * 8,
+                     "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                     "api": "DistributedJoin.step on per-rank pinned host slices"} if e2e_steps else
+                    {"value": None, "unit": B.UNIT, "skipped": "SMJ_BENCH_NO_E2E"}),
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "achieved": 40.0 * 2 * n / (ms_step * 1e-3) / 1e9 / world,
                          "peak": peak, "unit": "GB/s", "frac": 40.0 * 2 * n / (ms_step * 1e-3) / 1e9 / world / peak,
@@ -137,8 +168,4 @@ def run(args, smj):
                          "nvlink_gbs_sent_per_gpu_over_step": link_gbs},
             "cpu_baseline": None, "matches": cnt, "checksum": cks,
         }
-    if px is not None:
-        px.close()
-    dist.barrier()
-    dist.destroy_process_group()
     return line

@@ -164,9 +164,25 @@ enum {
 int smjdev_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                             int layout, uint64_t *out, uint64_t capacity, uint64_t *count);
 
+/* Pass A into a local buffer laid out bucket-major; hist512_dev is the DEVICE histogram
+ * smjdev_msd_hist produced (no host round trip: the pass can run while the ranks all-gather). */
+int smjdev_msd_scatter_local(const uint64_t *in, uint64_t n, uint32_t shift1,
+                             const uint64_t *hist512_dev, uint64_t *out);
 int smjdev_join_level1(const uint64_t *r, const uint64_t *rcounts512, const uint64_t *s,
                        const uint64_t *scounts512, uint32_t shift1, uint32_t lo_bit,
                        smj_join_stats_t *stats);
+/* Same, for first-level buckets that arrive in SEGMENTS (copy-engine exchange: every source rank
+ * contributes one contiguous segment per bucket).  rseg / sseg: HOST arrays {start[nseg],
+ * count[nseg], bucket[nseg]} (items, items, bucket index 0..511), nseg <= 8192. */
+int smjdev_join_level1_seg(const uint64_t *r, uint32_t nseg_r, const uint64_t *rseg, const uint64_t *s,
+                           uint32_t nseg_s, const uint64_t *sseg, uint32_t shift1, uint32_t lo_bit,
+                           smj_join_stats_t *stats);
+/* Bulk exchange on the copy engines, ordered with the compute stream: begin() makes the copy stream
+ * wait for everything enqueued so far, copy() enqueues one contiguous copy (dst / src may be peer
+ * buffers opened with smjdev_ipc_open), end() makes the compute stream wait for the copies. */
+int smjdev_exchange_begin(void);
+int smjdev_exchange_copy(void *dst, const void *src, size_t bytes);
+int smjdev_exchange_end(void);
 
 /* Multi-GPU building blocks (one process per GPU; the exchange itself is done by the
  * caller with NCCL).

@@ -154,3 +154,41 @@ def test_msd_layout_and_plan():
     assert dj.msd_plan(5 << 32, 5 << 32, 5 << 32, 5 << 32) is None
     assert dj.msd_plan_holds(items_or, 0, items_or, 0, 0, 26)
     assert not dj.msd_plan_holds(items_or | (1 << 62), 0, items_or, 0, 0, 26)
+
+
+def test_msd_layout_dma_simulated_exchange():
+    """Layout of the copy-engine exchange (pure host logic): scatter every rank's items bucket-major
+    into a send buffer, apply the planned copies, and check that every owner's receive buffer is
+    exactly covered by its segments and that each segment holds one bucket's items."""
+    import importlib
+    dj = importlib.import_module("avx-sort-merge-joins_b200.distributed")
+    rng = np.random.default_rng(0)
+    for W in (1, 2, 3, 8):
+        hist = rng.integers(0, 50, size=(W, 2, 512))
+        hist[:, :, 100:140] = 0
+        hist[:, 1, 17] += 5000  # a heavy S bucket
+        if W == 8:
+            hist[:, :, 300:] = 0  # some ranks may own nothing at the top
+        lays = [dj.msd_layout_dma(hist, g) for g in range(W)]
+        assert all(np.array_equal(lays[0]["owner"], l["owner"]) for l in lays)
+        for rel in range(2):
+            send = [np.concatenate([np.full(hist[g][rel][b], b) for b in range(512)]) for g in range(W)]
+            recv = [np.full(lays[p]["recv"][rel], -1) for p in range(W)]
+            for g in range(W):
+                lay = lays[g]
+                lo, hi = lay["first"][g], lay["first"][g + 1]
+                start = lay["send_off"][rel][lo] if lo < 512 else 0
+                blk = send[g][start:start + hist[g][rel][lo:hi].sum()]
+                recv[g][lay["self_off"][rel]:lay["self_off"][rel] + blk.size] = blk
+                for (crel, p, src, cnt, dst) in lay["copies"]:
+                    if crel == rel:
+                        assert p != g and cnt > 0
+                        recv[p][dst:dst + cnt] = send[g][src:src + cnt]
+            for p in range(W):
+                assert (recv[p] >= 0).all()
+                st, ct, bk = lays[p]["segs"][rel]
+                seen = np.zeros(recv[p].size, bool)
+                for a, c, b in zip(st, ct, bk):
+                    assert lays[p]["owner"][b] == p and (recv[p][a:a + c] == b).all() and not seen[a:a + c].any()
+                    seen[a:a + c] = True
+                assert seen.all() and ct.sum() == hist[:, rel, lays[p]["owner"] == p].sum()

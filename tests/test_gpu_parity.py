@@ -383,9 +383,10 @@ def test_mway_optimistic_partition_and_its_exact_repeats(smj, orc, monkeypatch):
         st = _device_mway_stats(smj, r, s)
         assert (st.matches, st.checksum) == exp, hook
         # shrink1: both relations overflow at level 1 and are repartitioned exactly by the host;
-        # shrink2: every first-level bucket is repartitioned exactly on the device
+        # shrink2: every first-level bucket of R (unique keys: equal slots; S has duplicate keys
+        # and takes the exact second level anyway) is repartitioned exactly on the device
         assert st.path == smj.PATH_MSD_OPT, hook
-        assert st.repeats == 2 if hook == "shrink1" else st.repeats > 500, (hook, st.repeats)
+        assert st.repeats == 2 if hook == "shrink1" else st.repeats > 300, (hook, st.repeats)
     monkeypatch.delenv("SMJ_MSD_TEST")
 
 
