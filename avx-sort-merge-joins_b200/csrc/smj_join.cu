@@ -956,7 +956,14 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     const u64 *samp_s = (up_s && up_s->active()) ? up_s->host : s;
     int rc = smj_msd_sample(ctx, samp_r, nr, samp_s, ns, uploading ? 1u << 16 : 1u << 18, d_st, d_sub,
                             samp.data());
-    if (rc) return rc;
+    bool have_sample = true;
+    if (rc == 1) {
+        // no cooperative launch on this device: plain sampled OR/AND, exact (histogram) passes
+        std::fill(samp.begin(), samp.end(), 0ull);
+        if ((rc = smj_key_bits_sampled(ctx, samp_r, nr, samp_s, ns, samp.data()))) return rc;
+        have_sample = false;
+    } else if (rc)
+        return rc;
     MsdPlan pl;
     if (!smj_msd_plan(samp.data(), &pl)) return 0;
     // key bits outside [lo, hi] are constant in the sample: every key must carry the same value there
@@ -968,7 +975,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
         // equal slots at the second level are trusted only for relations whose sample shows no
         // duplicate keys (see k_msd_sample); the first level adapts its capacities to any skew
         const u64 nsamp = samp[8 + q], dups = samp[6 + q];
-        x.opt1 = mode && x.n >= (1u << 20);
+        x.opt1 = mode && have_sample && x.n >= (1u << 20);
         x.opt2 = x.opt1 && dups <= 16;
         x.alloc1 = x.opt1 ? smj_msd_caps1(samp.data() + 16 + 512 * q, nsamp, x.n, shrink1) : x.n;
         x.alloc2 = x.opt2 ? smj_msd_alloc2(x.n) : x.n;

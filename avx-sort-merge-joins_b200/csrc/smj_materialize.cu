@@ -22,6 +22,7 @@
 #include <algorithm>
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
+int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used);
 
 namespace {
 
@@ -172,8 +173,14 @@ extern "C" int smjdev_join_materialize(const uint64_t *r_, uint64_t nr, const ui
         return smj_fail_msg("smjdev_join_materialize: out of device memory");
     u64 *sr = nullptr, *ss = nullptr;
     int  rc;
-    if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
-    if ((rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
+    // key order is all that is needed; the MSD sort (whole-word order) is the faster one when it applies
+    int used = 0;
+    if ((rc = smj_msd_sort(ctx, r, nr, aR, &used))) return rc;
+    sr = aR;
+    if (!used && (rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
+    if ((rc = smj_msd_sort(ctx, s, ns, aS, &used))) return rc;
+    ss = aS;
+    if (!used && (rc = smj_lsd_sort(ctx, s, aS, bS, ns, 2, &ss))) return rc;
     SMJ_CHECK(cudaMemsetAsync(d_total, 0, 8, ctx->stream));
     SMJ_LAUNCH(ctx, k_mat_bounds, (unsigned)div_up(nchunks, 256), 256, 0, sr, nr, ss, ns, nchunks, d_lo, d_hi);
     SMJ_ITEMS(ctx, nr + ns);

@@ -1304,7 +1304,6 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
 // [8..9] items sampled R S, [16..528) hist R, [528..1040) hist S.
 constexpr int SAMP_TAB_BITS = 20;  // hash table slots per relation
 constexpr int SAMP_CTAS = 192, SAMP_THREADS = 512, SAMP_SPT = 3, SAMP_WORDS = 16 + 2 * MSD_NB;
-constexpr u32 SAMP_MAX_SECTORS = SAMP_CTAS * SAMP_THREADS * SAMP_SPT;
 
 __global__ void __launch_bounds__(SAMP_THREADS)
     k_msd_sample(const u64 *__restrict__ r, u64 nr, const u64 *__restrict__ s, u64 ns,
@@ -1653,6 +1652,19 @@ __global__ void __launch_bounds__(1024) k_scan_add(u64 *__restrict__ out, u64 nb
 
 }  // namespace
 
+// exclusive scan of n <= 2^20 u64 entries (device arrays; out may not alias in)
+int smj_exclusive_scan_u64(SmjCtx *ctx, const u64 *in, u64 n, u64 *out) {
+    const unsigned nblk = (unsigned)div_up(n, 1024);
+    if (nblk == 0) return 0;
+    if (nblk > 1024) return smj_fail_msg("smj_exclusive_scan_u64: too many entries");
+    SmjScratch sc(ctx);
+    u64 *d_tot = (u64 *)sc.get((size_t)nblk * 8);
+    if (!d_tot) return smj_fail_msg("smj_exclusive_scan_u64: scratch");
+    SMJ_LAUNCH(ctx, k_scan_local, nblk, 1024, 0, in, n, out, d_tot);
+    SMJ_LAUNCH(ctx, k_scan_add, nblk, 1024, 0, out, n, d_tot);
+    return 0;
+}
+
 static int msd_scatter2_attr(SmjCtx *ctx) {
     static int       attr_gen = -1;
     constexpr size_t SMEM     = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
@@ -1724,9 +1736,26 @@ int smj_msd_pass_b_seg(SmjCtx *ctx, const u64 *a, u64 n, u32 nseg, const u64 *d_
 
 // ---- optimistic passes -------------------------------------------------------------------------
 // Sample of R and S (see k_msd_sample).  host: SMJ_MSD_SAMPLE_WORDS u64.  Synchronises.
+// Returns 1 (no error recorded) when the cooperative kernel cannot run on this device.
 int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *d_st,
                    u32 *d_sub, u64 *host) {
-    if (max_sectors > SAMP_MAX_SECTORS) max_sectors = SAMP_MAX_SECTORS;
+    // the kernel contains a grid barrier: size the grid to what the device can hold at once (a
+    // smaller GPU, a MIG slice) and return 1 when even that fails, so that the caller can fall back
+    // to the exact passes instead of failing the join
+    static int max_ctas = -1, occ_gen = -1;
+    if (occ_gen != ctx->generation) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msd_sample, SAMP_THREADS, 0) != cudaSuccess) {
+            cudaGetLastError();
+            per_sm = 0;
+        }
+        max_ctas = per_sm * ctx->sm_count;
+        occ_gen  = ctx->generation;
+    }
+    const int   ctas = std::min(SAMP_CTAS, max_ctas / 2);
+    const char *hook = getenv("SMJ_MSD_TEST");  // "nocoop": behave like a device without cooperative launch
+    if (ctas < 1 || (hook && !strcmp(hook, "nocoop"))) return 1;
+    max_sectors = std::min<u32>(max_sectors, (u32)ctas * SAMP_THREADS * SAMP_SPT);
     SMJ_CHECK(cudaMemsetAsync(d_st, 0, SAMP_WORDS * 8, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_sub, 0, ((size_t)2 << SAMP_TAB_BITS) * 4, ctx->stream));
     const u64 init[4] = {0ull, ~0ull, 0ull, ~0ull};
@@ -1736,12 +1765,15 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
     void *args[] = {(void *)&r, (void *)&nr, (void *)&s, (void *)&ns, (void *)&max_sectors, (void *)&d_st,
                     (void *)&d_sub};
     if (ctx->profiling) smj_prof_before(ctx, "k_msd_sample");
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_msd_sample, dim3(SAMP_CTAS, 2),
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_msd_sample, dim3(ctas, 2),
                                                 dim3(SAMP_THREADS), args, 0, ctx->stream);
     if (ctx->profiling) smj_prof_after(ctx);
     ctx->next_items = 0;
     ctx->launches++;
-    if (e != cudaSuccess) return smj_fail(e, "k_msd_sample", __FILE__, __LINE__);
+    if (e != cudaSuccess) {  // e.g. cooperative launches not available here
+        cudaGetLastError();
+        return 1;
+    }
     SMJ_CHECK(cudaMemcpyAsync(host, d_st, SAMP_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -1,14 +1,16 @@
 // smj_sort.cu -- C-ABI sort entry points (include/smj_device.h).
 //
 // smjdev_sort replaces src/avxsort/avxsort.c:128-245 (avxsort_aligned/_unaligned behind
-// avxsort_tuples / avxsort_int64) with LSD one-sweep radix passes over the varying bits
-// (smj_radix.cu).  The m-way join does not go through here: it partitions MSD-first and never
+// avxsort_tuples / avxsort_int64): whole-word sorts of large inputs take the MSD path
+// (smj_msdsort.cu: two histogram-free range-partition passes + in-bucket counting sort), everything
+// else LSD one-sweep radix passes over the varying bits (smj_radix.cu).  The m-way join does not go through here: it partitions MSD-first and never
 // materialises sorted buckets (smj_join.cu).
 #include "smj_common.cuh"
 #include <algorithm>
 #include "../../include/smj_device.h"
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
+int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used);
 
 extern "C" int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_only, int algo,
                            uint64_t **sorted) {
@@ -17,8 +19,19 @@ extern "C" int smjdev_sort(uint64_t *buf, uint64_t *tmp, uint64_t n, int key_onl
     if (!sorted) return smj_fail_msg("smjdev_sort: sorted must not be NULL");
     u64 *res = nullptr;
     if (algo != 0 && algo != 1) return smj_fail_msg("smjdev_sort: unknown algorithm");
-    // classic two-buffer ping-pong: pass 1 buf -> tmp, pass 2 tmp -> buf, ...
-    int rc = smj_lsd_sort(ctx, (const u64 *)buf, (u64 *)tmp, (u64 *)buf, n, key_only, &res);
+    int rc;
+    if (key_only == 0) {
+        // whole-word order, large input: MSD range partition + in-bucket counting sort, buf -> tmp
+        // (smj_msdsort.cu); it declines inputs it does not suit
+        int used = 0;
+        if ((rc = smj_msd_sort(ctx, (const u64 *)buf, n, (u64 *)tmp, &used))) return rc;
+        if (used) {
+            *sorted = tmp;
+            return 0;
+        }
+    }
+    // LSD passes, classic two-buffer ping-pong: pass 1 buf -> tmp, pass 2 tmp -> buf, ...
+    rc = smj_lsd_sort(ctx, (const u64 *)buf, (u64 *)tmp, (u64 *)buf, n, key_only, &res);
     if (rc) return rc;
     *sorted = (uint64_t *)res;
     return 0;

@@ -29,6 +29,55 @@ def _inputs(rng, n, kind):
 
 
 # ------------------------------------------------------------------------------------ sort
+def _sort_device(smj, items, key_only=0):
+    n = items.size
+    buf, tmp = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+    res = C.c_void_p()
+    smj.check(smj.lib.smjdev_sort(buf.ptr, tmp.ptr, n, key_only, 1, C.byref(res)), "sort")
+    smj.check(smj.lib.smjdev_sync())
+    assert res.value in (buf.ptr, tmp.ptr)
+    got = (buf if res.value == buf.ptr else tmp).to_host()
+    buf.free()
+    tmp.free()
+    return got
+
+
+def test_device_sort_msd_path(smj, orc, monkeypatch):
+    """Whole-word sorts of >= 2^21 items take the MSD path (two histogram-free partition passes +
+    in-bucket counting sort, ties ordered by payload) when it applies and the LSD sort otherwise;
+    bit-identical to the oracle (== the reference's avxsort order) either way."""
+    rng = np.random.default_rng(21)
+    n = 3_000_017
+    lo32 = np.uint64(0xFFFFFFFF)
+    cases = {
+        "unique": ol.make_unique(rng, n),                               # keys a permutation: no ties
+        "row_ids": orc.gen_unique(n, 12345),                            # bench_sort's data
+        "short_ties": ol.rand_items(rng, n, 1 << 21),                   # ~1.4 items per key: runs ordered in place
+        "wide": ol.rand_items(rng, n, (1 << 31) - 1),                   # 31 key bits: 13 bits left per bucket
+        "long_ties": ol.rand_items(rng, n, 1 << 10) | (np.uint64(1 << 30) << np.uint64(32)),  # runs > 64: LSD
+        "narrow": ol.rand_items(rng, n, 1 << 12),                       # 12 key bits: LSD
+        "sorted": np.sort(ol.make_unique(rng, n)),
+        "reverse": np.sort(ol.make_unique(rng, n))[::-1].copy(),
+    }
+    skew = ol.make_unique(rng, n)
+    skew[: n // 2] = (skew[: n // 2] & lo32) | (np.uint64(77) << np.uint64(32))  # half the items share a key
+    cases["skew"] = skew
+    for name, items in cases.items():
+        exp = orc.sort(items)
+        monkeypatch.setenv("SMJ_SORT_PATH", "msd")  # the MSD path from 2^21 items on (default: 40 M)
+        assert np.array_equal(_sort_device(smj, items), exp), name
+        monkeypatch.setenv("SMJ_SORT_PATH", "lsd")
+        assert np.array_equal(_sort_device(smj, items), exp), name + " (lsd)"
+        monkeypatch.delenv("SMJ_SORT_PATH")
+    # the optimistic passes' repair paths under the sort
+    monkeypatch.setenv("SMJ_SORT_PATH", "msd")
+    for hook in ("shrink2", "nocoop"):
+        monkeypatch.setenv("SMJ_MSD_TEST", hook)
+        assert np.array_equal(_sort_device(smj, cases["unique"]), orc.sort(cases["unique"])), hook
+        monkeypatch.delenv("SMJ_MSD_TEST")
+    monkeypatch.delenv("SMJ_SORT_PATH")
+
+
 @pytest.mark.parametrize("n", SORT_SIZES)
 @pytest.mark.parametrize("algo", [1, 0])
 def test_device_sort(smj, orc, n, algo):
@@ -378,6 +427,9 @@ def test_mway_optimistic_partition_and_its_exact_repeats(smj, orc, monkeypatch):
     st = _device_mway_stats(smj, r, s)
     assert (st.matches, st.checksum, st.path, st.repeats) == (*exp, smj.PATH_MSD, 0)
     monkeypatch.delenv("SMJ_MSD_MODE")
+    monkeypatch.setenv("SMJ_MSD_TEST", "nocoop")  # no cooperative launch: sampled bits + exact passes
+    st = _device_mway_stats(smj, r, s)
+    assert (st.matches, st.checksum, st.path, st.repeats) == (*exp, smj.PATH_MSD, 0)
     for hook in ("shrink1", "shrink2"):
         monkeypatch.setenv("SMJ_MSD_TEST", hook)
         st = _device_mway_stats(smj, r, s)
@@ -482,7 +534,7 @@ def _materialize(smj, r, s, layout):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-def test_join_materialize(smj, orc, layout):
+def test_join_materialize(smj, orc, layout, monkeypatch):
     """smjdev_join_materialize against the oracle's restatement of the JOIN_MATERIALIZE loop
     (joincommon.c:256-278): same multiset of emitted tuples, for unique / foreign-key / duplicate /
     heavy-run / disjoint / empty inputs."""
@@ -499,7 +551,9 @@ def test_join_materialize(smj, orc, layout):
     s = ol.rand_items(rng, 3_000, 50)
     assert np.array_equal(np.sort(_materialize(smj, r, s, layout)), np.sort(orc.join_materialize(r, s, layout)))
     r, s = orc.gen_unique(1 << 20, 5), orc.gen_fk((1 << 21) + 7, 1 << 20, 9)
+    monkeypatch.setenv("SMJ_SORT_PATH", "msd")  # S (2^21 items) is sorted MSD-first, R LSD
     got = _materialize(smj, r, s, layout)
+    monkeypatch.delenv("SMJ_SORT_PATH")
     assert got.size == s.size
     assert np.array_equal(np.sort(got), np.sort(orc.join_materialize(r, s, layout)))
 
