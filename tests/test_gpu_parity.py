@@ -517,6 +517,38 @@ def test_join_pinned_host_relations_overlap_upload(smj, orc, monkeypatch):
         lib.smjdev_host_free(hs)
 
 
+def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
+    """Eight or more runs in whole-word order with a large total are merged by range-partitioning
+    their union (the MSD sort) instead of log2(k) merge rounds: same output as the oracle's merge,
+    with adjacent and with scattered runs, and the rounds still run when the shortcut is off."""
+    rng = np.random.default_rng(8)
+    nruns, per = 16, 150_001
+    runs = [np.sort(ol.rand_items(rng, per + 13 * i, 1 << 24)) for i in range(nruns)]
+    exp = orc.multiway_merge(runs)
+    total = exp.size
+    bufs = [smj.DeviceBuffer.from_host(x) for x in runs]
+    out, tmp = smj.DeviceBuffer(total), smj.DeviceBuffer(total)
+    ptrs = (C.c_void_p * nruns)(*[b.ptr for b in bufs])
+    lens = (C.c_uint64 * nruns)(*[x.size for x in runs])
+    for path in ("msd", "lsd"):  # lsd: the sort declines, the merge rounds run
+        monkeypatch.setenv("SMJ_SORT_PATH", path)
+        smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, lens, nruns, 0), "multiway_merge")
+        assert np.array_equal(out.to_host(), exp), path
+    monkeypatch.setenv("SMJ_SORT_PATH", "msd")
+    # runs that lie back to back in one buffer are sorted where they are (no gathering)
+    cat = smj.DeviceBuffer.from_host(np.concatenate(runs))
+    offs = np.concatenate([[0], np.cumsum([x.size for x in runs])])
+    ptrs2 = (C.c_void_p * nruns)(*[cat.ptr + 8 * int(o) for o in offs[:-1]])
+    smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs2, lens, nruns, 0), "multiway_merge")
+    assert np.array_equal(out.to_host(), exp)
+    assert np.array_equal(cat.to_host(), np.concatenate(runs)), "inputs must stay unmodified"
+    monkeypatch.setenv("SMJ_MERGE_PATH", "rounds")
+    smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, lens, nruns, 0), "multiway_merge")
+    assert np.array_equal(out.to_host(), exp)
+    for b in bufs + [out, tmp, cat]:
+        b.free()
+
+
 # ------------------------------------------------------------------------------------ materialisation
 def _materialize(smj, r, s, layout):
     dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
