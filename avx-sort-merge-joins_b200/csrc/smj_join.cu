@@ -45,7 +45,6 @@ size_t smj_msd_sample_bytes(int which);
 u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, int shrink);
 int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc_r, u64 alloc_s, int shrink,
                          u64 *tab_r, u64 *tab_s, u32 *d_flags);
-u64 smj_msd_tile_items();
 u64 smj_msd_alloc2(u64 n);
 int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
                        u32 kmask, u32 kref, u32 *d_kflag);

@@ -209,7 +209,7 @@ int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used) {
     SmjScratch sc(ctx);
     u64 *d_st = (u64 *)sc.get(smj_msd_sample_bytes(0));
     u32 *d_sub = (u32 *)sc.get(smj_msd_sample_bytes(1)), *d_flags = (u32 *)sc.get(64);
-    u64 *d_misc = (u64 *)sc.get(64);  // [0] largest bucket, [1] repaired buckets, [2] bucket counter (u32)
+    u64 *d_misc = (u64 *)sc.get(64);  // [0] largest bucket, [1] repaired first-level buckets
     if (!d_st || !d_sub || !d_flags || !d_misc) return smj_fail_msg("smj_msd_sort: scratch allocation failed");
     SMJ_CHECK(cudaMemsetAsync(d_flags, 0, 64, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_misc, 0, 64, ctx->stream));

@@ -2,15 +2,21 @@
 //
 // B200 restatement of two reference subsystems:
 //   * src/partition/partition.c:94-287   radix_cluster{,_optimized,_optimized_V2}: histogram +
-//     software-write-combining scatter  ->  k_hist_* + k_onesweep (shared-memory staged scatter,
-//     warp-aggregated ranks via match.any, decoupled look-back instead of a second data pass).
+//     software-write-combining scatter  ->  k_hist_* + scatter kernels that stage a tile in shared
+//     memory in bin order and write it as runs of consecutive addresses:
+//       k_onesweep           STABLE (partition API, LSD passes): per-warp histograms, peers found by
+//                            ballot / shared-memory bitmask, decoupled look-back between tiles;
+//       k_onesweep_unstable  order inside a bin irrelevant (MSD passes, first LSD pass, exchange):
+//                            rank = return value of a shared-memory atomicAdd, one global atomicAdd
+//                            per (tile, bin) on the bin cursor, no look-back chain; optional bin
+//                            capacity check for the histogram-free (optimistic) passes.
 //   * src/avxsort/avxsort.c:128-209      avxsort_aligned: in-register networks + bitonic merges
-//     ->  one-sweep style LSD radix sort over the VARYING bits only (k_bits_reduce finds them).
+//     ->  LSD radix sort over the VARYING bits only (k_bits_reduce finds them); large whole-word
+//     sorts go MSD first (smj_msdsort.cu).
+//   * the m-way join's two-level MSD range partition (exact: k_msd_hist1/2 + scatter; optimistic:
+//     k_msd_sample, k_msd_caps1, k_msd_level2_plan, k_msd_scatter2<true>, k_msd_fix_*).
 //
-// Every pass is STABLE (the reference's partition tests require stability,
-// tests/check_partitioning.c:82-90, and LSD sorting needs it).
-//
-// HBM traffic per item: k_bits_reduce 8 B, k_hist_digits 8 B, each k_onesweep pass 16 B.
+// HBM traffic per item: k_bits_reduce 8 B, histograms 8 B, every scatter pass 16 B.
 #include "smj_common.cuh"
 #include "../../include/smj_device.h"
 
@@ -1798,7 +1804,6 @@ int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc
     SMJ_LAUNCH(ctx, k_msd_caps1, 2, MSD_NB, 0, d_st, nr, ns, alloc_r, alloc_s, shrink, tab_r, tab_s, d_flags);
     return 0;
 }
-u64 smj_msd_tile_items() { return MSD_TILE; }
 // upper bound of the items the second-level slots of an n-item relation span (k_msd_level2_plan)
 u64 smj_msd_alloc2(u64 n) {
     const double per = (double)n / (double)(MSD_NB * MSD_NB);
@@ -1931,28 +1936,6 @@ int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns
     if (ns) SMJ_LAUNCH(ctx, k_bits_sample, 64, 256, 0, s, ns, std::max<u64>(1, ns >> 16), d + 2);
     SMJ_CHECK(cudaMemcpyAsync(host, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-    return 0;
-}
-
-// OR / AND of all items of two relations: host[0..1] = R, host[2..3] = S.  Synchronises.
-int smj_key_bits(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *host) {
-    SmjScratch sc(ctx);
-    u64 *d = (u64 *)sc.get(48);
-    if (!d) return smj_fail_msg("smj_key_bits: scratch allocation failed");
-    const u64 init[6] = {0ull, ~0ull, 0ull, 0ull, ~0ull, 0ull};
-    SMJ_CHECK(cudaMemcpyAsync(d, init, 48, cudaMemcpyHostToDevice, ctx->stream));
-    if (nr) {
-        SMJ_ITEMS(ctx, nr);
-        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, nr, 256, 16), 256, 0, r, nr, d);
-    }
-    if (ns) {
-        SMJ_ITEMS(ctx, ns);
-        SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, ns, 256, 16), 256, 0, s, ns, d + 3);
-    }
-    u64 h[6];
-    SMJ_CHECK(cudaMemcpyAsync(h, d, 48, cudaMemcpyDeviceToHost, ctx->stream));
-    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-    host[0] = h[0], host[1] = h[1], host[2] = h[3], host[3] = h[4];
     return 0;
 }
 
