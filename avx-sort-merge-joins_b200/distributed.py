@@ -309,33 +309,11 @@ class DistributedJoin:
         MSD plan."""
         e, lib, smj, W = self.e, self.e.lib, self.e.smj, self.world
         dev = e.device
-        # ---- 1. plan: varying key bits of R and S over all ranks (sampled, verified below)
-        b4 = (C.c_uint64 * 4)()
-        smj.check(lib.smjdev_sample_key_bits(r.data_ptr(), nr, s.data_ptr(), ns, b4), "sample_key_bits")
-        mine = torch.from_numpy(np.array(list(b4) + [nr, ns], dtype=np.uint64).view(np.int64)).to(dev)
-        allm = [torch.empty_like(mine) for _ in range(W)]
-        dist.all_gather(allm, mine)
-        m = torch.stack(allm).cpu().numpy().view(np.uint64)
-        fold = lambda col, op: int(op.reduce(m[:, col]))
-        sizes_ok = int(m[:, 4].sum() + m[:, 5].sum()) >= (1 << 20) and m[:, 4].sum() > 0 and m[:, 5].sum() > 0
-        plan = msd_plan(fold(0, np.bitwise_or), fold(1, np.bitwise_and), fold(2, np.bitwise_or),
-                        fold(3, np.bitwise_and)) if sizes_ok else None
-        if plan is None:
-            return self.step_p2p(r, nr, s, ns, self._fallback_splitters(m), px)
-        lo, hi, shift1 = plan
-        # ---- 2. first-level histograms + exact OR/AND, all-gathered
-        loc = torch.zeros(2 * 512 + 4, dtype=torch.int64, device=dev)
-        loc[1025], loc[1027] = -1, -1  # AND accumulators start at ~0
-        smj.check(lib.smjdev_msd_hist(r.data_ptr(), nr, shift1, loc[0:512].data_ptr(), loc[1024:1026].data_ptr()), "msd_hist")
-        smj.check(lib.smjdev_msd_hist(s.data_ptr(), ns, shift1, loc[512:1024].data_ptr(), loc[1026:1028].data_ptr()), "msd_hist")
-        alll = [torch.empty_like(loc) for _ in range(W)]
-        dist.all_gather(alll, loc)
-        a = torch.stack(alll).cpu().numpy()
-        ex = a[:, 1024:1028].view(np.uint64)
-        if not msd_plan_holds(int(np.bitwise_or.reduce(ex[:, 0])), int(np.bitwise_and.reduce(ex[:, 1])),
-                              int(np.bitwise_or.reduce(ex[:, 2])), int(np.bitwise_and.reduce(ex[:, 3])), lo, hi):
-            return self.step_p2p(r, nr, s, ns, self._fallback_splitters(m), px)
-        hist = a[:, :1024].reshape(W, 2, 512)
+        # ---- 1 + 2. plan, first-level histograms and exact OR/AND of all ranks (one collective)
+        pre = self._msd_plan_and_hist(r, nr, s, ns)
+        if pre is None:
+            return self.step_p2p(r, nr, s, ns, self._fallback, px)
+        lo, hi, shift1, hist = pre
         owner, offs, mine_counts = msd_layout(hist, self.rank)
         for rel in range(2):
             if int(mine_counts[rel].sum()) > px.cap[rel]:
@@ -421,19 +399,47 @@ class DistributedJoin:
         return int(out[0]), int(out[1]), sent
 
     def _msd_plan_and_hist(self, r, nr: int, s, ns: int, overlap=None):
-        """Steps 1-2 of the MSD exchanges: the digit plan from the sampled OR/AND of all ranks and
-        the all-gathered first-level histograms (with the exact OR/AND that verifies the plan).
-        overlap(loc, shift1): called after the all-gather has been ENQUEUED and before the host
-        waits for it, with the device tensor of the local histograms (R at 0:512, S at 512:1024).
+        """Steps 1-2 of the MSD exchanges in ONE collective: every rank derives the digit plan from
+        the sampled OR/AND of its OWN slices, histograms them by that plan's first digit and
+        all-gathers {histograms, exact OR/AND, sampled OR/AND, sizes, the digit it used}.  When all
+        ranks used the digit of the global plan (the usual case: every slice spans the key domain)
+        the histograms are the ones needed; otherwise they are taken again with the global digit
+        (a second collective).  overlap(loc, shift1): called after the all-gather has been ENQUEUED
+        and before the host waits for it, with the device tensor of the local histograms (R at
+        0:512, S at 512:1024); called again if the digit turns out to be another one.
         Returns (lo, hi, shift1, hist[W][2][512]) or None (then self._fallback holds splitters)."""
         e, lib, smj, W = self.e, self.e.lib, self.e.smj, self.world
         dev = e.device
         b4 = (C.c_uint64 * 4)()
         smj.check(lib.smjdev_sample_key_bits(r.data_ptr(), nr, s.data_ptr(), ns, b4), "sample_key_bits")
-        mine = torch.from_numpy(np.array(list(b4) + [nr, ns], dtype=np.uint64).view(np.int64)).to(dev)
-        allm = [torch.empty_like(mine) for _ in range(W)]
-        dist.all_gather(allm, mine)
-        m = torch.stack(allm).cpu().numpy().view(np.uint64)
+        local = msd_plan(int(b4[0]), int(b4[1]), int(b4[2]), int(b4[3])) if nr and ns else None
+        guess = local[2] if local is not None else 0
+
+        def gather(shift1):
+            """histograms by the digit at shift1 (0: none) + the bookkeeping words, all-gathered"""
+            tail = np.array([0, -1, 0, -1] + [int(x) for x in np.array(list(b4), dtype=np.uint64).view(np.int64)]
+                            + [nr, ns, shift1], dtype=np.int64)
+            loc = torch.zeros(1024 + tail.size, dtype=torch.int64, device=dev)
+            loc[1024:] = torch.from_numpy(tail).to(dev, non_blocking=True)
+            if shift1:
+                smj.check(lib.smjdev_msd_hist(r.data_ptr(), nr, shift1, loc[0:512].data_ptr(),
+                                              loc[1024:1026].data_ptr()), "msd_hist")
+                smj.check(lib.smjdev_msd_hist(s.data_ptr(), ns, shift1, loc[512:1024].data_ptr(),
+                                              loc[1026:1028].data_ptr()), "msd_hist")
+            alll = torch.empty(W, loc.numel(), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(alll, loc)
+            if getattr(self, "_pin", None) is None or self._pin.shape != alll.shape:
+                self._pin = torch.empty(alll.shape, dtype=torch.int64).pin_memory()
+            self._pin.copy_(alll, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if overlap is not None and shift1:
+                overlap(loc, shift1)  # work that needs only local data runs while the host waits
+            ev.synchronize()
+            return self._pin.numpy().copy()
+
+        a = gather(guess)
+        m = a[:, 1028:1034].view(np.uint64)  # sampled OR_R AND_R OR_S AND_S, nr, ns of every rank
         self._fallback = self._fallback_splitters(m)
         fold = lambda col, op: int(op.reduce(m[:, col]))
         sizes_ok = int(m[:, 4].sum() + m[:, 5].sum()) >= (1 << 20) and m[:, 4].sum() > 0 and m[:, 5].sum() > 0
@@ -442,21 +448,8 @@ class DistributedJoin:
         if plan is None:
             return None
         lo, hi, shift1 = plan
-        loc = torch.zeros(2 * 512 + 4, dtype=torch.int64, device=dev)
-        loc[1025], loc[1027] = -1, -1  # AND accumulators start at ~0
-        smj.check(lib.smjdev_msd_hist(r.data_ptr(), nr, shift1, loc[0:512].data_ptr(), loc[1024:1026].data_ptr()), "msd_hist")
-        smj.check(lib.smjdev_msd_hist(s.data_ptr(), ns, shift1, loc[512:1024].data_ptr(), loc[1026:1028].data_ptr()), "msd_hist")
-        alll = torch.empty(W, loc.numel(), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(alll, loc)
-        if getattr(self, "_pin", None) is None or self._pin.shape != alll.shape:
-            self._pin = torch.empty(alll.shape, dtype=torch.int64).pin_memory()
-        self._pin.copy_(alll, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        if overlap is not None:
-            overlap(loc, shift1)  # work that needs only local data runs while the host waits
-        ev.synchronize()
-        a = self._pin.numpy().copy()
+        if not np.all(a[:, 1034] == shift1):  # some rank guessed another digit: once more, all alike
+            a = gather(shift1)
         ex = a[:, 1024:1028].view(np.uint64)
         if not msd_plan_holds(int(np.bitwise_or.reduce(ex[:, 0])), int(np.bitwise_and.reduce(ex[:, 1])),
                               int(np.bitwise_or.reduce(ex[:, 2])), int(np.bitwise_and.reduce(ex[:, 3])), lo, hi):
