@@ -463,6 +463,40 @@ def test_mway_optimistic_partition_input_orders(smj, orc):
     assert (st.matches, st.checksum) == orc.join_bruteforce(base, s2)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_mway_fast_path_fuzz(smj, orc, seed):
+    """Randomly shaped relations through the optimistic m-way path against the oracle: sizes around
+    the 2^20 threshold, 19..31 key bits, unique / duplicated / Zipf / clustered / partly sorted keys.
+    Whatever the passes guess, count and checksum must be the oracle's."""
+    rng = np.random.default_rng(1000 + seed)
+    bits = int(rng.integers(19, 32))
+    kmax = (1 << bits) - 1
+    nr = int(rng.integers(1 << 19, 3 << 20))
+    ns = int(rng.integers(1 << 19, 5 << 20))
+
+    def keys(n, kind):
+        if kind == "unique" and min(kmax, 8 * n) >= n:
+            k = rng.permutation(np.arange(1, min(kmax, 8 * n) + 1, dtype=np.uint64))[:n]
+        elif kind == "uniform":
+            k = rng.integers(1, kmax + 1, size=n, dtype=np.uint64)
+        elif kind == "zipf":
+            k = ol.zipf_keys(rng, n, min(kmax, n), float(rng.uniform(0.3, 1.1)))
+        elif kind == "clustered":  # most keys inside a few narrow ranges
+            centres = rng.integers(1, kmax + 1, size=5, dtype=np.uint64)
+            k = (centres[rng.integers(0, 5, size=n)] + rng.integers(0, 4096, size=n, dtype=np.uint64)) % np.uint64(kmax) + np.uint64(1)
+        else:  # sorted blocks
+            k = np.sort(rng.integers(1, kmax + 1, size=n, dtype=np.uint64))
+        k[0], k[-1] = np.uint64(1), np.uint64(kmax)  # the whole key domain varies in both relations
+        return k
+
+    kr = keys(nr, ["unique", "uniform", "sorted"][seed % 3])
+    ks = keys(ns, ["uniform", "zipf", "clustered", "unique", "sorted"][seed % 5])
+    r = ol.keys_ok((kr << np.uint64(32)) | rng.integers(0, 1 << 32, size=nr, dtype=np.uint64))
+    s = ol.keys_ok((ks << np.uint64(32)) | np.arange(ns, dtype=np.uint64))
+    st = _device_mway_stats(smj, r, s)
+    assert (st.matches, st.checksum) == orc.join_bruteforce(r, s), (seed, bits, nr, ns, st.path, st.repeats)
+
+
 def test_join_pinned_host_relations_overlap_upload(smj, orc, monkeypatch):
     """Pinned host relations go to smjdev_join as they are: uploaded in 64 MiB chunks on the copy
     stream while the first partitioning pass consumes the chunks (several chunks per relation
