@@ -63,9 +63,11 @@ __global__ void __launch_bounds__(256) k_bucket_sizes(const u64 *__restrict__ st
 // of the bucket over the 2^lbits key values left inside it.  A bucket of up to BS_THREADS * IPT
 // items stays in registers between the counting and the placing pass and is put in order in a
 // shared-memory staging area, so that it is read once and written with coalesced stores; a larger
-// bucket (skew) is read twice and placed directly in global memory.  Runs of equal keys are
-// ordered by payload afterwards (insertion sort by the thread that owns the key slot); a run
-// longer than BS_MAXRUN raises *flag.
+// bucket (skew) is read twice and placed directly in global memory.  The loop is software
+// pipelined: the bounds of the next bucket are requested when the current one starts, its items
+// as soon as the registers are free (before the current bucket is written out).  Runs of equal
+// keys are ordered by payload (insertion sort by the thread that owns the key slot); a run longer
+// than BS_MAXRUN raises *flag.
 template <int BS_THREADS, int IPT>
 __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort(const u64 *__restrict__ in,
                                                             const u64 *__restrict__ starts,
@@ -81,19 +83,29 @@ __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort(const u64 *__restric
     __shared__ u32 s_w[BS_THREADS / 32];
     const u32 per = (slots + BS_THREADS - 1) / BS_THREADS;  // consecutive slots per thread
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u32 b = blockIdx.x; b < nbuckets; b += gridDim.x) {
-        const u64 s0 = starts[b], c = ends[b] - s0, o0 = outoff[b];
-        if (c == 0) continue;
-        const bool small = c <= (u64)CAP;
-        u64        x[IPT];
-        if (small) {
+    u32 b = blockIdx.x;
+    if (b >= nbuckets) return;
+    u64 s0 = starts[b], c = ends[b] - s0, o0 = outoff[b];
+    u64 x[IPT];
+    auto load_items = [&](u64 from, u64 count) {
 #pragma unroll
-            for (int j = 0; j < IPT; j++)
-                x[j] = ((u64)j * BS_THREADS + threadIdx.x < c) ? ld_stream(in + s0 + j * BS_THREADS + threadIdx.x) : 0ull;
+        for (int j = 0; j < IPT; j++)
+            x[j] = ((u64)j * BS_THREADS + threadIdx.x < count) ? ld_stream(in + from + j * BS_THREADS + threadIdx.x)
+                                                                : 0ull;
+    };
+    if (c <= (u64)CAP) load_items(s0, c);
+    for (u32 i = threadIdx.x; i < slots; i += BS_THREADS) cnt[i] = 0;
+    while (true) {
+        // bounds of the next bucket: requested now, needed when this one is done
+        const u32 nb = b + gridDim.x;
+        u64 ns0 = 0, nc = 0, no0 = 0;
+        if (nb < nbuckets) {
+            ns0 = starts[nb];
+            nc  = ends[nb] - ns0;
+            no0 = outoff[nb];
         }
-        __syncthreads();  // the previous bucket is done with cnt / stage
-        for (u32 i = threadIdx.x; i < slots; i += BS_THREADS) cnt[i] = 0;
-        __syncthreads();
+        const bool small = c <= (u64)CAP;
+        __syncthreads();  // cnt is zero, the staging area is free
         if (small) {
 #pragma unroll
             for (int j = 0; j < IPT; j++)
@@ -143,6 +155,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort(const u64 *__restric
                 out[o0 + atomicAdd(&cnt[(u32)(y >> lo_shift) & mask], 1u)] = y;
             }
         }
+        // the registers are free: the next bucket's items travel while this one is finished
+        if (nb < nbuckets && nc <= (u64)CAP) load_items(ns0, nc);
         __syncthreads();  // the bucket is in place (this CTA's stores are visible to it)
         if (any_tie) {
             // cnt[sl] is now the END of slot sl's run; it starts where the previous slot's ends
@@ -168,8 +182,11 @@ __global__ void __launch_bounds__(BS_THREADS) k_bucket_sort(const u64 *__restric
             }
             __syncthreads();
         }
+        for (u32 i = threadIdx.x; i < slots; i += BS_THREADS) cnt[i] = 0;  // for the next bucket
         if (small)
             for (u32 i = threadIdx.x; i < (u32)c; i += BS_THREADS) st_stream(out + o0 + i, stage[i]);
+        if (nb >= nbuckets) break;
+        b = nb, s0 = ns0, c = nc, o0 = no0;
     }
 }
 
@@ -184,7 +201,13 @@ int launch_bucket_sort(SmjCtx *ctx, const u64 *b, const u64 *starts, const u64 *
         smem_set = smem;
         smem_gen = ctx->generation;
     }
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / BS_THREADS, (200u * 1024u) / std::max<size_t>(smem, 1024)));
+    int per_sm = 1;  // resident CTAs per SM: the grid is exactly one wave (static bucket assignment)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_sort<BS_THREADS, IPT>, BS_THREADS, smem) !=
+            cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, (k_bucket_sort<BS_THREADS, IPT>), ctx->sm_count * per_sm, BS_THREADS, smem, b, starts, bend, outoff, NB2,
                lo_shift, lbits, out, flag);
@@ -200,7 +223,7 @@ int launch_bucket_sort(SmjCtx *ctx, const u64 *b, const u64 *starts, const u64 *
 int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used) {
     *used = 0;
     // 2^18 buckets pay off from ~150 items per bucket on (measured: 16 M items 0.77 ms against
-    // 0.41 ms for the LSD sort, 128 M items 1.93 against 3.20 ms, 10^9 items 16.3 against 25.1 ms)
+    // 0.41 ms for the LSD sort, 128 M items 1.89 against 3.20 ms, 10^9 items 14.2 against 25.1 ms)
     const char *mode_env = getenv("SMJ_SORT_PATH");  // "lsd" disables this path, "msd" lowers the threshold
     if (mode_env && mode_env[0] == 'l') return 0;
     if (n < ((mode_env && mode_env[0] == 'm') ? (1ull << 21) : 40000000ull)) return 0;
@@ -247,11 +270,11 @@ int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used) {
     SMJ_LAUNCH(ctx, k_bucket_sizes, NB2 / 256, 256, 0, starts, bend, NB2, sizes, d_misc);
     if ((rc = smj_exclusive_scan_u64(ctx, sizes, NB2, outoff))) return rc;
     // register-resident buckets: 128 threads x 8 items (buckets up to 1024 items) when the average
-    // bucket is small, 256 x 20 (up to 5120) otherwise; larger buckets take the kernel's slow path
+    // bucket is small, 512 x 10 (up to 5120) otherwise; larger buckets take the kernel's slow path
     if (n / NB2 <= 700)
         rc = launch_bucket_sort<128, 8>(ctx, b, starts, bend, outoff, pl.lo_shift, pl.lbits, out, d_flags + 6, n);
     else
-        rc = launch_bucket_sort<256, 20>(ctx, b, starts, bend, outoff, pl.lo_shift, pl.lbits, out, d_flags + 6, n);
+        rc = launch_bucket_sort<512, 10>(ctx, b, starts, bend, outoff, pl.lo_shift, pl.lbits, out, d_flags + 6, n);
     if (rc) return rc;
     u32 hf[16];
     u64 hm[8];
