@@ -122,6 +122,7 @@ SIGNATURES = {
     "smjdev_msd_scatter_local": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp, _vp]),
     "smjdev_join_level1_seg": (C.c_int, [_vp, C.c_uint32, _u64p, _vp, C.c_uint32, _u64p, C.c_uint32, C.c_uint32,
                                          C.POINTER(smj_join_stats_t)]),
+    "smjdev_debug_copy": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32]),
     "smjdev_exchange_begin": (C.c_int, []),
     "smjdev_exchange_copy": (C.c_int, [_vp, _vp, C.c_size_t]),
     "smjdev_exchange_end": (C.c_int, []),

@@ -495,3 +495,37 @@ int smjdev_download(void *dst, const void *src, size_t bytes) {
     return staged_copy(c, (char *)const_cast<void *>(src), (char *)dst, bytes, 1);
 }
 }
+
+// ---------------------------------------------------------------------------------------
+// Measurement helper (tools/p2p_store_bw.py): copy n 64-bit items with SM stores of `width` bytes
+// per lane (8 or 16), run length `run` items: after every run the destination skips `gap` items,
+// which mimics the (tile, bin) runs the scatter kernels write into peer memory.
+// ---------------------------------------------------------------------------------------
+namespace {
+template <int WIDTH>
+__global__ void __launch_bounds__(256) k_debug_copy(const u64 *__restrict__ src, u64 *__restrict__ dst, u64 n,
+                                                    u32 run, u32 gap) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    if (WIDTH == 16) {
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; 2 * i + 1 < n; i += stride) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + 2 * i);
+            const u64        o = 2 * i + ((2 * i) / run) * gap;
+            *reinterpret_cast<ulonglong2 *>(dst + o) = v;
+        }
+    } else {
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            dst[i + (i / run) * gap] = src[i];
+    }
+}
+}  // namespace
+extern "C" int smjdev_debug_copy(const uint64_t *src, uint64_t *dst, uint64_t n, int width, uint32_t run,
+                                 uint32_t gap) {
+    SmjCtx *c = smj_ctx();
+    if (!c) return -1;
+    if (run == 0 || (run & 1) || (gap & 1)) return smj_fail_msg("smjdev_debug_copy: run and gap must be even");
+    if (width == 16)
+        SMJ_LAUNCH(c, k_debug_copy<16>, c->sm_count * 8, 256, 0, (const u64 *)src, (u64 *)dst, n, run, gap);
+    else
+        SMJ_LAUNCH(c, k_debug_copy<8>, c->sm_count * 8, 256, 0, (const u64 *)src, (u64 *)dst, n, run, gap);
+    return 0;
+}

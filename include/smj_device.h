@@ -180,6 +180,10 @@ int smjdev_join_level1_seg(const uint64_t *r, uint32_t nseg_r, const uint64_t *r
 /* Bulk exchange on the copy engines, ordered with the compute stream: begin() makes the copy stream
  * wait for everything enqueued so far, copy() enqueues one contiguous copy (dst / src may be peer
  * buffers opened with smjdev_ipc_open), end() makes the compute stream wait for the copies. */
+/* Measurement helper (tools/p2p_store_bw.py): SM-store copy of n items, `width` (8 or 16) bytes per
+ * lane, in runs of `run` items separated by `gap` items in dst (dst may be a peer buffer). */
+int smjdev_debug_copy(const uint64_t *src, uint64_t *dst, uint64_t n, int width, uint32_t run,
+                      uint32_t gap);
 int smjdev_exchange_begin(void);
 int smjdev_exchange_copy(void *dst, const void *src, size_t bytes);
 int smjdev_exchange_end(void);
