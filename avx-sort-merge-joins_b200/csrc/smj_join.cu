@@ -49,7 +49,8 @@ u64 smj_msd_alloc2(u64 n);
 int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
                        u32 kmask, u32 kref, u32 *d_kflag);
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
-                       u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink);
+                       u32 dense_slot, u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed,
+                       int shrink);
 int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
 
 namespace {
@@ -1013,7 +1014,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
                                          kref, flags + 12 + 2 * q)))
                 return rc;
             if (x.opt2) {
-                if ((rc = smj_msd_pass_b_opt(ctx, x.a, x.n, x.d_tab, x.b, x.alloc2, pl.shift2, x.starts,
+                if ((rc = smj_msd_pass_b_opt(ctx, x.a, x.n, x.d_tab, x.b, x.alloc2, pl.shift2, 1u << pl.lbits, x.starts,
                                              x.ends, x.d_counts, flags + 4 + 2 * q, d_state + 12 + q, shrink2)))
                     return rc;
             } else {

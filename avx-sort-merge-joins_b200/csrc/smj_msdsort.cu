@@ -29,7 +29,8 @@ u64 smj_msd_alloc2(u64 n);
 int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
                        u32 kmask, u32 kref, u32 *d_kflag);
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
-                       u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink);
+                       u32 dense_slot, u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed,
+                       int shrink);
 int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
 int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
                    u32 shift2, u64 *offsets);
@@ -259,7 +260,7 @@ int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used) {
     if ((rc = smj_msd_pass_a_opt(ctx, in, n, a, pl.shift1, d_tab, d_flags, kmask, kref, d_flags + 2))) return rc;
     const u64 *bend = ends;
     if (slots) {
-        if ((rc = smj_msd_pass_b_opt(ctx, a, n, d_tab, b, alloc2, pl.shift2, starts, ends, d_counts, d_flags + 4,
+        if ((rc = smj_msd_pass_b_opt(ctx, a, n, d_tab, b, alloc2, pl.shift2, 1u << pl.lbits, starts, ends, d_counts, d_flags + 4,
                                      d_misc + 1, shrink2)))
             return rc;
     } else {

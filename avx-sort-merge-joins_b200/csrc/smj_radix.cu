@@ -1440,6 +1440,7 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_caps1(const u64 *__restrict__ st
 // starts and initial cursors of bucket b's sub-buckets; CTA 0 also writes the per-bucket arrays.
 // Raises *flag and plans no tiles when the slots do not fit alloc2 items.
 __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restrict__ tab1, u64 alloc2,
+                                                            u32 dense_slot,
                                                             u64 *__restrict__ tile_prefix,
                                                             u64 *__restrict__ bucket_count,
                                                             u64 *__restrict__ cap2,
@@ -1447,25 +1448,38 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restric
                                                             u64 *__restrict__ starts,
                                                             u64 *__restrict__ cursors,
                                                             MsdTile *__restrict__ tiles, u32 *flag) {
-    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB], s_cap[MSD_NB], s_cnt1[MSD_NB];
+    __shared__ u64 s_t[MSD_NB], s_c[MSD_NB], s_d[MSD_NB], s_cap[MSD_NB], s_cnt1[MSD_NB];
     const int b   = threadIdx.x;
     const u64 st1 = tab1[MSD_NB + b];
     const u64 c   = min(tab1[b] - st1, tab1[2 * MSD_NB + b] - st1);
     const u64 t   = (c + MSD_TILE - 1) / MSD_TILE;
     const u64 avg = (c + MSD_NB - 1) / MSD_NB;
-    const u64 cap = c ? ((avg + (u64)ceil(7.0 * sqrt((double)avg + 1.0)) + 8 + 3) & ~3ull) : 0ull;
+    u64       cap = c ? ((avg + (u64)ceil(7.0 * sqrt((double)avg + 1.0)) + 8 + 3) & ~3ull) : 0ull;
+    // Relations that come here have (practically) unique keys, so a sub-bucket cannot hold more
+    // than dense_slot = 2^lbits items, and a first-level bucket that is only partly filled (the top
+    // of a dense key domain) fills the sub-buckets it does use completely: give such a bucket slots
+    // of that size -- if the whole layout still fits (sparse key domains: 2^lbits is large).
+    const u64 dcap = c ? max(cap, (min((u64)dense_slot, c) + 3) & ~3ull) : 0ull;
     s_t[b]        = t;
     s_c[b]        = cap * MSD_NB;
-    s_cap[b]      = cap;
+    s_d[b]        = dcap * MSD_NB;
     s_cnt1[b]     = c;
     __syncthreads();
     for (int o = 1; o < MSD_NB; o <<= 1) {
-        u64 at = (b >= o) ? s_t[b - o] : 0, ac = (b >= o) ? s_c[b - o] : 0;
+        u64 at = (b >= o) ? s_t[b - o] : 0, ac = (b >= o) ? s_c[b - o] : 0, ad = (b >= o) ? s_d[b - o] : 0;
         __syncthreads();
         s_t[b] += at;
         s_c[b] += ac;
+        s_d[b] += ad;
         __syncthreads();
     }
+    if (s_d[MSD_NB - 1] <= alloc2) {  // the roomier layout fits: use it (uniform for the whole CTA)
+        cap = dcap;
+        __syncthreads();
+        s_c[b] = s_d[b];
+    }
+    s_cap[b] = cap;
+    __syncthreads();
     const bool fits = s_c[MSD_NB - 1] <= alloc2;
     if (blockIdx.x == 0) {
         tile_prefix[b]  = fits ? s_t[b] - t : 0;
@@ -1833,10 +1847,12 @@ int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts) {
 // bucket into 512 equal slots, no histogram; buckets with an overflowing slot are repartitioned
 // exactly inside their region by the k_msd_fix_* kernels.  starts / ends (device, 2^18 entries
 // each): sub-bucket q is b[starts[q] .. ends[q]).  d_counts (device, 512) receives the
-// first-level bucket sizes.  alloc2 = items b can hold.  *d_flag is raised when the slots do not fit alloc2 (nothing is partitioned then);
+// first-level bucket sizes.  alloc2 = items b can hold; dense_slot = 2^(key bits left inside a
+// sub-bucket): the most items a sub-bucket of a relation with unique keys can hold.  *d_flag is raised when the slots do not fit alloc2 (nothing is partitioned then);
 // *d_nfixed (u64) counts the repartitioned buckets.
 int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
-                       u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed, int shrink) {
+                       u32 dense_slot, u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed,
+                       int shrink) {
     SmjScratch sc(ctx);
     u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_cap2 = (u64 *)sc.get(MSD_NB * 8);
     u64 *d_base2 = (u64 *)sc.get(MSD_NB * 8);
@@ -1849,7 +1865,7 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
     MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
     if (!d_tiles) return smj_fail_msg("smj_msd_pass_b_opt: scratch allocation failed");
-    SMJ_LAUNCH(ctx, k_msd_level2_plan, MSD_NB, MSD_NB, 0, d_tab, alloc2, d_tpref, d_counts, d_cap2, d_base2,
+    SMJ_LAUNCH(ctx, k_msd_level2_plan, MSD_NB, MSD_NB, 0, d_tab, alloc2, dense_slot, d_tpref, d_counts, d_cap2, d_base2,
                starts, ends, d_tiles, d_flag);
     const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 4, max_tiles);
     if (msd_scatter2_attr(ctx)) return -1;
