@@ -859,7 +859,7 @@ struct MsdRel {
     BucketSet set() const { return BucketSet{b, starts, opt2 ? ends : starts + 1, n}; }
 };
 
-// A relation in pinned host memory on its way to HBM: copied chunk by chunk on the copy stream,
+// A relation in pinned host memory on its way to HBM: copied chunk by chunk (128 MiB) on the copy stream,
 // one event per chunk, so that the first partitioning pass can consume chunk k while chunk k + 1
 // is still crossing PCIe (the pass needs no histogram, hence no complete relation).
 struct Upload {
@@ -895,7 +895,12 @@ static cudaEvent_t upload_event(SmjCtx *ctx, size_t idx) {
 }
 // starts the copies; ev_base: first index of this relation's events in the cache
 static int upload_begin(SmjCtx *ctx, SmjScratch &sc, const u64 *host, u64 n, size_t ev_base, Upload &up) {
-    constexpr u64 CHUNK = 8ull << 20;  // 8 Mi items = 64 MiB = 1024 scatter tiles
+    static u64 CHUNK = 0;  // items per chunk, a multiple of the scatter tile (8192 items)
+    if (!CHUNK) {
+        // measured end to end (128 M x 128 M): 32 MiB 38.3 ms, 64 MiB 38.2, 128 MiB 38.1, 256 MiB 38.1
+        const char *e = getenv("SMJ_UPLOAD_CHUNK_MB");
+        CHUNK         = ((e && atoi(e) > 0) ? (u64)atoi(e) : 128ull) << 17;
+    }
     up.ctx   = ctx;
     up.host  = host;
     up.n     = n;
@@ -950,7 +955,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<u64> samp(SMJ_MSD_SAMPLE_WORDS);
     // an uploading relation is sampled where it is complete: in pinned host memory, over PCIe
-    // (a smaller sample: 2 MiB per relation next to the 64 MiB chunks of the upload)
+    // (a smaller sample: 2 MiB per relation next to the 128 MiB chunks of the upload)
     const bool uploading = (up_r && up_r->active()) || (up_s && up_s->active());
     const u64 *samp_r = (up_r && up_r->active()) ? up_r->host : r;
     const u64 *samp_s = (up_s && up_s->active()) ? up_s->host : s;
@@ -1114,7 +1119,7 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             r = up_r.dev;
         }
         if (smj_is_host_pointer(s)) {
-            if ((rc = upload_begin(ctx, sc, s, ns, 1 + div_up(nr, 8ull << 20), up_s))) return rc;
+            if ((rc = upload_begin(ctx, sc, s, ns, 1 + up_r.ev.size() + 1, up_s))) return rc;
             s = up_s.dev;
         }
         SMJ_CHECK(cudaEventRecord(h2d1, ctx->copy_stream));

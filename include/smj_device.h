@@ -145,7 +145,7 @@ typedef struct smj_join_stats_t {
 enum { SMJ_PATH_GENERAL = 0, SMJ_PATH_MSD = 1, SMJ_PATH_MSD_OPT = 2 };
 
 /* Join of two relations in device memory or in PINNED host memory (left unmodified).  A pinned
- * host relation is uploaded in 64 MiB chunks on a separate copy stream; the m-way path runs its
+ * host relation is uploaded in 128 MiB chunks on a separate copy stream; the m-way path runs its
  * first partitioning pass on every chunk as it arrives, so partitioning hides behind the PCIe
  * transfer (stats->ms_h2d = duration of the copies).
  * nruns: number of sorted runs per relation for m-pass / mpsm (>=1; m-way ignores it). */
