@@ -212,7 +212,6 @@ def run_single_gpu(args, smj) -> dict:
     ms = C.c_float()
     smj.check(lib.smjdev_event_elapsed_ms(e0, e1, C.byref(ms)), "elapsed")
     launches = lib.smjdev_launch_count() - launches0
-    clocks = sampler.stop()
     ms_step = ms.value / args.steps
     value = 2 * n / (ms_step * 1e-3) / 1e6
 
@@ -247,6 +246,10 @@ def run_single_gpu(args, smj) -> dict:
                 "whole_join_frac": (40.0 * 2 * n / (ms_step * 1e-3) / 1e9) / peak,
                 "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
                             for k, v in prof.items()}}
+
+    # (the clock sampler keeps running through the per-kernel pass above: the timed region itself is
+    # a few milliseconds, shorter than nvidia-smi's sampling period)
+    clocks = sampler.stop()
 
     # ---- end to end through sortmergejoin_multiway() with pinned host relations
     hr, hs = lib.smjdev_host_alloc(n * 8), lib.smjdev_host_alloc(n * 8)
