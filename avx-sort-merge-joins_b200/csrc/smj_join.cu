@@ -1109,7 +1109,14 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     // pinned host relations are uploaded chunk by chunk on the copy stream (the m-way fast path
     // overlaps its first partitioning pass with the transfer); everything else sees device arrays
     Upload up_r, up_s;
-    cudaEvent_t h2d0 = nullptr, h2d1 = nullptr;
+    struct EventPair {  // timing events around the copies, destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } h2d;
+    cudaEvent_t &h2d0 = h2d.a, &h2d1 = h2d.b;
     if (nr && ns && (smj_is_host_pointer(r) || smj_is_host_pointer(s))) {
         SMJ_CHECK(cudaEventCreate(&h2d0));
         SMJ_CHECK(cudaEventCreate(&h2d1));
@@ -1209,8 +1216,6 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
     if (h2d0) {
         cudaEventSynchronize(h2d1);
         cudaEventElapsedTime(&stats->ms_h2d, h2d0, h2d1);
-        cudaEventDestroy(h2d0);
-        cudaEventDestroy(h2d1);
     }
     stats->matches      = h[0];
     stats->checksum     = h[1];

@@ -519,6 +519,10 @@ def test_join_pinned_host_relations_overlap_upload(smj, orc, monkeypatch):
             assert st.ms_h2d > 0
             if algo == smj.ALGO_MWAY:
                 assert st.path == smj.PATH_MSD_OPT
+        # small pinned relations (below the fast path's threshold: general path behind the upload)
+        st = smj.smj_join_stats_t()
+        smj.check(lib.smjdev_join(smj.ALGO_MWAY, hr, 5000, hs, 3000, 1, C.byref(st)), "smjdev_join")
+        assert (st.matches, st.checksum) == orc.join_bruteforce(r[:5000], s[:3000]) and st.path == smj.PATH_GENERAL
         # mixed: R on the device, S pinned; and the exact passes (the upload is awaited first)
         dr = smj.DeviceBuffer.from_host(r)
         st = smj.smj_join_stats_t()
