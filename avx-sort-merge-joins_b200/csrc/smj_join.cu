@@ -902,6 +902,7 @@ struct Upload {
     u64                      n = 0, chunk = 0;  // items, items per chunk
     std::vector<cudaEvent_t> ev;                // ev[k]: chunk k has arrived (cached, not owned)
     bool                     waited = false;
+    bool                     host_visible = false;  // kernels can read `host` directly
     bool active() const { return host != nullptr; }
     u64  nchunks() const { return ev.size(); }
     // every later operation on ctx->stream sees the whole relation
@@ -937,6 +938,14 @@ static int upload_begin(SmjCtx *ctx, SmjScratch &sc, const u64 *host, u64 n, siz
     up.ctx   = ctx;
     up.host  = host;
     up.n     = n;
+    // kernels may read the pinned copy directly (the sample) only if it is mapped into the device's
+    // address space at the same address; registered memory on some systems is not
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<u64 *>(host), 0) != cudaSuccess) {
+        cudaGetLastError();
+        dp = nullptr;
+    }
+    up.host_visible = dp == (const void *)host;
     up.chunk = CHUNK;
     up.dev   = (u64 *)sc.get(n * 8);
     if (!up.dev) return smj_fail_msg("smjdev_join: out of device memory");
@@ -989,9 +998,12 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     std::vector<u64> samp(SMJ_MSD_SAMPLE_WORDS);
     // an uploading relation is sampled where it is complete: in pinned host memory, over PCIe
     // (a smaller sample: 2 MiB per relation next to the 128 MiB chunks of the upload)
-    const bool uploading = (up_r && up_r->active()) || (up_s && up_s->active());
-    const u64 *samp_r = (up_r && up_r->active()) ? up_r->host : r;
-    const u64 *samp_s = (up_s && up_s->active()) ? up_s->host : s;
+    for (Upload *u : {up_r, up_s})  // a pinned copy the device cannot address: sample the uploaded one
+        if (u && u->active() && !u->host_visible && u->wait_all()) return -1;
+    const bool live_r = up_r && up_r->active() && !up_r->waited, live_s = up_s && up_s->active() && !up_s->waited;
+    const bool uploading = live_r || live_s;
+    const u64 *samp_r = live_r ? up_r->host : r;
+    const u64 *samp_s = live_s ? up_s->host : s;
     int rc = smj_msd_sample(ctx, samp_r, nr, samp_s, ns, uploading ? 1u << 16 : 1u << 18, d_st, d_sub,
                             samp.data());
     bool have_sample = true;
@@ -1034,7 +1046,8 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
             return rc;
     for (int q = 0; q < 2; q++) {
         MsdRel &x = rel[q];
-        if (x.opt1 && x.up && x.up->active()) {
+        const bool chunked = x.opt1 && x.up && x.up->active() && !x.up->waited;
+        if (chunked) {
             // the pass consumes the upload chunk by chunk (the bin cursors carry over)
             for (u64 k = 0; k < x.up->nchunks(); k++) {
                 const u64 off = k * x.up->chunk, len = std::min(x.up->chunk, x.n - off);
@@ -1047,7 +1060,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
         } else if (x.up && (rc = x.up->wait_all()))
             return rc;
         if (x.opt1) {
-            if (!(x.up && x.up->active()) &&
+            if (!chunked &&
                 (rc = smj_msd_pass_a_opt(ctx, x.in, x.n, x.a, pl.shift1, x.d_tab, flags + 2 * q, kmask,
                                          kref, flags + 12 + 2 * q)))
                 return rc;

@@ -21,4 +21,4 @@ for i in range(7):
     assert res.contents.totalresults == n
     st = smj.smj_join_stats_t(); lib.smj_last_join_stats(C.byref(st)); h2d.append(st.ms_h2d)
     libc.free(C.cast(res.contents.resultlist, C.c_void_p)); libc.free(C.cast(res, C.c_void_p))
-print(f"chunk {os.environ.get('SMJ_UPLOAD_CHUNK_MB', '64')} MiB: e2e {min(ts[2:]) * 1e3:.2f} ms (mean {sum(ts[2:]) / len(ts[2:]) * 1e3:.2f}), h2d {min(h2d[2:]):.2f} ms")
+print(f"chunk {os.environ.get('SMJ_UPLOAD_CHUNK_MB', '128')} MiB: e2e {min(ts[2:]) * 1e3:.2f} ms (mean {sum(ts[2:]) / len(ts[2:]) * 1e3:.2f}), h2d {min(h2d[2:]):.2f} ms")
