@@ -616,6 +616,109 @@ int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
 }
 }  // namespace
 
+// Wide key domains (11..13 key bits left inside a bucket) are usually SPARSE: 128 M random 31-bit
+// keys put ~500 tuples into a bucket with 8192 possible key values, and clearing a 64 KB
+// direct-address table per bucket would cost more than the bucket.  k_bucket_join_bitmap keeps the
+// direct addressing but tracks occupancy in a BITMAP (1 KB to clear per bucket): a slot holds only
+// the R payload (the R key of a match is the S key), atomicOr on the bitmap word claims it and
+// detects a duplicate R key, which marks the bucket in dupflag for k_bucket_join_cta (the general
+// {count, sum A} table).  33 KB of shared memory per CTA instead of 96: six CTAs per SM.
+// (An open-addressing hash table per warp was tried first: its divergent probe loops made it as
+// slow as clearing the big table, 2.9 ms for 128 M x 128 M.)
+namespace {
+__global__ void __launch_bounds__(256)
+    k_bucket_join_bitmap(const u64 *__restrict__ r, const u64 *__restrict__ rs_, const u64 *__restrict__ re_,
+                         const u64 *__restrict__ s, const u64 *__restrict__ ss_, const u64 *__restrict__ se_,
+                         u32 nbuckets, u32 lo_shift, u32 lbits, u64 big, u32 *next_bucket,
+                         u32 *__restrict__ dupflag, u64 *__restrict__ acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 slots = 1u << lbits, mask = slots - 1, words = slots >> 5;
+    u32 *tpay = (u32 *)smem_raw;  // [slots] R payload
+    u32 *bm   = tpay + slots;     // [slots / 32] occupancy
+    constexpr u32 CLAIM = 64;
+    constexpr int UN    = 4;
+    __shared__ u32 s_b, s_n, s_todo[CLAIM];
+    __shared__ u64 s_red[2][8];
+    u64 my_cnt = 0, my_cks = 0;
+    u32 q = 0, nq = 0;
+    while (true) {
+        if (q == nq) {  // next block of buckets: threads 0..63 test one bucket each
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_b = atomicAdd(next_bucket, CLAIM);
+                s_n = 0;
+            }
+            __syncthreads();
+            const u32 base = s_b;
+            if (base >= nbuckets) break;
+            if (threadIdx.x < CLAIM && base + threadIdx.x < nbuckets) {
+                const u32 bb  = base + threadIdx.x;
+                const u64 nr_ = re_[bb] - rs_[bb], ns_ = se_[bb] - ss_[bb];
+                if (nr_ && ns_ && nr_ <= big && ns_ <= big) s_todo[atomicAdd(&s_n, 1u)] = bb;
+            }
+            __syncthreads();
+            q  = 0;
+            nq = s_n;
+            continue;
+        }
+        __syncthreads();  // the previous bucket is done with the table
+        const u32 b = s_todo[q++];
+        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
+        for (u32 i = threadIdx.x; i < words; i += 256) bm[i] = 0;
+        __syncthreads();
+        int dup = 0;
+        for (u64 i = r0 + threadIdx.x; i < r1; i += UN * 256) {
+            u64 x[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) x[u] = (i + u * 256 < r1) ? ld_stream(r + i + u * 256) : 0ull;
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                if (i + u * 256 < r1) {
+                    const u32 slot = (u32)(x[u] >> lo_shift) & mask, bit = 1u << (slot & 31);
+                    dup |= (atomicOr(&bm[slot >> 5], bit) & bit) != 0;
+                    tpay[slot] = (u32)x[u];
+                }
+            }
+        }
+        if (__syncthreads_or(dup)) {  // a duplicate R key: the general table of k_bucket_join_cta
+            if (threadIdx.x == 0) dupflag[b] = 1u;
+            continue;
+        }
+        for (u64 j = s0 + threadIdx.x; j < s1; j += UN * 256) {
+            u64 y[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) y[u] = (j + u * 256 < s1) ? ld_stream(s + j + u * 256) : 0ull;
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                if (j + u * 256 < s1) {
+                    const u32 slot = (u32)(y[u] >> lo_shift) & mask;
+                    if ((bm[slot >> 5] >> (slot & 31)) & 1u) {  // equal keys: R item = S key + stored payload
+                        my_cnt += 1;
+                        my_cks += smj_cks_a((y[u] & 0xffffffff00000000ull) | tpay[slot]) * smj_cks_b(y[u]);
+                    }
+                }
+            }
+        }
+    }
+    my_cnt = warp_reduce_add(my_cnt);
+    my_cks = warp_reduce_add(my_cks);
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5] = my_cnt;
+        s_red[1][threadIdx.x >> 5] = my_cks;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 c = 0, x = 0;
+        for (int w = 0; w < 8; w++) {
+            c += s_red[0][w];
+            x += s_red[1][w];
+        }
+        if (c) atomicAdd(acc, c);
+        if (x) atomicAdd(acc + 1, x);
+    }
+}
+}  // namespace
+
 // Same join for 11..13 remaining key bits (key domains up to 2^31): the 2^L-slot table no longer
 // fits a warp's share of shared memory, so a whole CTA owns a bucket.
 __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__ r,
@@ -624,25 +727,45 @@ __global__ void __launch_bounds__(256) k_bucket_join_cta(const u64 *__restrict__
                                                          const u64 *__restrict__ s,
                                                          const u64 *__restrict__ ss_,
                                                          const u64 *__restrict__ se_, u32 nbuckets,
-                                                         u32 lo_shift, u32 lbits, u64 big,
+                                                         u32 lo_shift, u32 lbits, u64 big, u32 min_r,
+                                                         const u32 *__restrict__ dupflag,
                                                          u32 *next_bucket, u64 *__restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 slots = 1u << lbits, mask = slots - 1;
     u64 *t_sum = (u64 *)smem_raw;
     u32 *t_cnt = (u32 *)(t_sum + slots);
-    __shared__ u32 s_b;
+    constexpr u32 CLAIM = 64;  // buckets claimed per atomic; the ones this kernel has to do are compacted
+    __shared__ u32 s_b, s_n, s_todo[CLAIM];
     __shared__ u64 s_red[2][8];
     u64 my_cnt = 0, my_cks = 0;
     constexpr int UN = 4;  // loads in flight per thread
+    u32 q = 0, nq = 0;
     while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_b = atomicAdd(next_bucket, 1u);
-        __syncthreads();
-        const u32 b = s_b;
-        if (b >= nbuckets) break;
+        if (q == nq) {  // next block of buckets: threads 0..63 test one bucket each
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_b = atomicAdd(next_bucket, CLAIM);
+                s_n = 0;
+            }
+            __syncthreads();
+            const u32 base = s_b;
+            if (base >= nbuckets) break;
+            if (threadIdx.x < CLAIM && base + threadIdx.x < nbuckets) {
+                const u32 bb = base + threadIdx.x;
+                const u64 nr_ = re_[bb] - rs_[bb], ns_ = se_[bb] - ss_[bb];
+                // empty: nothing; heavy: the host takes the general path; without duplicate R keys:
+                // done by k_bucket_join_bitmap
+                if (nr_ && ns_ && nr_ <= big && ns_ <= big && (nr_ > (u64)min_r || dupflag[bb]))
+                    s_todo[atomicAdd(&s_n, 1u)] = bb;
+            }
+            __syncthreads();
+            q  = 0;
+            nq = s_n;
+            continue;
+        }
+        __syncthreads();  // the previous bucket is done with the table
+        const u32 b = s_todo[q++];
         const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
-        if (r0 == r1 || s0 == s1) continue;
-        if (r1 - r0 > big || s1 - s0 > big) continue;  // heavy: the host takes the general path
         // fast path as in k_bucket_join: the slot holds the (complemented) R item; a second R item
         // on a slot sends the bucket down the {count, sum A} path.  (Wiping only the used slots of a
         // sparse bucket instead of zeroing the table was measured: slower, 3.6 against 3.05 ms.)
@@ -818,11 +941,25 @@ static int bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u
 // key domain (lbits > 10), is left to the general sort + scan path.  d_state[1] is the bucket
 // counter (zero on entry).
 static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
-                       u64 *d_state, const u32 *d_list, u64 *acc) {
+                       u64 *d_state, u32 *d_list, u64 *acc) {
     const u32 nb2 = 512u * 512u;
     u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
-        // wide key domains (up to 2^31): one CTA per bucket, no cooperative heavy-hitter kernel
+        // wide key domains (up to 2^31): one CTA per bucket with a bitmap-tracked payload table;
+        // buckets with duplicate R keys are flagged (d_list doubles as the flags) and done by the
+        // general-table kernel afterwards; no cooperative heavy-hitter kernel.
+        const size_t bsmem = (size_t)(1u << lbits) * 4 + (size_t)(1u << lbits) / 8;
+        static int   gen_bm = -1;
+        if (gen_bm != ctx->generation) {
+            gen_bm = ctx->generation;
+            SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           48 * 1024));
+        }
+        const int bm_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / bsmem));
+        SMJ_CHECK(cudaMemsetAsync(d_list, 0, (size_t)nb2 * 4, ctx->stream));
+        SMJ_ITEMS(ctx, R.n + S.n);
+        SMJ_LAUNCH(ctx, k_bucket_join_bitmap, ctx->sm_count * bm_per_sm, 256, bsmem, R.items, R.starts, R.ends,
+                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, d_list, acc);
         const size_t smem = (size_t)(1u << lbits) * 12;
         static size_t smem_set_cta = 0;
         static int    gen_cta      = -1;
@@ -835,7 +972,7 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / smem));
         SMJ_ITEMS(ctx, R.n + S.n);
         SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, R.items, R.starts, R.ends,
-                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
+                   S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, 0xffffffffu, d_list, d_next + 1, acc);
         return 0;
     }
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
