@@ -39,7 +39,7 @@ def run(args, smj):
     # msd (default: the pass-A scatter kernel stores into the owners' buffers) | dma (copy engines)
     # | p2p (range partition fused with the exchange) | nccl (all-to-all).  Measured on B200
     # (128M x 128M): N=2 msd 3.27 ms, dma 3.26-3.46 ms; N=8 msd 2.00 ms, dma 2.28 ms.
-    # auto: dma when a rank sends at least 1 GB per step (config 5: 13.1 ms against 17.0 ms), else msd
+    # auto: dma when a rank sends at least 1 GB per step (config 5: 12.7 ms against 17.0 ms), else msd
     mode = os.environ.get("SMJ_EXCHANGE", "auto")
     if mode == "auto":
         mode = "dma" if 2 * count * 8 * (world - 1) / world >= 1e9 else "msd"
