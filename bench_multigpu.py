@@ -1,7 +1,9 @@
 """N-GPU leg of bench.py (launched by torchrun, one rank per GPU): the 128M x 128M m-way join with
-the relations spread evenly over the ranks, range-partition + NCCL all-to-all + local join +
-all-reduce per step (avx-sort-merge-joins_b200/distributed.py).  Strong scaling: the total work
-is the same at every N."""
+the relations spread evenly over the ranks.  A step = plan + first-level histograms (one small
+collective), the first MSD partitioning pass as the exchange (the scatter kernel stores into the
+bucket owners' buffers over NVLink, or copy engines move contiguous bucket ranges), second pass +
+bucket join per rank, all-reduce of {count, checksum} (avx-sort-merge-joins_b200/distributed.py).
+Strong scaling: the total work is the same at every N."""
 from __future__ import annotations
 
 import ctypes as C
@@ -35,10 +37,9 @@ def run(args, smj):
     s = eng.gen_unique(n, first, count, B.SEED_S)
     splitters = dj_mod.uniform_splitters(n, world)  # keys are a permutation of 1..n
 
-    # fused partition + exchange over peer memory (default); SMJ_EXCHANGE=nccl uses the all-to-all
-    # msd (default: the pass-A scatter kernel stores into the owners' buffers) | dma (copy engines)
-    # | p2p (range partition fused with the exchange) | nccl (all-to-all).  Measured on B200
-    # (128M x 128M): N=2 msd 3.27 ms, dma 3.26-3.46 ms; N=8 msd 2.00 ms, dma 2.28 ms.
+    # SMJ_EXCHANGE = msd (the pass-A scatter kernel stores into the owners' buffers) | dma (copy
+    # engines) | p2p (range partition fused with the exchange) | nccl (all-to-all).  Measured on
+    # B200 (128M x 128M): N=2 msd 3.11-3.17 ms, dma 3.28 ms; N=8 msd 1.91 ms, dma 2.50 ms.
     # auto: dma when a rank sends at least 1 GB per step (config 5: 12.7 ms against 17.0 ms), else msd
     mode = os.environ.get("SMJ_EXCHANGE", "auto")
     if mode == "auto":
@@ -80,7 +81,6 @@ def run(args, smj):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([lib.smjdev_launch_count() - launches0], dtype=torch.int64, device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    clocks = sampler.stop() if sampler else None
     ms_step = float(ms.item()) / args.steps
     # how much of a step is kernels of this library (rank 0, CUDA events around every launch)
     lib.smjdev_profile_begin()
@@ -98,6 +98,9 @@ def run(args, smj):
         e2e_steps, e2e_s = 0, float("nan")
     else:
         e2e_steps, e2e_s = _e2e(args, r, s, count, dev, one_step, sync_all, n)
+    # the sampler runs through the per-kernel pass and the end-to-end steps as well: the timed
+    # region alone (a few milliseconds) is shorter than nvidia-smi's sampling period
+    clocks = sampler.stop() if sampler else None
     line = _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kernel_ms, prof, clocks,
                  e2e_s, e2e_steps, launches, cnt, cks)
     if px is not None:
