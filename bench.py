@@ -247,10 +247,6 @@ def run_single_gpu(args, smj) -> dict:
                 "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
                             for k, v in prof.items()}}
 
-    # (the clock sampler keeps running through the per-kernel pass above: the timed region itself is
-    # a few milliseconds, shorter than nvidia-smi's sampling period)
-    clocks = sampler.stop()
-
     # ---- end to end through sortmergejoin_multiway() with pinned host relations
     hr, hs = lib.smjdev_host_alloc(n * 8), lib.smjdev_host_alloc(n * 8)
     assert hr and hs, "pinned host allocation failed"
@@ -309,6 +305,11 @@ def run_single_gpu(args, smj) -> dict:
         del r_pg, s_pg
     except Exception as exc:
         e2e["pageable_host_memory"] = {"value": None, "error": str(exc)}
+
+    # the clock sampler ran through the device-resident steps, the per-kernel pass and the
+    # end-to-end steps (the first timed region alone, a few milliseconds, is shorter than
+    # nvidia-smi's sampling period); it stops before the CPU baseline loads the host
+    clocks = sampler.stop()
 
     # ---- CPU baseline: the reference's own m-way join on this box's host cores
     cpu = None
