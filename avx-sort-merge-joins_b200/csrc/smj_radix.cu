@@ -525,6 +525,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // reservation does not fit does not store that bin's items at all and raises a flag, and the pass
 // (or the bucket) is repeated exactly, histogram first.  limit(b) = one past the last item index
 // bin b may use.
+// Per-bin offsets of a tile are (global start of the tile's slice) - (tile position of the bin): any
+// value in [-8192, 2^62).  A bin whose reservation did not fit is marked with SKIP64, which is not
+// such a value (an all-ones marker would collide with the legitimate offset -1).
+constexpr u64 SKIP64 = 1ull << 62;
+
 struct NoLimit {
     static constexpr bool on = false, keys = false;
     __device__ __forceinline__ u64 operator()(u32) const { return ~0ull; }
@@ -631,7 +636,7 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
             const u64 limit = LIM::on ? lim(b) : ~0ull;
             gbase[q]        = atomicAdd(&cursors[b], (u64)cntb[q]);
             if (LIM::on && gbase[q] + cntb[q] > limit) {  // does not fit: store nothing, raise the flag
-                gbase[q] = ~0ull;
+                gbase[q] = SKIP64;
                 lim.raise();
             }
         }
@@ -651,7 +656,7 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
         const u32 b = threadIdx.x * BPT + q;
         if (b < NB) {
             s_cnt[b]  = excl;  // tile position of the bin's first item
-            s_goff[b] = (LIM::on && gbase[q] == ~0ull) ? ~0ull : gbase[q] - (u64)excl;
+            s_goff[b] = (LIM::on && gbase[q] == SKIP64) ? SKIP64 : gbase[q] - (u64)excl;
         }
         excl += cntb[q];
     }
@@ -671,12 +676,12 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
 #pragma unroll 4
         for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
             const u64 x = s_items[i], g = s_goff[fn(x)];
-            if (!LIM::on || g != ~0ull) st_stream(out + g + i, x);
+            if (!LIM::on || g != SKIP64) st_stream(out + g + i, x);
         }
     } else {
         for (u32 i = threadIdx.x; i < valid; i += THREADS) {
             const u64 x = s_items[i], g = s_goff[fn(x)];
-            if (!LIM::on || g != ~0ull) st_stream(out + g + i, x);
+            if (!LIM::on || g != SKIP64) st_stream(out + g + i, x);
         }
     }
 }
