@@ -4,7 +4,7 @@
 directory: headline metrics per launch, warp-stall breakdown, and stall samples per block of SASS
 instructions (program order) so that the phases of a kernel can be told apart.
 
-    python profiles/summarize.py gpurun_out/prof.ncu-rep [instructions-per-bucket] > profiles/rNN_x.txt
+    python profiles/summarize.py gpurun_out/prof.ncu-rep [instructions-per-bucket [kernel-regex ...]] > profiles/rNN_x.txt
 """
 import csv
 import subprocess
@@ -46,9 +46,12 @@ def raw_page(rep):
         print("    warp stall samples:", ", ".join(f"{h} {100 * v / tot:.0f}%" for v, h in st[:8]))
 
 
-def source_page(rep, bucket):
+def source_page(rep, bucket, kernel=None):
+    """SASS stall samples of the first launch in the report, or of the first launch whose name
+    matches the regex `kernel`."""
     rows, hdr, nk = [], None, 0
-    for r in csv.reader(ncu(rep, "--page", "source", "--csv", "--print-source", "sass").splitlines()):
+    extra = ["--kernel-name", "regex:" + kernel, "--launch-count", "1"] if kernel else []
+    for r in csv.reader(ncu(rep, "--page", "source", "--csv", "--print-source", "sass", *extra).splitlines()):
         if r and r[0] == "Kernel Name":
             nk += 1
             if nk > 1:
@@ -90,4 +93,9 @@ def source_page(rep, bucket):
 if __name__ == "__main__":
     rep = sys.argv[1]
     raw_page(rep)
-    source_page(rep, int(sys.argv[2]) if len(sys.argv) > 2 else 60)
+    bucket = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+    if len(sys.argv) > 3:  # regexes of the kernels whose SASS pages are wanted
+        for k in sys.argv[3:]:
+            source_page(rep, bucket, k)
+    else:
+        source_page(rep, bucket)
