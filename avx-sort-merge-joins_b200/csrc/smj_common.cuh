@@ -122,6 +122,12 @@ __device__ __forceinline__ u32 lanemask_lt() {
 __device__ __forceinline__ u64 ld_stream(const u64 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(u64 *p, u64 v) { __stcs(p, v); }
 
+// pull one 128-byte line into L2 (no register, no dependency): used to fetch the tile a later CTA
+// will start with, so that its loads find L2 instead of DRAM
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
     u64 v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n,
                         const __grid_constant__ F fn,
                         u64 *cursors /* [NB], initialised to the start of every bin */,
-                        const __grid_constant__ LIM lim) {
+                        const __grid_constant__ LIM lim, u32 pf_dist) {
     constexpr int NB   = 1 << BITS;
     constexpr int TILE = THREADS * IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -719,6 +719,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
     if (tile < nfull) {
         u64 item[IPT];
         unstable_load<THREADS, IPT, true>(item, in + tile * TILE, (u32)TILE);
+        // one CTA per tile (the usual launch): the CTA that will take this CTA's slot next starts
+        // with tile + pf_dist; one line per thread covers its whole tile
+        if (pf_dist && tile + pf_dist < nfull && threadIdx.x * 16 < TILE)
+            prefetch_l2(in + (tile + pf_dist) * TILE + threadIdx.x * 16);
         while (true) {
             const u64  next = tile + gridDim.x;
             const u64 *nsrc = next < nfull ? in + next * TILE : nullptr;
@@ -753,8 +757,9 @@ int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64
     const unsigned grid = host_in ? (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB)
                                   : (unsigned)div_up(n, TILE);
     SMJ_ITEMS(ctx, n);
+    const u32 pf_dist = host_in ? 0u : (u32)(ctx->sm_count * MINB);  // resident CTAs = tiles in flight
     SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>), grid, THREADS, SMEM, in, out,
-               n, fn, bases, lim);
+               n, fn, bases, lim, pf_dist);
     return 0;
 }
 
@@ -1257,7 +1262,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
                    const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
                    u64 *cursors2 /* [512][512] */, const u64 *__restrict__ base2,
-                   const u64 *__restrict__ cap2, u32 *flag, int shrink) {
+                   const u64 *__restrict__ cap2, u32 *flag, int shrink, u32 pf_dist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = (u64 *)smem_raw;
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
@@ -1272,6 +1277,10 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     u64     item[MSD_IPT];
     MsdTile ti   = tiles[t];
     bool    have = false;  // item[] already holds tile t
+    if (pf_dist && t + pf_dist < ntiles) {  // the tile of the CTA that takes this slot next (see level 1)
+        const MsdTile pf = tiles[t + pf_dist];
+        if (threadIdx.x * 16 < pf.valid) prefetch_l2(in + pf.start + threadIdx.x * 16);
+    }
     while (true) {
         const u64 tn  = t + gridDim.x;
         MsdTile   nx  = ti;
@@ -1741,7 +1750,7 @@ static int msd_pass_b_common(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_coun
     SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<false>, grid2, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2,
-               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0);
+               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0, (u32)(ctx->sm_count * 2));
     return 0;
 }
 
@@ -1876,7 +1885,7 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
-               d_base2, d_cap2, d_bflag, shrink);
+               d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2));
     SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,
