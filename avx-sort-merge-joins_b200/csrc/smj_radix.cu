@@ -1268,14 +1268,16 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
     u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
     __shared__ u32 s_wsum[32];
-    const u64 ntiles = tile_prefix[MSD_NB];
+    // the tile entry is requested together with the tile count (the table has an entry, possibly
+    // unused, for every CTA of the grid): one dependent round trip to L2 less before the items
     u64       t      = blockIdx.x;
+    MsdTile   ti     = tiles[t];
+    const u64 ntiles = tile_prefix[MSD_NB];
     if (t >= ntiles) return;
     s_cnt[threadIdx.x] = 0;
     __syncthreads();
     using Lim = typename std::conditional<OPT, LimitSlots, NoLimit>::type;
     u64     item[MSD_IPT];
-    MsdTile ti   = tiles[t];
     bool    have = false;  // item[] already holds tile t
     if (pf_dist && t + pf_dist < ntiles) {  // the tile of the CTA that takes this slot next (see level 1)
         const MsdTile pf = tiles[t + pf_dist];
