@@ -16,6 +16,18 @@ received with the single-GPU pipeline and the counts / checksums are all-reduced
 The per-rank engine is pluggable so that the orchestration (splitters, count exchange, ragged
 all-to-all, reduction) can be tested on CPU with the gloo backend; the product engine is
 CudaEngine.
+
+Four exchanges, from the simplest to the ones bench.py uses:
+  step          range partition into send regions + NCCL all-to-all (the reference design)
+  step_p2p      range partition whose scatter kernel stores straight into the peers' receive
+                buffers (CUDA IPC over NVLink), then the single-GPU join on what arrived
+  step_msd      the m-way join's FIRST partitioning pass is the exchange: every item is stored
+                into the buffer of the GPU that owns its key bucket; the receiver only runs the
+                second pass and the bucket join (default for small relations)
+  step_msd_dma  the same first pass into a local bucket-major send buffer, contiguous bucket
+                ranges moved by the copy engines, second pass over the received segments
+                (default when a rank sends >= 1 GB per step)
+All of them return the same {count, checksum} as one GPU does.
 """
 from __future__ import annotations
 
