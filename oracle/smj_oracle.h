@@ -60,7 +60,10 @@ int orc_join_mway(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns
 /* the join result written out: reference src/joins/joincommon.c:256-278 (JOIN_MATERIALIZE) emits
  * <S.key, S.payload> for every matching pair; layout 1 emits R.payload << 32 | S.payload instead.
  * Sorts copies of r and s, then the literal loop.  out may be NULL (count only); at most cap items
- * are written, in the loop's order.  Returns the number of matching pairs. */
+ * are written, in the loop's order.  Returns the number of matching pairs.
+ * PARITY UNPINNED for the emitted tuples: the reference's JOIN_MATERIALIZE build does not compile
+ * (tuple_buffer.h is missing), so this loop is checked against numpy only; the COUNT it returns is
+ * pinned like every other join count. */
 uint64_t orc_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                               int layout, uint64_t *out, uint64_t cap);
 
