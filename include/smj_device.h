@@ -256,6 +256,17 @@ int smjdev_check_partition(const uint64_t *out, const uint64_t *offs, const uint
  * fk:     keys are uniformly drawn from 1..maxkey. */
 int smjdev_gen_unique(uint64_t *out, uint64_t n, uint64_t first, uint64_t count, uint64_t seed);
 int smjdev_gen_fk(uint64_t *out, uint64_t first, uint64_t count, uint32_t maxkey, uint64_t seed);
+/* zipf: src/datagen/genzipf.c:29-159 (create_relation_zipf, generator.c:517-534).  Keys are drawn from
+ * the alphabet 1..A with P(rank i) ~ i^-theta through the reference's cumulative table and binary
+ * search; the alphabet is the permutation smjdev_gen_unique(n = A, seed = alphabet_seed) produces
+ * (so rank i is the key of R's row i when R was generated with that seed); payload = row index.
+ * The reference draws from glibc's sequential rand(); here row i uses 31 bits of a counter-based
+ * hash of (seed, i) -- same distribution, rows independent.  smjdev_zipf_lut builds the cumulative
+ * table (A doubles; tmp = A/256 + A/65536 + 4 doubles of scratch) once for several calls;
+ * smjdev_gen_zipf(lut = NULL) builds and drops its own. */
+int smjdev_zipf_lut(double *lut, uint32_t A, double theta, double *tmp);
+int smjdev_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, double theta,
+                    uint64_t seed, uint64_t alphabet_seed, const double *lut);
 
 #ifdef __cplusplus
 }

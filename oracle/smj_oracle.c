@@ -528,3 +528,151 @@ void orc_gen_fk(uint64_t *out, uint64_t n, uint32_t maxkey, uint64_t seed) {
     for (uint64_t i = 0; i < n; i++)
         out[i] = ((mix64(i + (seed << 32)) % maxkey + 1) << 32) | (i & 0xffffffffull);
 }
+
+/* ------------------------------------------------------------------ Zipf generator -------- */
+/* (1) orc_gen_zipf_ref: src/datagen/genzipf.c:29-159 restated LITERALLY -- glibc rand() for the
+ *     alphabet shuffle (:43-51) and the draws (:121), libm pow() and one running double sum for the
+ *     cumulative table (:76-90), the binary search of :126-143.  Under the same srand() it must
+ *     reproduce the compiled reference's gen_zipf bit for bit (tests/test_oracle_vs_ref.py).
+ * (2) orc_zipf_weight / orc_zipf_lut / orc_gen_zipf: what the DEVICE generator computes
+ *     (csrc/smj_datagen.cu): the same table and search, but rows are independent (31 bits of a
+ *     counter-based hash instead of the sequential rand() stream, the Feistel permutation of
+ *     orc_gen_unique as alphabet) and the table is reproducible: i^-theta from IEEE add / mul / div /
+ *     fma only, summed in fixed blocks of 256 / 256 / rest.  The tests check (2) against (1): table
+ *     values to 1e-13, drawn key frequencies by a chi-square test. */
+#include <math.h>
+
+void orc_gen_zipf_ref(uint64_t *out, uint32_t n, uint32_t A, double theta, uint32_t *alphabet_out,
+                      double *lut_out) {
+    uint32_t *alphabet = (uint32_t *)malloc((size_t)A * sizeof(uint32_t));
+    double   *lut      = (double *)malloc((size_t)A * sizeof(double));
+    for (uint32_t i = 0; i < A; i++) alphabet[i] = i + 1;
+    for (uint32_t i = A - 1; i > 0; i--) {
+        uint32_t k   = (uint32_t)((unsigned long)i * rand() / RAND_MAX);
+        uint32_t tmp = alphabet[i];
+        alphabet[i]  = alphabet[k];
+        alphabet[k]  = tmp;
+    }
+    double scaling = 0.0, sum = 0.0;
+    for (uint32_t i = 1; i <= A; i++) scaling += 1.0 / pow(i, theta);
+    for (uint32_t i = 1; i <= A; i++) {
+        sum += 1.0 / pow(i, theta);
+        lut[i - 1] = sum / scaling;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        double   r = ((double)rand()) / RAND_MAX;
+        uint32_t left = 0, right = A - 1, pos;
+        if (lut[0] >= r)
+            pos = 0;
+        else {
+            while (right - left > 1) {
+                uint32_t m = (left + right) / 2;
+                if (lut[m] < r) left = m; else right = m;
+            }
+            pos = right;
+        }
+        /* the reference writes the key only (genzipf.c:147-150); the payload half is kept as it was */
+        out[i] = ((uint64_t)alphabet[pos] << 32) | (out[i] & 0xffffffffull);
+    }
+    if (alphabet_out) memcpy(alphabet_out, alphabet, (size_t)A * sizeof(uint32_t));
+    if (lut_out) memcpy(lut_out, lut, (size_t)A * sizeof(double));
+    free(lut);
+    free(alphabet);
+}
+
+/* i^-theta, reproducibly (every operation below is a correctly rounded IEEE operation; the file is
+ * compiled with -ffp-contract=off so that nothing else is fused) */
+double orc_zipf_weight(uint32_t i, double theta) {
+    const double x = (double)i;
+    uint64_t     bits;
+    memcpy(&bits, &x, 8);
+    int      e  = (int)((bits >> 52) & 0x7ff) - 1023;
+    uint64_t mb = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double   m;
+    memcpy(&m, &mb, 8);
+    if (m > 1.4142135623730951) {
+        m = m * 0.5;
+        e += 1;
+    }
+    const double z = (m + -1.0) / (m + 1.0), z2 = z * z;
+    double       p = 1.0 / 23.0;
+    for (int k = 21; k >= 1; k -= 2) p = fma(p, z2, 1.0 / (double)k);
+    const double ln_m = (2.0 * z) * p;
+    const double ln_i = fma((double)e, 0.6931471805599453, ln_m);
+    const double y    = -theta * ln_i;
+    const double kf   = rint(y * 1.4426950408889634);
+    double       r    = fma(-kf, 0.6931471803691238, y);
+    r                 = fma(-kf, 1.9082149292705877e-10, r);
+    static const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                        1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,     1.0 / 120.0,
+                                        1.0 / 24.0,        1.0 / 6.0,        0.5,             1.0,
+                                        1.0};
+    double q = 1.0 / 6227020800.0;
+    for (int k = 0; k < 13; k++) q = fma(q, r, inv_fact[k]);
+    const uint64_t pb = (uint64_t)((int)kf + 1023) << 52;
+    double         p2;
+    memcpy(&p2, &pb, 8);
+    return q * p2;
+}
+
+#define ORC_ZB 256
+void orc_zipf_lut(double *lut, uint32_t A, double theta) {
+    const uint32_t nblocks = (A + ORC_ZB - 1) / ORC_ZB, nsuper = (nblocks + ORC_ZB - 1) / ORC_ZB;
+    double *t1 = (double *)malloc((size_t)nblocks * 8), *t2 = (double *)malloc((size_t)(nsuper + 1) * 8);
+    for (uint32_t b = 0; b < nblocks; b++) {
+        double sum = 0.0;
+        for (uint64_t i = (uint64_t)b * ORC_ZB; i < A && i < (uint64_t)(b + 1) * ORC_ZB; i++) {
+            sum    = sum + orc_zipf_weight((uint32_t)i + 1u, theta);
+            lut[i] = sum;
+        }
+        t1[b] = sum;
+    }
+    for (uint32_t sb = 0; sb < nsuper; sb++) {
+        double sum = 0.0;
+        for (uint64_t b = (uint64_t)sb * ORC_ZB; b < nblocks && b < (uint64_t)(sb + 1) * ORC_ZB; b++) {
+            const double v = t1[b];
+            t1[b]          = sum;
+            sum            = sum + v;
+        }
+        t2[sb] = sum;
+    }
+    double total = 0.0;
+    for (uint32_t sb = 0; sb < nsuper; sb++) {
+        const double v = t2[sb];
+        t2[sb]         = total;
+        total          = total + v;
+    }
+    for (uint64_t i = 0; i < A; i++) {
+        const uint64_t b = i / ORC_ZB;
+        lut[i]           = ((t2[b / ORC_ZB] + t1[b]) + lut[i]) / total;
+    }
+    free(t1);
+    free(t2);
+}
+
+/* rows [first, first + count) of the device generator's Zipf relation (smjdev_gen_zipf) */
+void orc_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, double theta, uint64_t seed,
+                  uint64_t alphabet_seed, const double *lut_in) {
+    double *own = NULL;
+    if (!lut_in) {
+        own = (double *)malloc((size_t)A * 8);
+        orc_zipf_lut(own, A, theta);
+        lut_in = own;
+    }
+    for (uint64_t i = 0; i < count; i++) {
+        const uint64_t row = first + i;
+        const double   r   = (double)(mix64(row + (seed << 32)) >> 33) / 2147483647.0;
+        uint32_t       left = 0, right = A - 1, pos;
+        if (lut_in[0] >= r)
+            pos = 0;
+        else {
+            while (right - left > 1) {
+                uint32_t m = (uint32_t)(((uint64_t)left + right) / 2);
+                if (lut_in[m] < r) left = m; else right = m;
+            }
+            pos = right;
+        }
+        out[i] = ((permute(pos, A, alphabet_seed) + 1) << 32) | (row & 0xffffffffull);
+    }
+    free(own);
+}

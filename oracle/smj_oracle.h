@@ -70,6 +70,15 @@ uint64_t orc_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s,
 /* deterministic generators (the reference's are seeded from time(), generator.c:136-139) */
 void orc_gen_unique(uint64_t *out, uint64_t n, uint64_t seed);                  /* keys = perm of 1..n */
 void orc_gen_fk(uint64_t *out, uint64_t n, uint32_t maxkey, uint64_t seed);     /* keys in 1..maxkey  */
+/* Zipf: orc_gen_zipf_ref = src/datagen/genzipf.c:29-159 literally (glibc rand(), pow(); the caller
+ * seeds with srand(); alphabet_out / lut_out may be NULL); orc_zipf_* / orc_gen_zipf = the device
+ * generator's reproducible variant (smjdev_zipf_lut / smjdev_gen_zipf), bit for bit. */
+void orc_gen_zipf_ref(uint64_t *out, uint32_t n, uint32_t A, double theta, uint32_t *alphabet_out,
+                      double *lut_out);
+double orc_zipf_weight(uint32_t i, double theta);
+void orc_zipf_lut(double *lut, uint32_t A, double theta);
+void orc_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, double theta, uint64_t seed,
+                  uint64_t alphabet_seed, const double *lut);
 uint64_t orc_cks_a(uint64_t r);
 uint64_t orc_cks_b(uint64_t s);
 #endif

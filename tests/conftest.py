@@ -41,3 +41,12 @@ def ref():
     if r is None:
         pytest.skip("oracle/_ref/libsmj_ref.so not built (needs /root/reference: make -C oracle ref)")
     return r
+
+
+@pytest.fixture(scope="session")
+def refmat():
+    import oracle_lib
+    r = oracle_lib.reference_mat()
+    if r is None:
+        pytest.skip("oracle/_ref/libsmj_ref_mat.so not built (needs /root/reference: make -C oracle ref)")
+    return r

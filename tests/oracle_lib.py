@@ -89,6 +89,12 @@ class Oracle:
         L.orc_join_materialize.restype = C.c_uint64
         L.orc_gen_unique.argtypes = [_vp, C.c_uint64, C.c_uint64]
         L.orc_gen_fk.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_uint64]
+        L.orc_gen_zipf_ref.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double, _vp, _vp]
+        L.orc_zipf_weight.argtypes = [C.c_uint32, C.c_double]
+        L.orc_zipf_weight.restype = C.c_double
+        L.orc_zipf_lut.argtypes = [_vp, C.c_uint32, C.c_double]
+        L.orc_gen_zipf.argtypes = [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_uint64,
+                                   C.c_uint64, _vp]
 
     # sort
     def sort(self, items: np.ndarray) -> np.ndarray:
@@ -181,6 +187,28 @@ class Oracle:
         self.lib.orc_gen_fk(_p(out), n, maxkey, seed)
         return out
 
+    def gen_zipf_ref(self, n: int, alphabet: int, theta: float, srand_seed: int):
+        """genzipf.c:98-159 literally, under srand(srand_seed).  Returns (items with payload = row
+        index, alphabet, lut)."""
+        out = np.arange(n, dtype=np.uint64)
+        alpha = np.empty(alphabet, dtype=np.uint32)
+        lut = np.empty(alphabet, dtype=np.float64)
+        C.CDLL(None).srand(srand_seed)
+        self.lib.orc_gen_zipf_ref(_p(out), n, alphabet, theta, _p(alpha), _p(lut))
+        return out, alpha, lut
+
+    def zipf_lut(self, alphabet: int, theta: float) -> np.ndarray:
+        lut = np.empty(alphabet, dtype=np.float64)
+        self.lib.orc_zipf_lut(_p(lut), alphabet, theta)
+        return lut
+
+    def gen_zipf(self, n: int, alphabet: int, theta: float, seed: int, alphabet_seed: int,
+                 first: int = 0) -> np.ndarray:
+        """what smjdev_gen_zipf generates (rows first .. first + n)"""
+        out = np.empty(n, dtype=np.uint64)
+        self.lib.orc_gen_zipf(_p(out), first, n, alphabet, theta, seed, alphabet_seed, None)
+        return out
+
 
 # --------------------------------------------------------------------------------- reference
 class _Rel(C.Structure):
@@ -256,6 +284,19 @@ class Reference:
         with silence_stdout():
             self.f["cpu_mapping_init"]()
 
+    def gen_zipf(self, n: int, alphabet: int, theta: float, srand_seed: int) -> np.ndarray:
+        """the compiled reference's gen_zipf (src/datagen/genzipf.c:98-159) under srand(srand_seed);
+        payload = row index (the reference writes keys only)"""
+        fn = self.lib._Z8gen_zipfjjdPP7tuple_t
+        fn.argtypes = [C.c_uint, C.c_uint, C.c_double, C.POINTER(_vp)]
+        fn.restype = _vp
+        out = np.arange(n, dtype=np.uint64)
+        po = _vp(out.ctypes.data)
+        C.CDLL(None).srand(srand_seed)
+        fn(n, alphabet, theta, C.byref(po))
+        assert po.value == out.ctypes.data
+        return out
+
     def sort(self, items: np.ndarray, which: str = "avxsort_tuples"):
         """returns (sorted array, placement) ; placement 1 = result in the output buffer"""
         n = items.size
@@ -319,21 +360,133 @@ class Reference:
 
     def join(self, r: np.ndarray, s: np.ndarray, which: str = "sortmergejoin_multiway",
              nthreads: int = 2, fanout: int = 128, mwaybuf: int = 1 << 22) -> int:
-        pad = nthreads * fanout * 8 + 64  # RELATION_PADDING, src/params.h:55-57, src/main.c:517-519
+        return self.join_timed(self.join_prepare(r, s, nthreads, fanout), which, nthreads, fanout, mwaybuf)[0]
+
+    @staticmethod
+    def join_prepare(r: np.ndarray, s: np.ndarray, nthreads: int, fanout: int):
+        """Copies both relations ONCE into 64-byte aligned buffers with the slack the reference's
+        main.c gives them (RELATION_PADDING, src/params.h:55-57, src/main.c:517-519).  The joins leave
+        their inputs unmodified, so the pair can be joined any number of times."""
+        pad = nthreads * fanout * 8 + 64
         rr, ss = aligned_u64(r.size + pad), aligned_u64(s.size + pad)
         rr[:r.size], ss[:s.size] = r, s
-        relr, rels = _Rel(rr.ctypes.data, r.size), _Rel(ss.ctypes.data, s.size)
+        return rr, ss, r.size, s.size
+
+    def join_timed(self, prepared, which: str = "sortmergejoin_multiway", nthreads: int = 2,
+                   fanout: int = 128, mwaybuf: int = 1 << 22):
+        """One join of a prepared pair.  Returns (totalresults, wall seconds around the bare call,
+        seconds of the reference's OWN timed region or None): the reference starts its clock inside
+        the threads behind the first barrier and prints TOTAL-TIME-USECS on stderr
+        (src/joins/sortmergejoin_multiway.c:145-153, 310-314; src/joins/joincommon.c:195, 214-227);
+        allocation of its temporaries is outside that region."""
+        import re
+        import tempfile
+        import time
+        rr, ss, nr, ns = prepared
+        relr, rels = _Rel(rr.ctypes.data, nr), _Rel(ss.ctypes.data, ns)
+        cfg = _Cfg(nthreads, fanout, 0, 0, mwaybuf, 2)
+        self.f["numa_shuffle_init"](2, nthreads)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        saved = (os.dup(1), os.dup(2))
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        with tempfile.TemporaryFile() as errf:
+            os.dup2(devnull, 1)
+            os.dup2(errf.fileno(), 2)
+            try:
+                t0 = time.perf_counter()
+                res = self.f[which](C.byref(relr), C.byref(rels), C.byref(cfg))
+                wall = time.perf_counter() - t0
+            finally:
+                C.CDLL(None).fflush(None)
+                os.dup2(saved[0], 1)
+                os.dup2(saved[1], 2)
+                os.close(saved[0])
+                os.close(saved[1])
+                os.close(devnull)
+            errf.seek(0)
+            txt = errf.read().decode(errors="replace")
+        m = re.search(r"TOTAL-TIME-USECS = ([0-9.]+)", txt)
+        region = float(m.group(1)) * 1e-6 if m else None
+        if not res:
+            return -1, wall, region
+        return res.contents.totalresults, wall, region
+
+
+class _ThreadRes(C.Structure):
+    _fields_ = [("nresults", C.c_int64), ("results", _vp), ("threadid", C.c_uint32)]
+
+
+REF_MAT_SO = os.path.join(ORACLE_DIR, "_ref", "libsmj_ref_mat.so")
+
+
+class ReferenceMat:
+    """The UNMODIFIED reference compiled with -DJOIN_MATERIALIZE (oracle/Makefile `ref`), with
+    oracle/shim/tuple_buffer.h standing in for the header its tree lacks: the joins then emit
+    <S.key, S.payload> per matching pair into per-thread chained buffers
+    (src/joins/joincommon.c:256-278, sortmergejoin_multiway.c:559-599)."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_MAT_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_MAT_SO)
+        self.f = {k: getattr(L, Reference.SYMS[k]) for k in
+                  ("sortmergejoin_multiway", "sortmergejoin_multipass", "numa_shuffle_init",
+                   "cpu_mapping_init", "merge_join")}
+        for k in ("sortmergejoin_multiway", "sortmergejoin_multipass"):
+            self.f[k].argtypes = [C.POINTER(_Rel), C.POINTER(_Rel), C.POINTER(_Cfg)]
+            self.f[k].restype = _vp
+        self.f["merge_join"].argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, _vp]
+        self.f["merge_join"].restype = C.c_uint64
+        self.f["numa_shuffle_init"].argtypes = [C.c_int, C.c_int]
+        L.orc_shim_cb_count.argtypes = [_vp]
+        L.orc_shim_cb_count.restype = C.c_uint64
+        L.orc_shim_cb_copy.argtypes = [_vp, _vp, C.c_uint64]
+        L.orc_shim_cb_copy.restype = C.c_uint64
+        L.orc_shim_cb_free.argtypes = [_vp]
+        with silence_stdout():
+            self.f["cpu_mapping_init"]()
+
+    def join_materialize(self, r: np.ndarray, s: np.ndarray, which: str = "sortmergejoin_multiway",
+                         nthreads: int = 2, fanout: int = 128, mwaybuf: int = 1 << 22):
+        """returns (totalresults, [emitted items of thread 0, thread 1, ...]) in emission order"""
+        rr, ss, nr, ns = Reference.join_prepare(r, s, nthreads, fanout)
+        relr, rels = _Rel(rr.ctypes.data, nr), _Rel(ss.ctypes.data, ns)
         cfg = _Cfg(nthreads, fanout, 0, 0, mwaybuf, 2)
         with silence_all():
             self.f["numa_shuffle_init"](2, nthreads)
             res = self.f[which](C.byref(relr), C.byref(rels), C.byref(cfg))
-        if not res:
-            return -1
-        return res.contents.totalresults
+        assert res
+        resv = _Res.from_address(res)
+        lst = (_ThreadRes * nthreads).from_address(resv.resultlist)
+        outs = []
+        for t in range(nthreads):
+            k = self.lib.orc_shim_cb_count(lst[t].results)
+            assert k == lst[t].nresults
+            out = np.empty(k, dtype=np.uint64)
+            assert self.lib.orc_shim_cb_copy(lst[t].results, out.ctypes.data, k) == k
+            self.lib.orc_shim_cb_free(lst[t].results)
+            outs.append(out)
+        libc = C.CDLL(None)
+        libc.free.argtypes = [_vp]
+        libc.free(resv.resultlist)
+        total = resv.totalresults
+        libc.free(res)
+        return total, outs
 
 
 _ORACLE = None
 _REF = None
+_REF_MAT = None
+
+
+def reference_mat() -> "ReferenceMat | None":
+    global _REF_MAT
+    if _REF_MAT is None and ReferenceMat.available():
+        _REF_MAT = ReferenceMat()
+    return _REF_MAT
 
 
 def oracle() -> Oracle:

@@ -8,6 +8,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_r2.npz"))
 
 
 def test_sort_golden_gpu(smj):
@@ -65,3 +66,24 @@ def test_join_golden_gpu(smj):
     for algo, nthreads in (("multiway", 2), ("multiway", 4), ("multipass", 4), ("mpsm", 4)):
         assert smj.join_host(algo, R, S, nthreads=nthreads)[0] == int(G["join_RS_mway_2"])
         assert smj.join_host(algo, D1, D2, nthreads=nthreads)[0] == int(G["join_DD_mway_2"])
+
+
+def test_materialize_golden_gpu(smj):
+    """sortmergejoin_multiway_materialize (host buffers, the reference's JOIN_MATERIALIZE contract)
+    against the tuples the compiled reference emitted (tests/golden/make_golden_r2.py)."""
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for name in G2["mat_names"]:
+        r, s = G2[f"mat_{name}_r"].copy(), G2[f"mat_{name}_s"].copy()
+        exp = G2[f"mat_{name}_sorted"]
+        cfg = smj.joinconfig_t(4, 128, 0, 0, 20 * 1024 * 1024, smj.NUMA_NEXT)
+        res = smj.lib.sortmergejoin_multiway_materialize(C.byref(smj.rel(r)), C.byref(smj.rel(s)), C.byref(cfg))
+        assert res and res.contents.totalresults == exp.size, name
+        tr = res.contents.resultlist[0]
+        got = (np.ctypeslib.as_array(C.cast(tr.results, C.POINTER(C.c_uint64)), shape=(exp.size,)).copy()
+               if exp.size else np.zeros(0, dtype=np.uint64))
+        assert np.array_equal(np.sort(got), exp), name
+        if tr.results:
+            libc.free(C.cast(tr.results, C.c_void_p))
+        libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+        libc.free(C.cast(res, C.c_void_p))

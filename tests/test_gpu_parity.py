@@ -336,6 +336,44 @@ def test_generators_match_oracle(smj, orc):
         d.free()
 
 
+@pytest.mark.parametrize("alphabet,theta", [(1, 0.9), (1000, 0.5), (100003, 1.0), (65536, 0.75), (300, 1.05),
+                                            (70001, 0.0), (1 << 20, 0.6)])
+def test_gen_zipf_matches_oracle(smj, orc, alphabet, theta):
+    """smjdev_zipf_lut / smjdev_gen_zipf (genzipf.c:29-159 on the device) bit for bit against the
+    oracle's restatement: cumulative table, drawn keys, row ranges, shared table."""
+    n = 200_003
+    lut = smj.DeviceBuffer(alphabet)
+    tmp = smj.DeviceBuffer(alphabet // 256 + alphabet // 65536 + 8)
+    smj.check(smj.lib.smjdev_zipf_lut(lut.ptr, alphabet, theta, tmp.ptr))
+    got_lut = lut.to_host(dtype=np.float64)
+    assert np.array_equal(got_lut.view(np.uint64), orc.zipf_lut(alphabet, theta).view(np.uint64))
+    d = smj.DeviceBuffer(n)
+    smj.check(smj.lib.smjdev_gen_zipf(d.ptr, 0, n, alphabet, theta, 54321, 12345, None))
+    exp = orc.gen_zipf(n, alphabet, theta, 54321, 12345)
+    assert np.array_equal(d.to_host(), exp)
+    # a row range with a prepared table gives the same rows
+    smj.check(smj.lib.smjdev_gen_zipf(d.ptr, 1000, 5000, alphabet, theta, 54321, 12345, lut.ptr))
+    assert np.array_equal(d.to_host(5000), exp[1000:6000])
+    keys = exp >> np.uint64(32)
+    assert keys.min() >= 1 and keys.max() <= alphabet
+    for b in (lut, tmp, d):
+        b.free()
+
+
+def test_gen_zipf_joins_like_the_reference_workload(smj, orc):
+    """config 4 in small: R = permutation of 1..A, S = Zipf over R's keys: every S tuple finds its
+    partner (count = |S|), checksum as the oracle's."""
+    a, n = 1 << 20, (1 << 21) + 11
+    dr, ds = smj.DeviceBuffer(a), smj.DeviceBuffer(n)
+    smj.check(smj.lib.smjdev_gen_unique(dr.ptr, a, 0, a, 12345))
+    smj.check(smj.lib.smjdev_gen_zipf(ds.ptr, 0, n, a, 0.9, 54321, 777, None))
+    st = smj.device_join(smj.ALGO_MWAY, dr, ds)
+    exp = orc.join_bruteforce(orc.gen_unique(a, 12345), orc.gen_zipf(n, a, 0.9, 54321, 777))
+    assert (st.matches, st.checksum) == exp and st.matches == n
+    dr.free()
+    ds.free()
+
+
 def test_range_partition(smj, orc):
     rng = np.random.default_rng(4)
     n = 300007

