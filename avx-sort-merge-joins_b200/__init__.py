@@ -139,6 +139,7 @@ SIGNATURES = {
                                          _u64p]),
     "smjdev_gen_unique": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "smjdev_gen_fk": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]),
+    "smjdev_gen_fk_from": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.c_uint64]),
     "smjdev_zipf_lut": (C.c_int, [_vp, C.c_uint32, C.c_double, _vp]),
     "smjdev_gen_zipf": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_uint64, C.c_uint64,
                                   _vp]),

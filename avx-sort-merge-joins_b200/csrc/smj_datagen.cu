@@ -22,6 +22,8 @@ __host__ __device__ __forceinline__ u64 mix64(u64 z) {
     return z ^ (z >> 31);
 }
 
+__device__ __forceinline__ u64 permute_row(u64 x, u64 n, u64 seed, int half);
+
 __global__ void __launch_bounds__(256) k_gen_unique(u64 *__restrict__ out, u64 n, u64 first, u64 count,
                                                     u64 seed, int half) {
     const u64 mask   = (1ull << half) - 1;
@@ -48,8 +50,21 @@ __global__ void __launch_bounds__(256) k_gen_fk(u64 *__restrict__ out, u64 first
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const u64 row = first + i;
-        out[i]        = ((mix64(row + (seed << 32)) % maxkey + 1) << 32) | (row & 0xffffffffull);
+        u64       x   = ((mix64(row + (seed << 32)) % maxkey + 1) << 32) | (row & 0xffffffffull);
+        // keys with bits 20..30 all set read as NaN when the word is a double: the reference's
+        // generators clear key bit 20 of those (avoid_NaN, generator.c:107-121)
+        if ((x & (0x7FFull << 52)) == (0x7FFull << 52)) x &= ~(1ull << 52);
+        out[i] = x;
     }
+}
+
+// S = the rows of R repeated |S| / |R| times (+ remainder) and shuffled (create_relation_fk_from_pk,
+// generator.c:458-488): row i of S is R's row pi(i) mod |R|, pi a pseudo-random permutation of [0, |S|)
+__global__ void __launch_bounds__(256) k_gen_fk_from(u64 *__restrict__ out, u64 n, u64 first, u64 count,
+                                                     const u64 *__restrict__ src, u64 src_n, u64 seed, int half) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        out[i] = src[permute_row(first + i, n, seed, half) % src_n];
 }
 
 // Feistel permutation of [0, n) shared by k_gen_unique and the Zipf alphabet
@@ -234,6 +249,21 @@ extern "C" int smjdev_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, ui
     while ((1ull << bits) < (u64)A) bits++;
     const unsigned grid = (unsigned)std::min<u64>(div_up(count, 256), (u64)ctx->sm_count * 32);
     SMJ_LAUNCH(ctx, k_gen_zipf, grid, 256, 0, (u64 *)out, first, count, lut, A, seed, alphabet_seed,
+               (bits + 1) / 2);
+    return 0;
+}
+
+// rows [first, first + count) of an n-row relation whose rows are rows of src (device, src_n items)
+extern "C" int smjdev_gen_fk_from(uint64_t *out, uint64_t n, uint64_t first, uint64_t count, const uint64_t *src,
+                                  uint64_t src_n, uint64_t seed) {
+    SmjCtx *ctx = smj_ctx();
+    if (!ctx) return -1;
+    if (count == 0) return 0;
+    if (src_n == 0 || first + count > n) return smj_fail_msg("smjdev_gen_fk_from: bad arguments");
+    int bits = 2;
+    while ((1ull << bits) < n) bits++;
+    const unsigned grid = (unsigned)std::min<u64>(div_up(count, 256), (u64)ctx->sm_count * 32);
+    SMJ_LAUNCH(ctx, k_gen_fk_from, grid, 256, 0, (u64 *)out, n, first, count, (const u64 *)src, src_n, seed,
                (bits + 1) / 2);
     return 0;
 }

@@ -31,7 +31,7 @@ def run(args, smj):
     dj = dj_mod.DistributedJoin(eng, rank, world)
     lib = smj.lib
 
-    n = args.size
+    n = args.size or (2_000_000_000 if args.config == 5 else B.N1)
     first, count = (n * rank) // world, (n * (rank + 1)) // world - (n * rank) // world
     r = eng.gen_unique(n, first, count, B.SEED_R)
     s = eng.gen_unique(n, first, count, B.SEED_S)
@@ -136,13 +136,11 @@ def _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kern
         peak, peak_src = B.measured_peak()
         link_gbs = sent / (ms_step * 1e-3) / 1e9  # exchange bytes leaving this GPU / whole step
         line = {
-            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": B.METRICS[5 if n == 2_000_000_000 else 1][0], "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"sortmergejoins -a m-way, |R|=|S|={n} 8-byte tuples, uniform unique keys "
-                                   + ("(BASELINE.json configs[0])" if n == 128_000_000 else
-                                      "(BASELINE.json configs[4], scale-out)" if n == 2_000_000_000 else "")
-                                   + f", relations spread evenly over {world} GPUs",
+            "config": {"workload": B.workload(5 if n == 2_000_000_000 else 1, n),
+                       "distribution": f"relations spread evenly over {world} GPUs",
                        "parallelism": (f"first MSD partitioning pass into a bucket-major send buffer, contiguous bucket "
                                        f"ranges copied to their owners over NVLink by the copy engines (overlapping "
                                        f"the scatter of the other relation) over {world} GPUs" if mode == "dma" else

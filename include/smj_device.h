@@ -253,9 +253,15 @@ int smjdev_check_partition(const uint64_t *out, const uint64_t *offs, const uint
  * and :458-488 for the benchmark workloads; the reference's own are seeded from time()).
  * Rows [first, first+count) of the relation are written to out[0..count); payload = row index.
  * unique: keys are a pseudo-random permutation of 1..n (Feistel network + cycle walking).
- * fk:     keys are uniformly drawn from 1..maxkey. */
+ * fk:     keys are uniformly drawn from 1..maxkey; a key with bits 20..30 all set (a NaN when the
+ *         word is read as a double) gets bit 20 cleared like generator.c:107-121 avoid_NaN does. */
 int smjdev_gen_unique(uint64_t *out, uint64_t n, uint64_t first, uint64_t count, uint64_t seed);
 int smjdev_gen_fk(uint64_t *out, uint64_t first, uint64_t count, uint32_t maxkey, uint64_t seed);
+/* fk_from: rows [first, first + count) of an n-row relation made of the rows of src (device array of
+ * src_n items) repeated n / src_n times (+ remainder) and shuffled: create_relation_fk_from_pk,
+ * src/datagen/generator.c:458-488 (what `--full-range` gives S).  Row i = src[pi(i) mod src_n]. */
+int smjdev_gen_fk_from(uint64_t *out, uint64_t n, uint64_t first, uint64_t count, const uint64_t *src,
+                       uint64_t src_n, uint64_t seed);
 /* zipf: src/datagen/genzipf.c:29-159 (create_relation_zipf, generator.c:517-534).  Keys are drawn from
  * the alphabet 1..A with P(rank i) ~ i^-theta through the reference's cumulative table and binary
  * search; the alphabet is the permutation smjdev_gen_unique(n = A, seed = alphabet_seed) produces

@@ -525,8 +525,15 @@ void orc_gen_unique(uint64_t *out, uint64_t n, uint64_t seed) {
 }
 /* replaces src/datagen/generator.c:458-488 (foreign keys uniformly drawn from 1..maxkey) */
 void orc_gen_fk(uint64_t *out, uint64_t n, uint32_t maxkey, uint64_t seed) {
-    for (uint64_t i = 0; i < n; i++)
-        out[i] = ((mix64(i + (seed << 32)) % maxkey + 1) << 32) | (i & 0xffffffffull);
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t x = ((mix64(i + (seed << 32)) % maxkey + 1) << 32) | (i & 0xffffffffull);
+        if ((x & (0x7FFull << 52)) == (0x7FFull << 52)) x &= ~(1ull << 52); /* generator.c:107-121 avoid_NaN */
+        out[i] = x;
+    }
+}
+/* replaces src/datagen/generator.c:458-488 create_relation_fk_from_pk: the rows of src repeated and shuffled */
+void orc_gen_fk_from(uint64_t *out, uint64_t n, const uint64_t *src, uint64_t src_n, uint64_t seed) {
+    for (uint64_t i = 0; i < n; i++) out[i] = src[permute(i, n, seed) % src_n];
 }
 
 /* ------------------------------------------------------------------ Zipf generator -------- */

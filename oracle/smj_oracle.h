@@ -79,6 +79,7 @@ double orc_zipf_weight(uint32_t i, double theta);
 void orc_zipf_lut(double *lut, uint32_t A, double theta);
 void orc_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, double theta, uint64_t seed,
                   uint64_t alphabet_seed, const double *lut);
+void orc_gen_fk_from(uint64_t *out, uint64_t n, const uint64_t *src, uint64_t src_n, uint64_t seed);
 uint64_t orc_cks_a(uint64_t r);
 uint64_t orc_cks_b(uint64_t s);
 #endif

@@ -89,6 +89,7 @@ class Oracle:
         L.orc_join_materialize.restype = C.c_uint64
         L.orc_gen_unique.argtypes = [_vp, C.c_uint64, C.c_uint64]
         L.orc_gen_fk.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_uint64]
+        L.orc_gen_fk_from.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64]
         L.orc_gen_zipf_ref.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double, _vp, _vp]
         L.orc_zipf_weight.argtypes = [C.c_uint32, C.c_double]
         L.orc_zipf_weight.restype = C.c_double
@@ -185,6 +186,12 @@ class Oracle:
     def gen_fk(self, n: int, maxkey: int, seed: int) -> np.ndarray:
         out = np.empty(n, dtype=np.uint64)
         self.lib.orc_gen_fk(_p(out), n, maxkey, seed)
+        return out
+
+    def gen_fk_from(self, n: int, src: np.ndarray, seed: int) -> np.ndarray:
+        src = np.ascontiguousarray(src, dtype=np.uint64)
+        out = np.empty(n, dtype=np.uint64)
+        self.lib.orc_gen_fk_from(_p(out), n, _p(src), src.size, seed)
         return out
 
     def gen_zipf_ref(self, n: int, alphabet: int, theta: float, srand_seed: int):

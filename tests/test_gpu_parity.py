@@ -711,8 +711,7 @@ def test_pageable_relations_use_the_staging_pipeline(smj, orc):
     assert np.array_equal(res, np.sort(s))
 
 
-def test_reference_style_cli(smj):
-    """The sortmergejoins command line driver (src/main.c) on top of the library."""
+def _cli(smj):
     import os
     import subprocess
     exe = os.path.join(os.path.dirname(smj.LIB_PATH), "sortmergejoins")
@@ -720,6 +719,14 @@ def test_reference_style_cli(smj):
         subprocess.run(["make", "-C", os.path.dirname(smj.LIB_PATH), exe], check=True, capture_output=True)
     env = dict(os.environ)
     env.pop("SMJ_QUIET", None)
+    return exe, env
+
+
+def test_reference_style_cli(smj):
+    """The sortmergejoins command line driver (src/main.c) on top of the library: short options,
+    the reference's long options (src/main.c:716-745) and its data set switches."""
+    import subprocess
+    exe, env = _cli(smj)
     for algo, extra in (("m-way", []), ("m-pass", ["-n", "4"]), ("mpsm", ["-n", "4"]), ("m-way", ["-d"]),
                         ("m-way", ["-s", "3000000"])):
         out = subprocess.run([exe, "-a", algo, "-r", "1000000", "-s", "1000000"] + extra, capture_output=True,
@@ -728,5 +735,147 @@ def test_reference_style_cli(smj):
         n_s = 3000000 if "-s" in extra else 1000000
         assert f"Results = {n_s}. DONE." in out.stdout, out.stdout
         assert "TUPLES-PER-SECOND" in out.stderr  # the reference's timing line, src/joins/joincommon.c:214-227
+    # the call the reference's scripts make (scripts/tput-scalability.sh:32,53)
+    for extra, expect in ((["--scalarmerge", "--scalarsort"], 1500000),
+                          (["--skew=0.9", "--s-size=4000000"], 4000000),          # every Zipf key is a key of R
+                          (["--partfanout=256", "--numastrategy=RING", "--mwaybufsize=1048576", "--verbose"], 1500000),
+                          (["--device-resident", "--r-seed=7", "--s-seed=8", "--no-numa-localize"], 1500000)):
+        out = subprocess.run([exe, "--algo=m-way", "--nthreads=4", "--r-size=1500000", "--s-size=1500000"] + extra,
+                             capture_output=True, text=True, env=env, timeout=300)
+        assert out.returncode == 0 and f"Results = {expect}. DONE." in out.stdout, out.stdout + out.stderr
+    # --non-unique / --full-range: the result is whatever the key multisets give; it must be the
+    # same from all three algorithms (and --full-range S holds R's rows, so every S tuple matches)
+    for flag in ("--non-unique", "--full-range"):
+        res = set()
+        for algo in ("m-way", "m-pass", "mpsm"):
+            out = subprocess.run([exe, f"--algo={algo}", "--nthreads=2", "--r-size=1200000", "--s-size=2500000", flag],
+                                 capture_output=True, text=True, env=env, timeout=300)
+            assert out.returncode == 0, out.stdout + out.stderr
+            res.add([ln for ln in out.stdout.splitlines() if "Results =" in ln][0])
+        assert len(res) == 1, res
+        if flag == "--full-range":
+            assert int(res.pop().split("=")[1].split(".")[0]) >= 2500000
     bad = subprocess.run([exe, "-n", "3", "-r", "1000", "-s", "1000"], capture_output=True, text=True, env=env)
-    assert "power of 2" in bad.stdout and bad.returncode != 0
+    assert "power of 2" in bad.stdout and "Results" not in bad.stdout  # src/joins/sortmergejoin_multiway.c:54-57
+    bad = subprocess.run([exe, "--partfanout=100"], capture_output=True, text=True, env=env)
+    assert "must be a power of 2" in bad.stdout
+    bad = subprocess.run([exe, "--nthreads=256", "--partfanout=128"], capture_output=True, text=True, env=env)
+    assert "must be >= num-threads" in bad.stdout
+    bad = subprocess.run([exe, "--algo=nope"], capture_output=True, text=True, env=env)
+    assert "does not exist" in bad.stdout
+
+
+def test_experiment_script_runs_unmodified_options(smj, tmp_path):
+    """scripts/tput-scalability.sh (the reference's sweep: --algo= --nthreads= --r-size= --s-size=
+    [--scalarmerge --scalarsort], stderr scraped into the results table) against this build."""
+    import os
+    import subprocess
+    exe, env = _cli(smj)
+    root = os.path.dirname(os.path.dirname(smj.LIB_PATH))
+    env.update(BIN=exe, RESULTS=str(tmp_path), NTUPLES="1000000", THREADS="4 1", REPS="1", OUTPUTFILE="tput-test")
+    out = subprocess.run(["bash", os.path.join(root, "scripts", "tput-scalability.sh")], env=env, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [ln.split() for ln in open(tmp_path / "tput-test.txt") if ln and ln[0] not in "#="]
+    rows = [r for r in rows if r]
+    assert len(rows) == 3 * 2 * 2  # algorithms x thread counts x {avx, scalar}
+    for r in rows:
+        # <algo> <nthreads> <rep> five stage times, then NUM-TUPLES = n TOTAL-TIME-USECS = t TUPLES-PER-SECOND = x
+        assert r[0].split("-scalar")[0] in ("m-pass", "m-way", "mpsm") and r[1] in ("4", "1"), r
+        assert "NUM-TUPLES" in r and r[r.index("NUM-TUPLES") + 2] == "1000000", r
+        assert float(r[r.index("TUPLES-PER-SECOND") + 2]) > 0
+    log = open(tmp_path / "tput-test.log").read()
+    assert log.count("Results = 1000000. DONE.") == 12
+
+
+def test_dropin_reference_main(smj):
+    """The reference's OWN driver (src/main.c, compiled unmodified by `make -C oracle dropin` with its
+    generators and cpu mapping) linked against libsmj_b200.so: its joins run on the GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(smj.LIB_PATH))
+    exe = os.path.join(root, "oracle", "_ref", "sortmergejoins_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sortmergejoins_dropin not built (needs /root/reference: make -C oracle dropin)")
+    env = dict(os.environ)
+    env.pop("SMJ_QUIET", None)
+    for args, expect in ((["--algo=m-way", "--nthreads=4", "--r-size=2000000", "--s-size=2000000"], 2000000),
+                         (["--algo=m-pass", "--nthreads=2", "--r-size=1000000", "--s-size=3000000"], 3000000),
+                         (["--algo=mpsm", "--nthreads=2", "--r-size=1000000", "--s-size=1000000"], 1000000),
+                         (["--algo=m-way", "--nthreads=2", "--r-size=1000000", "--s-size=2000000", "--skew=0.8"], 2000000)):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=600, cwd=root)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert f"Results = {expect}. DONE." in out.stdout, out.stdout[-2000:]
+        assert "TOTAL-TIME-USECS" in out.stderr
+
+
+def test_remaining_exports(smj, orc, capfd):
+    """Entry points no other test calls: sortmergejoin_initrun (joincommon.h:59-61), the _modulo /
+    _bitand twins of the scalar multiway merge (scalar_multiwaymerge.h:47-78), avxsortmultiway_int64,
+    scalarsort_int64, avx_merge_int64 / scalar_merge_int64, print_timing, is_sorted_helper, check_sorted."""
+    rng = np.random.default_rng(77)
+    r, s = orc.gen_unique(300_000, 3), orc.gen_fk(700_001, 300_000, 4)
+    cfg = smj.joinconfig_t(4, 128, 1, 1, 1 << 20, smj.NUMA_RING)  # SCALARSORT / SCALARMERGE set: same result
+    res = smj.lib.sortmergejoin_initrun(C.byref(smj.rel(r)), C.byref(smj.rel(s)), C.byref(cfg), None)
+    assert res and res.contents.totalresults == s.size and res.contents.nthreads == 4
+    st = smj.smj_join_stats_t()
+    assert smj.lib.smj_last_join_stats(C.byref(st)) == 0
+    assert (st.matches, st.checksum) == orc.join_bruteforce(r, s)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+    libc.free(C.cast(res, C.c_void_p))
+    # scalar multiway merge twins: key-sorted, same multiset, inputs consumed
+    runs = [np.sort(ol.rand_items(rng, int(rng.integers(1, 5000)), 1 << 14)) for _ in range(8)]
+    total = sum(x.size for x in runs)
+    for name in ("scalar_multiway_merge_modulo", "scalar_multiway_merge_bitand"):
+        rels = (smj.relation_t * 8)(*[smj.relation_t(x.ctypes.data, x.size) for x in runs])
+        pp = (C.POINTER(smj.relation_t) * 8)(*[C.pointer(rels[i]) for i in range(8)])
+        out = np.zeros(total, dtype=np.uint64)
+        assert getattr(smj.lib, name)(out.ctypes.data, pp, 8, None, 0) == total
+        assert np.all(np.diff((out >> np.uint64(32)).astype(np.int64)) >= 0), name
+        assert np.array_equal(np.sort(out), orc.multiway_merge(runs)), name
+        assert all(rels[i].num_tuples == 0 for i in range(8))
+    # int64 twins of the sorts and merges
+    n = 70_001
+    items = ol.rand_items(rng, n, 1 << 27)
+    for name, mw in (("avxsortmultiway_int64", 1), ("scalarsort_int64", None)):
+        a, b = items.copy(), np.zeros(n, dtype=np.uint64)
+        pa, pb = C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)
+        getattr(smj.lib, name)(C.byref(pa), C.byref(pb), n)
+        placement = 0 if mw is None else orc.placement(n, mw)  # scalarsort sorts in place and swaps
+        assert pb.value == (b.ctypes.data if placement else a.ctypes.data), name
+        assert np.array_equal((b if placement else a), orc.sort(items)), name
+    a, b = np.sort(ol.rand_items(rng, 5000, 99)), np.sort(ol.rand_items(rng, 3001, 99))
+    out = np.zeros(8001, dtype=np.uint64)
+    for name in ("avx_merge_int64", "scalar_merge_int64"):
+        out[:] = 0
+        assert getattr(smj.lib, name)(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size, b.size) == 8001
+        assert np.array_equal(out, orc.merge(a, b, 0)), name
+    # host-side helpers
+    srt = orc.sort(items)
+    assert smj.lib.is_sorted_helper(srt.ctypes.data, n) == 1
+    assert smj.lib.is_sorted_helper(items.ctypes.data, n) == 0
+    capfd.readouterr()
+    smj.lib.check_sorted(srt.ctypes.data, items.ctypes.data, n, n, 3)
+    C.CDLL(None).fflush(None)
+    txt = capfd.readouterr().out
+    assert "3-thread -> R is sorted" in txt and "3-thread -> S is NOT sorted" in txt
+
+
+def test_gen_fk_from_and_nan_keys(smj, orc):
+    """smjdev_gen_fk_from (create_relation_fk_from_pk, generator.c:458-488) and the avoid_NaN rule
+    of smjdev_gen_fk for full-range keys (generator.c:107-121) against the oracle."""
+    nr, ns = 100_003, 350_001
+    r = orc.gen_fk(nr, (1 << 31) - 1, 5)
+    assert not np.any((r & np.uint64(0x7FF << 52)) == np.uint64(0x7FF << 52))
+    dr, ds = smj.DeviceBuffer(nr), smj.DeviceBuffer(ns)
+    smj.check(smj.lib.smjdev_gen_fk(dr.ptr, 0, nr, (1 << 31) - 1, 5))
+    assert np.array_equal(dr.to_host(), r)
+    smj.check(smj.lib.smjdev_gen_fk_from(ds.ptr, ns, 0, ns, dr.ptr, nr, 9))
+    s = ds.to_host()
+    assert np.array_equal(s, orc.gen_fk_from(ns, r, 9))
+    vals, cnt = np.unique(s, return_counts=True)
+    assert np.array_equal(vals, np.unique(r)) and cnt.min() >= ns // nr  # every row of R 3 or 4 times
+    dr.free()
+    ds.free()
