@@ -4,31 +4,53 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <unordered_map>
+#include <vector>
+
 typedef unsigned long long u64;
 typedef unsigned int       u32;
 
 // ---------------------------------------------------------------------------------------
 // runtime context (smj_runtime.cu)
 // ---------------------------------------------------------------------------------------
+struct SmjProfRec {
+    const char *name;
+    cudaEvent_t start, stop;
+    u64         items;
+};
+// One context per CUDA device.  A host thread works on the context it bound itself to with
+// smjdev_init(device) (threads that never called it share the first context created), so several
+// threads can drive several GPUs of one process concurrently (one thread per GPU: a context is
+// not meant to be used by two threads at the same time).
 struct SmjCtx {
     int          device;
     int          sm_count;
     cudaStream_t stream;      // stream all kernels are launched on
     cudaStream_t own_stream;  // the library's own stream (used when the caller sets none)
     cudaStream_t copy_stream; // host->device copies that overlap kernels on `stream`
-    u64          launches;    // kernels launched so far
+    cudaStream_t aux_stream;  // second compute stream (multi-GPU join: pass B of R under the exchange of S)
+    u64          launches;    // kernels launched so far on this device
     bool         ready;
     bool         profiling;   // smjdev_profile_begin(): CUDA events around every launch
     u64          next_items;  // items the next launch processes (annotation for the profile)
-    int          generation;  // bumped whenever the device changes: per-device kernel attributes
+    // per-device caches (were function-local statics while the library knew one device)
+    std::unordered_map<const void *, size_t> func_smem;   // dynamic shared memory limit set per kernel
+    std::unordered_map<const void *, int>    func_occ;    // cached occupancy queries
+    std::vector<cudaEvent_t>                 event_pool;  // untimed events (uploads, exchange)
+    std::vector<SmjProfRec>                  prof;
 };
 void smj_prof_before(SmjCtx *ctx, const char *kernel_name);
 void smj_prof_after(SmjCtx *ctx);
+void smj_count_launch(SmjCtx *ctx);
 #define SMJ_ITEMS(ctx, n) ((ctx)->next_items = (u64)(n))
-SmjCtx *smj_ctx();                 // initialises lazily; nullptr on failure
+SmjCtx *smj_ctx();                 // the calling thread's context; initialises lazily; nullptr on failure
+SmjCtx *smj_ctx_of(int device);    // context of a given device (created on demand), does not bind
 int     smj_fail(cudaError_t e, const char *what, const char *file, int line);
 int     smj_fail_msg(const char *msg);
 bool    smj_is_host_pointer(const void *p);  // mapped (pinned / registered) host memory
+// raises the kernel's dynamic shared memory limit on ctx's device once (per device and kernel)
+int     smj_func_smem(SmjCtx *ctx, const void *kernel, size_t bytes);
+cudaEvent_t smj_pool_event(SmjCtx *ctx, size_t idx);  // idx-th cached untimed event of this device
 
 #define SMJ_CHECK(expr)                                                        \
     do {                                                                       \
@@ -43,31 +65,34 @@ bool    smj_is_host_pointer(const void *p);  // mapped (pinned / registered) hos
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
         if ((ctx)->profiling) smj_prof_after((ctx));                           \
         (ctx)->next_items = 0;                                                 \
-        (ctx)->launches++;                                                     \
+        smj_count_launch(ctx);                                                 \
         cudaError_t e__ = cudaGetLastError();                                  \
         if (e__ != cudaSuccess) return smj_fail(e__, #kernel, __FILE__, __LINE__); \
     } while (0)
 
 // stream-ordered scratch allocation with automatic release at scope exit
 struct SmjScratch {
-    SmjCtx *ctx;
-    void   *ptrs[32];
-    int     n;
-    u64     bytes;
-    explicit SmjScratch(SmjCtx *c) : ctx(c), n(0), bytes(0) {}
+    SmjCtx             *ctx;
+    std::vector<void *> ptrs;
+    u64                 bytes;
+    explicit SmjScratch(SmjCtx *c) : ctx(c), bytes(0) {}
+    SmjScratch(const SmjScratch &) = delete;
+    SmjScratch &operator=(const SmjScratch &) = delete;
     ~SmjScratch() { release(); }
     void *get(size_t nbytes) {
-        if (n >= 32) return nullptr;
         void *p = nullptr;
         if (nbytes == 0) nbytes = 16;
-        if (cudaMallocAsync(&p, nbytes, ctx->stream) != cudaSuccess) return nullptr;
-        ptrs[n++] = p;
+        if (cudaMallocAsync(&p, nbytes, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        ptrs.push_back(p);
         bytes += nbytes;
         return p;
     }
     void release() {
-        for (int i = 0; i < n; i++) cudaFreeAsync(ptrs[i], ctx->stream);
-        n = 0;
+        for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
+        ptrs.clear();
     }
 };
 

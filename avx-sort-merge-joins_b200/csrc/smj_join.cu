@@ -26,6 +26,10 @@
 #include <vector>
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
+int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
+                      u64 **sorted);
+int smj_item_bits(SmjCtx *ctx, const u64 *in, u64 n, u64 *h_bits);
+constexpr u64 SMJ_SMALL_SORT_MAX = 16384;
 int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, const u64 *lens,
                        u32 nruns, int mode);
 int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
@@ -598,16 +602,31 @@ void chunk_bounds(u64 n, int runs, std::vector<u64> &off) {
     off[runs] = n;
 }
 
+// Sorts the `runs` chunks of a relation by key.  The varying key bits are probed ONCE for the whole
+// relation (one host synchronisation instead of one per run; a bit that varies in the relation but
+// not in a run only costs that run a pass), small runs take the one-CTA sort.
 int sort_runs(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int runs,
               std::vector<const u64 *> &ptrs, std::vector<u64> &lens) {
     std::vector<u64> off;
     chunk_bounds(n, runs, off);
     ptrs.clear();
     lens.clear();
+    u64  h_bits[3] = {0, 0, 0};
+    bool have_bits = false;
     for (int i = 0; i < runs; i++) {
         u64  len    = off[i + 1] - off[i];
         u64 *sorted = nullptr;
-        int  rc = smj_lsd_sort(ctx, in + off[i], a + off[i], b + off[i], len, 2, &sorted);
+        int  rc;
+        if (len <= SMJ_SMALL_SORT_MAX) {
+            rc = smj_lsd_sort(ctx, in + off[i], a + off[i], b + off[i], len, 2, &sorted);
+        } else {
+            if (!have_bits) {
+                if ((rc = smj_item_bits(ctx, in, n, h_bits))) return rc;
+                h_bits[2] |= 1;  // "already sorted" of the whole relation is not probed per run: sort
+                have_bits = true;
+            }
+            rc = smj_lsd_sort_bits(ctx, in + off[i], a + off[i], b + off[i], len, 2, h_bits, &sorted);
+        }
         if (rc) return rc;
         ptrs.push_back(sorted);
         lens.push_back(len);
@@ -949,26 +968,14 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
         // buckets with duplicate R keys are flagged (d_list doubles as the flags) and done by the
         // general-table kernel afterwards; no cooperative heavy-hitter kernel.
         const size_t bsmem = (size_t)(1u << lbits) * 4 + (size_t)(1u << lbits) / 8;
-        static int   gen_bm = -1;
-        if (gen_bm != ctx->generation) {
-            gen_bm = ctx->generation;
-            SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           48 * 1024));
-        }
+        if (smj_func_smem(ctx, (const void *)k_bucket_join_bitmap, 48 * 1024)) return -1;
         const int bm_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / bsmem));
         SMJ_CHECK(cudaMemsetAsync(d_list, 0, (size_t)nb2 * 4, ctx->stream));
         SMJ_ITEMS(ctx, R.n + S.n);
         SMJ_LAUNCH(ctx, k_bucket_join_bitmap, ctx->sm_count * bm_per_sm, 256, bsmem, R.items, R.starts, R.ends,
                    S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, d_list, acc);
         const size_t smem = (size_t)(1u << lbits) * 12;
-        static size_t smem_set_cta = 0;
-        static int    gen_cta      = -1;
-        if (smem > smem_set_cta || gen_cta != ctx->generation) {
-            gen_cta = ctx->generation;
-            SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join_cta, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-            smem_set_cta = smem;
-        }
+        if (smj_func_smem(ctx, (const void *)k_bucket_join_cta, smem)) return -1;
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / smem));
         SMJ_ITEMS(ctx, R.n + S.n);
         SMJ_LAUNCH(ctx, k_bucket_join_cta, ctx->sm_count * per_sm, 256, smem, R.items, R.starts, R.ends,
@@ -976,16 +983,8 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
         return 0;
     }
     const size_t smem = (size_t)BJ_WARPS * (1u << lbits) * 12;
-    static size_t smem_set = 0;
-    static int    smem_gen = -1;
-    if (smem > smem_set || smem_gen != ctx->generation) {
-        smem_gen = ctx->generation;
-        SMJ_CHECK(cudaFuncSetAttribute(k_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        SMJ_CHECK(cudaFuncSetAttribute(k_big_bucket_join, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        smem_set = smem;
-    }
+    if (smj_func_smem(ctx, (const void *)k_bucket_join, smem)) return -1;
+    if (smj_func_smem(ctx, (const void *)k_big_bucket_join, smem)) return -1;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
     SMJ_ITEMS(ctx, R.n + S.n);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts, R.ends,
@@ -1050,24 +1049,12 @@ struct Upload {
     }
     ~Upload() { wait_all(); }  // the staging buffer is freed in stream order behind the copies
 };
-static cudaEvent_t upload_event(SmjCtx *ctx, size_t idx) {
-    static std::vector<cudaEvent_t> pool;
-    static int                      gen = -1;
-    if (gen != ctx->generation) {
-        pool.clear();  // events of another device: leaked on purpose (a handful, once)
-        gen = ctx->generation;
-    }
-    while (pool.size() <= idx) {
-        cudaEvent_t e = nullptr;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        pool.push_back(e);
-    }
-    return pool[idx];
-}
+// (entries 0 and 1 of the context's event cache belong to smjdev_exchange_begin / _end)
+static cudaEvent_t upload_event(SmjCtx *ctx, size_t idx) { return smj_pool_event(ctx, idx + 2); }
 // starts the copies; ev_base: first index of this relation's events in the cache
 static int upload_begin(SmjCtx *ctx, SmjScratch &sc, const u64 *host, u64 n, size_t ev_base, Upload &up) {
-    static u64 CHUNK = 0;  // items per chunk, a multiple of the scatter tile (8192 items)
-    if (!CHUNK) {
+    u64 CHUNK = 0;  // items per chunk, a multiple of the scatter tile (8192 items)
+    {
         // measured end to end (128 M x 128 M): 32 MiB 38.3 ms, 64 MiB 38.2, 128 MiB 38.1, 256 MiB 38.1
         const char *e = getenv("SMJ_UPLOAD_CHUNK_MB");
         CHUNK         = ((e && atoi(e) > 0) ? (u64)atoi(e) : 128ull) << 17;

@@ -195,13 +195,7 @@ template <int BS_THREADS, int IPT>
 int launch_bucket_sort(SmjCtx *ctx, const u64 *b, const u64 *starts, const u64 *bend, const u64 *outoff,
                        u32 lo_shift, u32 lbits, u64 *out, u32 *flag, u64 n) {
     const size_t smem = (size_t)BS_THREADS * IPT * 8 + (size_t)(1u << lbits) * 4;
-    static size_t smem_set = 0;
-    static int    smem_gen = -1;
-    if (smem > smem_set || smem_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_bucket_sort<BS_THREADS, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-        smem_gen = ctx->generation;
-    }
+    if (smj_func_smem(ctx, (const void *)k_bucket_sort<BS_THREADS, IPT>, smem)) return -1;
     int per_sm = 1;  // resident CTAs per SM: the grid is exactly one wave (static bucket assignment)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bucket_sort<BS_THREADS, IPT>, BS_THREADS, smem) !=
             cudaSuccess ||

@@ -743,12 +743,7 @@ template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM
 int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim) {
     constexpr int    NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM = (size_t)TILE * 8 + NB * 4 + NB * 8;
-    static int       attr_gen = -1;
-    if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_gen = ctx->generation;
-    }
+    if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>, SMEM)) return -1;
     // One CTA per tile: measured faster on HBM-resident input than persistent CTAs with the next
     // tile in flight (0.49 vs 0.52 ms per 128 M items; the kernel is bound by the shared-memory
     // pipe, not by load latency).  Persistent CTAs (the kernel supports any grid) pay off when the
@@ -784,13 +779,7 @@ int launch_onesweep_cfg(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const
                         u64 *status, u32 *counter, DigitFn fn_full, const u64 *padshift) {
     using Cfg = OneSweepCfg<THREADS, IPT, BITS>;
     static_assert(Cfg::TILE >= OS_MIN_TILE, "status_bytes assumes tiles of at least OS_MIN_TILE");
-    static int attr_gen = -1;  // kernel attributes are per device
-    if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::SMEM));
-        attr_gen = ctx->generation;
-    }
+    if (smj_func_smem(ctx, (const void *)k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>, Cfg::SMEM)) return -1;
     const u64 tiles = div_up(n, Cfg::TILE);
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, (k_onesweep<THREADS, IPT, BITS, F, RANK, MINB>), (unsigned)tiles, THREADS,
@@ -874,20 +863,49 @@ int hist_grid(SmjCtx *ctx, u64 n, int threads, int per_thread) {
 // Reads `in`, ping-pongs between the scratch buffers a and b (pass 1: in -> a, pass 2: a -> b,
 // pass 3: b -> a, ...).  `in` may alias b (classic two-buffer sort) but not a.  *sorted is set
 // to the buffer that holds the result, which is `in` itself when no pass was necessary.
-int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted) {
-    *sorted = const_cast<u64 *>(in);
-    const u64 *buf = in;
-    if (n <= 1) return 0;
+int smj_small_sort(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, bool stable_key);
+constexpr u64 SMJ_SMALL_SORT_MAX = 16384;  // the reference's in-cache block (src/avxsort/avxsort.c:17)
+
+// OR / AND / order flags of n items (host array of 3 words); synchronises
+int smj_item_bits(SmjCtx *ctx, const u64 *in, u64 n, u64 *h_bits) {
     SmjScratch sc(ctx);
     u64 *d_bits = (u64 *)sc.get(24);
     if (!d_bits) return smj_fail_msg("smj_lsd_sort: scratch allocation failed");
     const u64 init[3] = {0ull, ~0ull, 0ull};
     SMJ_CHECK(cudaMemcpyAsync(d_bits, init, 24, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, n, 256, 16), 256, 0, buf, n, d_bits);
-    u64 h_bits[3];
+    SMJ_LAUNCH(ctx, k_bits_reduce, hist_grid(ctx, n, 256, 16), 256, 0, in, n, d_bits);
     SMJ_CHECK(cudaMemcpyAsync(h_bits, d_bits, 24, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
+                      u64 **sorted);
+
+int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted) {
+    *sorted = const_cast<u64 *>(in);
+    if (n <= 1) return 0;
+    if (n <= SMJ_SMALL_SORT_MAX && !getenv("SMJ_NO_SMALL_SORT")) {
+        // one CTA, one launch, no bit probe and no host synchronisation (smj_smallsort.cu)
+        *sorted = a;
+        return smj_small_sort(ctx, in, a, n, key_only == 1);
+    }
+    u64 h_bits[3];
+    int rc = smj_item_bits(ctx, in, n, h_bits);
+    if (rc) return rc;
+    return smj_lsd_sort_bits(ctx, in, a, b, n, key_only, h_bits, sorted);
+}
+
+// The passes of the LSD sort for items whose OR / AND / order flags are known (h_bits: exact for
+// these items, or of a superset of them -- extra varying bits only cost passes; order flags of a
+// superset that says "ascending" hold for every contiguous part).  No host synchronisation.
+int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
+                      u64 **sorted) {
+    *sorted = const_cast<u64 *>(in);
+    const u64 *buf = in;
+    if (n <= 1) return 0;
+    SmjScratch sc(ctx);
     u64 varying = h_bits[0] & ~h_bits[1];
     if (!key_only && !(h_bits[2] & 1)) return 0;  // already in whole-word order
     // payloads already ascend in input order (e.g. row numbers): the stable key passes suffice
@@ -972,12 +990,7 @@ static int run_hist_wide(SmjCtx *ctx, const u64 *in, u64 n, DigitFn fn, u32 nbin
     SMJ_CHECK(cudaMemsetAsync(hist, 0, (size_t)nbins * 8, ctx->stream));
     if (n == 0) return 0;
     if (nbins <= (1u << 14)) {
-        static int attr_gen = -1;
-        if (attr_gen != ctx->generation) {
-            SMJ_CHECK(cudaFuncSetAttribute(k_hist_wide_smem,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            attr_gen = ctx->generation;
-        }
+        if (smj_func_smem(ctx, (const void *)k_hist_wide_smem, 65536)) return -1;
         SMJ_LAUNCH(ctx, k_hist_wide_smem, hist_grid(ctx, n, 512, 16), 512, (size_t)nbins * 4, in, n,
                    fn, nbins, hist);
     } else {
@@ -1702,18 +1715,10 @@ int smj_exclusive_scan_u64(SmjCtx *ctx, const u64 *in, u64 n, u64 *out) {
 }
 
 static int msd_scatter2_attr(SmjCtx *ctx) {
-    static int       attr_gen = -1;
-    constexpr size_t SMEM     = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
-    if (attr_gen != ctx->generation) {
-        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM));
-        SMJ_CHECK(cudaFuncSetAttribute(k_msd_scatter2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM));
-        SMJ_CHECK(cudaFuncSetAttribute(k_msd_fix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SMEM));
-        attr_gen = ctx->generation;
-    }
-    return 0;
+    constexpr size_t SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
+    if (smj_func_smem(ctx, (const void *)k_msd_scatter2<false>, SMEM)) return -1;
+    if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true>, SMEM)) return -1;
+    return smj_func_smem(ctx, (const void *)k_msd_fix_scatter, SMEM);
 }
 constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
 
@@ -1778,16 +1783,16 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
     // the kernel contains a grid barrier: size the grid to what the device can hold at once (a
     // smaller GPU, a MIG slice) and return 1 when even that fails, so that the caller can fall back
     // to the exact passes instead of failing the join
-    static int max_ctas = -1, occ_gen = -1;
-    if (occ_gen != ctx->generation) {
+    auto occ = ctx->func_occ.find((const void *)k_msd_sample);
+    if (occ == ctx->func_occ.end()) {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msd_sample, SAMP_THREADS, 0) != cudaSuccess) {
             cudaGetLastError();
             per_sm = 0;
         }
-        max_ctas = per_sm * ctx->sm_count;
-        occ_gen  = ctx->generation;
+        occ = ctx->func_occ.emplace((const void *)k_msd_sample, per_sm * ctx->sm_count).first;
     }
+    const int max_ctas = occ->second;
     const int   ctas = std::min(SAMP_CTAS, max_ctas / 2);
     const char *hook = getenv("SMJ_MSD_TEST");  // "nocoop": behave like a device without cooperative launch
     if (ctas < 1 || (hook && !strcmp(hook, "nocoop"))) return 1;
@@ -1805,7 +1810,7 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
                                                 dim3(SAMP_THREADS), args, 0, ctx->stream);
     if (ctx->profiling) smj_prof_after(ctx);
     ctx->next_items = 0;
-    ctx->launches++;
+    smj_count_launch(ctx);
     if (e != cudaSuccess) {  // e.g. cooperative launches not available here
         cudaGetLastError();
         return 1;

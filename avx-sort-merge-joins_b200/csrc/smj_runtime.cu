@@ -3,6 +3,7 @@
 #include "../../include/smj_device.h"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -10,30 +11,33 @@
 #include <stdlib.h>
 #include <string.h>
 
-static SmjCtx              g_ctx = {-1, 0, nullptr, nullptr, 0, false, false, 0, 0};
+// ---- contexts: one per device, created on demand; a thread is bound to one of them
+constexpr int SMJ_MAX_DEVICES = 64;
+static std::mutex               g_mu;
+static SmjCtx                  *g_ctxs[SMJ_MAX_DEVICES] = {nullptr};
+static SmjCtx                  *g_default = nullptr;  // context of the first successful init
+static thread_local SmjCtx     *t_ctx = nullptr;
+static std::atomic<u64>         g_launches{0};        // all devices, for smjdev_launch_count()
+static thread_local char        g_err[512] = "";
+
+void smj_count_launch(SmjCtx *ctx) {
+    ctx->launches++;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 // ---- optional per-kernel timing (bench.py's roofline numbers): CUDA events on the launch stream
-struct ProfRec {
-    const char *name;
-    cudaEvent_t start, stop;
-    u64         items;
-};
-static std::vector<ProfRec> g_prof;
-
 void smj_prof_before(SmjCtx *ctx, const char *kernel_name) {
-    ProfRec r;
+    SmjProfRec r;
     r.name  = kernel_name;
     r.items = ctx->next_items;
     cudaEventCreate(&r.start);
     cudaEventCreate(&r.stop);
     cudaEventRecord(r.start, ctx->stream);
-    g_prof.push_back(r);
+    ctx->prof.push_back(r);
 }
 void smj_prof_after(SmjCtx *ctx) {
-    if (!g_prof.empty()) cudaEventRecord(g_prof.back().stop, ctx->stream);
+    if (!ctx->prof.empty()) cudaEventRecord(ctx->prof.back().stop, ctx->stream);
 }
-static std::mutex          g_mu;
-static thread_local char   g_err[512] = "";
 
 int smj_fail(cudaError_t e, const char *what, const char *file, int line) {
     snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d in `%s`", (int)e,
@@ -47,8 +51,8 @@ int smj_fail_msg(const char *msg) {
     return -1;
 }
 
-static int ctx_init_locked(int device) {
-    if (g_ctx.ready && (device < 0 || device == g_ctx.device)) return 0;
+// creates (once) the context of `device`; g_mu held.  device < 0: $SMJ_DEVICE, $LOCAL_RANK or 0
+static int ctx_create_locked(int device, SmjCtx **out) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -62,24 +66,33 @@ static int ctx_init_locked(int device) {
         device = env ? atoi(env) : 0;
         if (device < 0 || device >= ndev) device = device % ndev;
     }
-    if (device >= ndev) return smj_fail_msg("smjdev_init: device index out of range");
+    if (device >= ndev || device >= SMJ_MAX_DEVICES) return smj_fail_msg("smjdev_init: device index out of range");
+    if (g_ctxs[device]) {
+        *out = g_ctxs[device];
+        return 0;
+    }
     SMJ_CHECK(cudaSetDevice(device));
-    if (g_ctx.ready && g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
-    if (g_ctx.ready && g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
     cudaDeviceProp prop;
     SMJ_CHECK(cudaGetDeviceProperties(&prop, device));
-    g_ctx.device   = device;
-    g_ctx.generation++;
-    g_ctx.sm_count = prop.multiProcessorCount;
-    SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
-    SMJ_CHECK(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-    g_ctx.stream = g_ctx.own_stream;
+    SmjCtx *c   = new SmjCtx();
+    c->device   = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->launches = 0;
+    c->ready = c->profiling = false;
+    c->next_items = 0;
+    SMJ_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    SMJ_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SMJ_CHECK(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     // keep freed scratch in the pool: cudaMallocAsync then costs microseconds, not a driver call
     cudaMemPool_t pool;
     SMJ_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long thresh = ~0ull;
     SMJ_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    g_ctx.ready = true;
+    c->ready       = true;
+    g_ctxs[device] = c;
+    if (!g_default) g_default = c;
+    *out = c;
     return 0;
 }
 
@@ -92,13 +105,43 @@ bool smj_is_host_pointer(const void *p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
+// The calling thread's context.  The library makes its device the thread's current CUDA device
+// and leaves it so (like cudaSetDevice itself, this is visible to the caller).
 SmjCtx *smj_ctx() {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready && ctx_init_locked(-1) != 0) return nullptr;
-    // the caller may have switched devices (torch does); kernels must go to ours
+    if (!t_ctx) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        t_ctx = g_default;
+        if (!t_ctx && ctx_create_locked(-1, &t_ctx) != 0) return nullptr;
+    }
     int cur = -1;
-    if (cudaGetDevice(&cur) == cudaSuccess && cur != g_ctx.device) cudaSetDevice(g_ctx.device);
-    return &g_ctx;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != t_ctx->device) cudaSetDevice(t_ctx->device);
+    return t_ctx;
+}
+SmjCtx *smj_ctx_of(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    SmjCtx *c = nullptr;
+    int     cur = -1;
+    cudaGetDevice(&cur);
+    if (ctx_create_locked(device, &c) != 0) c = nullptr;
+    if (cur >= 0) cudaSetDevice(cur);
+    return c;
+}
+
+int smj_func_smem(SmjCtx *ctx, const void *kernel, size_t bytes) {
+    auto it = ctx->func_smem.find(kernel);
+    if (it != ctx->func_smem.end() && it->second >= bytes) return 0;
+    SMJ_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->func_smem[kernel] = bytes;
+    return 0;
+}
+
+cudaEvent_t smj_pool_event(SmjCtx *ctx, size_t idx) {
+    while (ctx->event_pool.size() <= idx) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ctx->event_pool.push_back(e);
+    }
+    return ctx->event_pool[idx];
 }
 
 extern "C" {
@@ -111,9 +154,21 @@ int smjdev_device_count(void) {
     }
     return n;
 }
+// binds the calling thread to `device` (device < 0: keep the thread's binding if it has one, else
+// $SMJ_DEVICE, $LOCAL_RANK or 0)
 int smjdev_init(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
-    return ctx_init_locked(device);
+    if (device < 0 && t_ctx) return 0;
+    if (device < 0 && g_default) {
+        t_ctx = g_default;
+        return 0;
+    }
+    SmjCtx *c = nullptr;
+    int     rc = ctx_create_locked(device, &c);
+    if (rc) return rc;
+    t_ctx = c;
+    SMJ_CHECK(cudaSetDevice(c->device));
+    return 0;
 }
 int smjdev_current_device(void) {
     SmjCtx *c = smj_ctx();
@@ -142,7 +197,7 @@ int smjdev_sync(void) {
     return 0;
 }
 const char *smjdev_last_error(void) { return g_err; }
-uint64_t    smjdev_launch_count(void) { return g_ctx.launches; }
+uint64_t    smjdev_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int         smjdev_sm_count(void) {
     SmjCtx *c = smj_ctx();
     return c ? c->sm_count : 0;
@@ -210,17 +265,14 @@ int smjdev_memset(void *dst, int value, size_t bytes) {
 // stream so far, and the compute stream continues only when they are done.  dst / src may be peer
 // GPUs' buffers (smjdev_ipc_open): a contiguous copy crosses NVLink at ~735 GB/s on B200, about
 // twice what scattered stores from the SMs reach.
-static cudaEvent_t g_xev[2] = {nullptr, nullptr};
-static int exchange_events(void) {
-    for (auto &e : g_xev)
-        if (!e) SMJ_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    return 0;
-}
+// (the two ordering events are entries 0 and 1 of the context's event cache; the chunk events of
+// an upload start at entry 2, see smj_join.cu)
 int smjdev_exchange_begin(void) {
     SmjCtx *c = smj_ctx();
-    if (!c || exchange_events()) return -1;
-    SMJ_CHECK(cudaEventRecord(g_xev[0], c->stream));
-    SMJ_CHECK(cudaStreamWaitEvent(c->copy_stream, g_xev[0], 0));
+    cudaEvent_t ev = c ? smj_pool_event(c, 0) : nullptr;
+    if (!ev) return -1;
+    SMJ_CHECK(cudaEventRecord(ev, c->stream));
+    SMJ_CHECK(cudaStreamWaitEvent(c->copy_stream, ev, 0));
     return 0;
 }
 int smjdev_exchange_copy(void *dst, const void *src, size_t bytes) {
@@ -231,9 +283,10 @@ int smjdev_exchange_copy(void *dst, const void *src, size_t bytes) {
 }
 int smjdev_exchange_end(void) {
     SmjCtx *c = smj_ctx();
-    if (!c || exchange_events()) return -1;
-    SMJ_CHECK(cudaEventRecord(g_xev[1], c->copy_stream));
-    SMJ_CHECK(cudaStreamWaitEvent(c->stream, g_xev[1], 0));
+    cudaEvent_t ev = c ? smj_pool_event(c, 1) : nullptr;
+    if (!ev) return -1;
+    SMJ_CHECK(cudaEventRecord(ev, c->copy_stream));
+    SMJ_CHECK(cudaStreamWaitEvent(c->stream, ev, 0));
     return 0;
 }
 
@@ -256,11 +309,11 @@ int smjdev_pointer_kind(const void *p) {
 int smjdev_profile_begin(void) {
     SmjCtx *c = smj_ctx();
     if (!c) return -1;
-    for (auto &r : g_prof) {
+    for (auto &r : c->prof) {
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
     }
-    g_prof.clear();
+    c->prof.clear();
     c->profiling = true;
     return 0;
 }
@@ -276,7 +329,7 @@ int smjdev_profile_end(char *out, size_t cap) {
     };
     std::map<std::string, Agg> agg;
     std::vector<std::string>   order;
-    for (auto &r : g_prof) {
+    for (auto &r : c->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.start, r.stop);
         if (!agg.count(r.name)) {
@@ -290,7 +343,7 @@ int smjdev_profile_end(char *out, size_t cap) {
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
     }
-    g_prof.clear();
+    c->prof.clear();
     std::string txt;
     for (auto &k : order) {
         char line[512];
@@ -377,34 +430,32 @@ constexpr int    STG_SLOTS = 12;
 constexpr size_t STG_CHUNK = 8u << 20;
 struct Stager {
     bool                   ready = false;
-    int                    device = -1;
     void                  *bounce[STG_SLOTS];
     cudaEvent_t            ev[STG_SLOTS];
     std::atomic<long long> done[STG_SLOTS];  // index of the last chunk whose event was recorded
     cudaStream_t           stream = nullptr;
     cudaEvent_t            fence  = nullptr;
-    std::mutex             mu;  // one staged transfer at a time (the ring is shared)
-} g_stg;
+    std::mutex             mu;  // one staged transfer at a time per device (the ring is shared)
+};
+Stager    *g_stgs[SMJ_MAX_DEVICES] = {nullptr};  // one ring per device, built on first use
+std::mutex g_stgs_mu;
 
-int stager_init(SmjCtx *c) {
-    if (g_stg.ready && g_stg.device == c->device) return 0;
-    if (g_stg.ready) {  // device changed: rebuild
-        for (int i = 0; i < STG_SLOTS; i++) {
-            cudaFreeHost(g_stg.bounce[i]);
-            cudaEventDestroy(g_stg.ev[i]);
-        }
-        cudaStreamDestroy(g_stg.stream);
-        cudaEventDestroy(g_stg.fence);
-        g_stg.ready = false;
-    }
+Stager *stager_of(SmjCtx *c) {
+    std::lock_guard<std::mutex> lk(g_stgs_mu);
+    if (!g_stgs[c->device]) g_stgs[c->device] = new Stager();
+    return g_stgs[c->device];
+}
+
+// st->mu held
+int stager_init(Stager *st) {
+    if (st->ready) return 0;
     for (int i = 0; i < STG_SLOTS; i++) {
-        SMJ_CHECK(cudaMallocHost(&g_stg.bounce[i], STG_CHUNK));
-        SMJ_CHECK(cudaEventCreateWithFlags(&g_stg.ev[i], cudaEventDisableTiming));
+        SMJ_CHECK(cudaHostAlloc(&st->bounce[i], STG_CHUNK, cudaHostAllocPortable));
+        SMJ_CHECK(cudaEventCreateWithFlags(&st->ev[i], cudaEventDisableTiming));
     }
-    SMJ_CHECK(cudaStreamCreateWithFlags(&g_stg.stream, cudaStreamNonBlocking));
-    SMJ_CHECK(cudaEventCreateWithFlags(&g_stg.fence, cudaEventDisableTiming));
-    g_stg.device = c->device;
-    g_stg.ready  = true;
+    SMJ_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    SMJ_CHECK(cudaEventCreateWithFlags(&st->fence, cudaEventDisableTiming));
+    st->ready = true;
     return 0;
 }
 
@@ -418,14 +469,15 @@ int stager_threads(size_t nchunks) {
 
 // dir 0: host -> device, dir 1: device -> host
 int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
-    std::lock_guard<std::mutex> lk(g_stg.mu);
-    int rc = stager_init(c);
+    Stager *st = stager_of(c);
+    std::lock_guard<std::mutex> lk(st->mu);
+    int rc = stager_init(st);
     if (rc) return rc;
     // the device buffer may have been produced (or allocated) on the compute stream
-    SMJ_CHECK(cudaEventRecord(g_stg.fence, c->stream));
-    SMJ_CHECK(cudaStreamWaitEvent(g_stg.stream, g_stg.fence, 0));
+    SMJ_CHECK(cudaEventRecord(st->fence, c->stream));
+    SMJ_CHECK(cudaStreamWaitEvent(st->stream, st->fence, 0));
     const size_t nchunks = (bytes + STG_CHUNK - 1) / STG_CHUNK;
-    for (int i = 0; i < STG_SLOTS; i++) g_stg.done[i].store((long long)i - STG_SLOTS);
+    for (int i = 0; i < STG_SLOTS; i++) st->done[i].store((long long)i - STG_SLOTS);
     std::atomic<size_t> next{0};
     std::atomic<int>    err{0};
     const int           device = c->device;
@@ -439,20 +491,20 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
             if (i >= nchunks) break;
             const int    slot = (int)(i % STG_SLOTS);
             const size_t off = i * STG_CHUNK, len = std::min(STG_CHUNK, bytes - off);
-            while (g_stg.done[slot].load() != (long long)i - STG_SLOTS) std::this_thread::yield();
-            cudaError_t e = cudaEventSynchronize(g_stg.ev[slot]);  // the slot's previous DMA is over
+            while (st->done[slot].load() != (long long)i - STG_SLOTS) std::this_thread::yield();
+            cudaError_t e = cudaEventSynchronize(st->ev[slot]);  // the slot's previous DMA is over
             if (e == cudaSuccess && dir == 0) {
-                memcpy(g_stg.bounce[slot], host + off, len);
-                e = cudaMemcpyAsync(dev + off, g_stg.bounce[slot], len, cudaMemcpyHostToDevice, g_stg.stream);
-                if (e == cudaSuccess) e = cudaEventRecord(g_stg.ev[slot], g_stg.stream);
+                memcpy(st->bounce[slot], host + off, len);
+                e = cudaMemcpyAsync(dev + off, st->bounce[slot], len, cudaMemcpyHostToDevice, st->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(st->ev[slot], st->stream);
             } else if (e == cudaSuccess) {
-                e = cudaMemcpyAsync(g_stg.bounce[slot], dev + off, len, cudaMemcpyDeviceToHost, g_stg.stream);
-                if (e == cudaSuccess) e = cudaEventRecord(g_stg.ev[slot], g_stg.stream);
-                if (e == cudaSuccess) e = cudaEventSynchronize(g_stg.ev[slot]);
-                if (e == cudaSuccess) memcpy(host + off, g_stg.bounce[slot], len);
+                e = cudaMemcpyAsync(st->bounce[slot], dev + off, len, cudaMemcpyDeviceToHost, st->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(st->ev[slot], st->stream);
+                if (e == cudaSuccess) e = cudaEventSynchronize(st->ev[slot]);
+                if (e == cudaSuccess) memcpy(host + off, st->bounce[slot], len);
             }
             if (e != cudaSuccess) err.store((int)e);
-            g_stg.done[slot].store((long long)i);
+            st->done[slot].store((long long)i);
         }
     };
     const int nthreads = stager_threads(nchunks);
@@ -462,9 +514,9 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
     for (auto &t : pool) t.join();
     if (err.load()) return smj_fail((cudaError_t)err.load(), "staged_copy", __FILE__, __LINE__);
     // later work on the compute stream must see the uploaded data
-    SMJ_CHECK(cudaEventRecord(g_stg.fence, g_stg.stream));
-    SMJ_CHECK(cudaStreamWaitEvent(c->stream, g_stg.fence, 0));
-    if (dir == 1) SMJ_CHECK(cudaStreamSynchronize(g_stg.stream));
+    SMJ_CHECK(cudaEventRecord(st->fence, st->stream));
+    SMJ_CHECK(cudaStreamWaitEvent(c->stream, st->fence, 0));
+    if (dir == 1) SMJ_CHECK(cudaStreamSynchronize(st->stream));
     return 0;
 }
 }  // namespace

@@ -126,8 +126,14 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
     g_have_stats = 1;
 
     /* result ownership as src/joins/joincommon.c:109-112, 168-173 */
-    result_t *res   = (result_t *)malloc(sizeof(result_t));
-    res->resultlist = (threadresult_t *)calloc((size_t)nthreads, sizeof(threadresult_t));
+    result_t *res = (result_t *)malloc(sizeof(result_t));
+    if (res) res->resultlist = (threadresult_t *)calloc((size_t)nthreads, sizeof(threadresult_t));
+    if (!res || !res->resultlist) { /* src/joins/joincommon.c:79-82: allocation failures are fatal */
+        free(res);
+        perror("[ERROR] result_t allocation failed");
+        if (!getenv("SMJ_NO_EXIT")) exit(EXIT_FAILURE);
+        return NULL;
+    }
     for (int i = 0; i < nthreads; i++) res->resultlist[i].threadid = (uint32_t)i;
     res->resultlist[0].nresults = (int64_t)st.matches;
     res->totalresults           = (int64_t)st.matches;

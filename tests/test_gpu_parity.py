@@ -879,3 +879,46 @@ def test_gen_fk_from_and_nan_keys(smj, orc):
     assert np.array_equal(vals, np.unique(r)) and cnt.min() >= ns // nr  # every row of R 3 or 4 times
     dr.free()
     ds.free()
+
+
+@pytest.mark.parametrize("n", [2, 31, 32, 33, 511, 1000, 4097, 8192, 16383, 16384])
+def test_small_sort_is_one_launch(smj, orc, n, monkeypatch):
+    """Inputs up to the reference's 16384-item in-cache block (src/avxsort/avxsort.c:17,
+    avxsort_core.h:1213-1274, 2056-2214) are sorted by ONE kernel launch (register sorting network +
+    merge-path rounds in shared memory), whole-word and stable key-only; the radix passes give the
+    same result."""
+    rng = np.random.default_rng(n)
+    for kind in ("unique", "dups", "equal", "reverse", "wide"):
+        items = _inputs(rng, n, kind)
+        for key_only, exp in ((0, orc.sort(items)), (1, orc.sort_key_stable(items))):
+            buf, tmp = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+            res = C.c_void_p()
+            before = smj.lib.smjdev_launch_count()
+            smj.check(smj.lib.smjdev_sort(buf.ptr, tmp.ptr, n, key_only, 1, C.byref(res)), "sort")
+            assert smj.lib.smjdev_launch_count() - before == 1
+            smj.check(smj.lib.smjdev_sync())
+            got = (buf if res.value == buf.ptr else tmp).to_host()
+            assert np.array_equal(got, exp), (kind, key_only)
+            monkeypatch.setenv("SMJ_NO_SMALL_SORT", "1")
+            buf2, tmp2 = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+            smj.check(smj.lib.smjdev_sort(buf2.ptr, tmp2.ptr, n, key_only, 1, C.byref(res)), "sort")
+            smj.check(smj.lib.smjdev_sync())
+            assert np.array_equal((buf2 if res.value == buf2.ptr else tmp2).to_host(), exp), (kind, key_only, "radix")
+            monkeypatch.delenv("SMJ_NO_SMALL_SORT")
+            for b in (buf, tmp, buf2, tmp2):
+                b.free()
+
+
+def test_run_sorts_share_one_bit_probe(smj, orc):
+    """m-pass / mpsm with many runs: the varying key bits are probed once per relation, tiny runs go
+    through the one-CTA sort; same {count, checksum} as the oracle for 1 .. 64 runs."""
+    rng = np.random.default_rng(12)
+    r, s = ol.rand_items(rng, 300_001, 40_000), ol.rand_items(rng, 500_003, 40_000)
+    exp = orc.join_bruteforce(r, s)
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    for algo in (smj.ALGO_MPASS, smj.ALGO_MPSM):
+        for runs in (1, 2, 8, 64):
+            st = smj.device_join(algo, dr, ds, nruns=runs)
+            assert (st.matches, st.checksum) == exp, (algo, runs)
+    dr.free()
+    ds.free()
