@@ -64,6 +64,7 @@ NUMA_RANDOM, NUMA_RING, NUMA_NEXT = 0, 1, 2
 ALGO_MWAY, ALGO_MPASS, ALGO_MPSM = 0, 1, 2
 PATH_GENERAL, PATH_MSD, PATH_MSD_OPT = 0, 1, 2
 OUT_S_TUPLE, OUT_RID_PAIR = 0, 1
+GROUP_HANDLE_BYTES = 256
 
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p
@@ -134,6 +135,15 @@ SIGNATURES = {
     "smjdev_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "smjdev_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "smjdev_ipc_close": (C.c_int, [_vp]),
+    "smjdev_group_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
+    "smjdev_group_export": (C.c_int, [_vp, C.c_char_p]),
+    "smjdev_group_connect": (C.c_int, [_vp, C.c_char_p]),
+    "smjdev_group_join": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(smj_join_stats_t), _u64p]),
+    "smjdev_group_destroy": (C.c_int, [_vp]),
+    "smjdev_join_multi": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(smj_join_stats_t)]),
+    "smjdev_join_multi_release": (C.c_int, []),
+    "smjdev_group_layout_host": (C.c_uint32, [C.c_int, C.c_int, _u64p, C.c_uint32, C.POINTER(C.c_uint32), _u64p, _u64p,
+                                              _u64p, _u64p]),
     "smjdev_check_order": (C.c_int, [_vp, C.c_uint64, C.c_int, _u64p]),
     "smjdev_check_partition": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64,
                                          _u64p]),

@@ -1,6 +1,7 @@
 // smj_common.cuh -- shared helpers for the sm_100a kernels (internal, not part of the ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -205,6 +206,15 @@ __host__ __device__ inline bool smj_msd_plan(const u64 *bits, MsdPlan *p) {
     p->shift2   = p->shift1 - 9;
     p->lo_shift = 32 + (u32)lo;
     return true;
+}
+
+// Capacity of a bin of an optimistic (histogram-free) partition pass from a sample: k of the sampled
+// items fell into the bin, every sampled item stands for `scale` items.  The estimate plus seven
+// standard deviations of the sampling error, rounded up to 16 items.  shrink (tests only) halves it.
+__host__ __device__ inline u64 smj_cap1(u64 k, double scale, int shrink) {
+    u64 cap = (u64)ceil(((double)k + 7.0 * sqrt((double)k + 1.0) + 8.0) * scale);
+    if (shrink) cap = (u64)((double)k * scale * 0.5);  // test hook: bins that cannot hold their items
+    return (cap + 15) & ~15ull;
 }
 
 // The join checksum (DESIGN.md / SURVEY.md 8d): sum over matched pairs of A(r)*B(s) mod 2^64.

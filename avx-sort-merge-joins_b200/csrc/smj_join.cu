@@ -25,37 +25,7 @@
 #include <string.h>
 #include <vector>
 
-int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted);
-int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
-                      u64 **sorted);
-int smj_item_bits(SmjCtx *ctx, const u64 *in, u64 n, u64 *h_bits);
-constexpr u64 SMJ_SMALL_SORT_MAX = 16384;
-int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, const u64 *lens,
-                       u32 nruns, int mode);
-int smj_msd_partition(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u64 *b, u32 shift1, u32 shift2,
-                      u64 *offsets, u64 *exact_bits);
-int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
-                   u32 shift2, u64 *offsets);
-int smj_msd_pass_b_seg(SmjCtx *ctx, const u64 *a, u64 n, u32 nseg, const u64 *d_seg, u64 *b, u32 shift2,
-                       u64 *offsets);
-int smj_msd_hist1(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *hist, u64 *exact_bits);
-int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const *dest_ptrs,
-                       const u64 *dest_offsets);
-int smj_msd_scatter_local(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, const u64 *d_hist512, u64 *out);
-int smj_key_bits_sampled(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *or_and_host);
-int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 max_sectors, u64 *d_st,
-                   u32 *d_sub, u64 *host);
-size_t smj_msd_sample_bytes(int which);
-u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, int shrink);
-int smj_msd_caps1_tables(SmjCtx *ctx, const u64 *d_st, u64 nr, u64 ns, u64 alloc_r, u64 alloc_s, int shrink,
-                         u64 *tab_r, u64 *tab_s, u32 *d_flags);
-u64 smj_msd_alloc2(u64 n);
-int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
-                       u32 kmask, u32 kref, u32 *d_kflag);
-int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *b, u64 alloc2, u32 shift2,
-                       u32 dense_slot, u64 *starts, u64 *ends, u64 *d_counts, u32 *d_flag, u64 *d_nfixed,
-                       int shrink);
-int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
+#include "smj_internal.cuh"
 
 namespace {
 
@@ -373,8 +343,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_mj_fixup(const MjRec *__restrict
 // accumulate count / checksum of R join S into the device pair acc[0..1] (asynchronous)
 // semi != 0: count the S tuples that have a partner in R (merge_join_interpolation semantics);
 // the checksum is only defined for semi == 0
-int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc,
-                       int semi = 0) {
+int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc, int semi) {
     if (nr == 0 || ns == 0) return 0;
     const u64  tiles = div_up(nr + ns, MJ_TILE);
     SmjScratch sc(ctx);
@@ -937,15 +906,11 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
 // Buckets of one relation after the second partitioning level: bucket q is items[starts[q] ..
 // ends[q]).  An exact pass B leaves them back to back (ends = starts + 1 of one offsets array), an
 // optimistic one in fixed slots.
-struct BucketSet {
-    const u64 *items, *starts, *ends;
-    u64        n;
-};
 
 // classification of the 2^18 bucket pairs: heavy ones (more than BIG tuples on a side) are listed
 // for the cooperative kernel; d_state[6] = {count, flag "heavy on both sides"}
 constexpr u64 BJ_BIG = 1u << 16, BJ_RMAX = 1u << 16;
-static int bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u64 *d_state, u32 *d_list) {
+int smj_bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u64 *d_state, u32 *d_list) {
     const u32 nb2 = 512u * 512u;
     SMJ_CHECK(cudaMemsetAsync(d_state + 6, 0, 8, ctx->stream));
     SMJ_LAUNCH(ctx, k_collect_big, nb2 / 256, 256, 0, R.starts, R.ends, S.starts, S.ends, nb2, BJ_BIG, BJ_RMAX,
@@ -959,8 +924,8 @@ static int bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u
 // d_state[6] (bucket_join_valid): a key that is heavy on BOTH sides, or any heavy bucket in a wide
 // key domain (lbits > 10), is left to the general sort + scan path.  d_state[1] is the bucket
 // counter (zero on entry).
-static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
-                       u64 *d_state, u32 *d_list, u64 *acc) {
+int smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
+                    u64 *d_state, u32 *d_list, u64 *acc) {
     const u32 nb2 = 512u * 512u;
     u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
@@ -993,7 +958,7 @@ static int bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 
                R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
     return 0;
 }
-static bool bucket_join_valid(const u64 *h_state, u32 lbits) {
+bool smj_bucket_join_valid(const u64 *h_state, u32 lbits) {
     const u32 nbig = (u32)(h_state[6] & 0xffffffffu), unsupported = (u32)(h_state[6] >> 32);
     return lbits > 10 ? nbig == 0 : unsupported == 0;
 }
@@ -1009,7 +974,7 @@ static bool msd_plan_holds(const u64 *exact, int lo, int hi) {
 // info, [8..11] overflow flags of the optimistic passes {R level 1, S level 1, R level 2, S level 2},
 // [12..13] first-level buckets of R / S whose second level was repeated exactly on the device,
 // [14..15] R / S hold a key outside the sampled key range (optimistic first pass)
-static const u64 MSD_STATE_INIT[16] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull,
+extern const u64 MSD_STATE_INIT[16] = {0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull,
                                        0ull, 0ull, 0ull, 0ull,  0ull, 0ull,  0ull, 0ull};
 
 struct Upload;
@@ -1204,9 +1169,9 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
     *path = (rel[0].opt1 || rel[1].opt1) ? SMJ_PATH_MSD_OPT : SMJ_PATH_MSD;
     u64 h[18];
     for (int attempt = 0;; attempt++) {
-        if ((rc = bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
+        if ((rc = smj_bucket_collect(ctx, rel[0].set(), rel[1].set(), d_state, d_list))) return rc;
         const int t_mid = tm.mark();
-        if ((rc = bucket_join(ctx, rel[0].set(), rel[1].set(), pl.lo_shift, pl.lbits, d_state, d_list, acc)))
+        if ((rc = smj_bucket_join(ctx, rel[0].set(), rel[1].set(), pl.lo_shift, pl.lbits, d_state, d_list, acc)))
             return rc;
         SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
         SMJ_CHECK(cudaMemcpyAsync(h + 16, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1239,7 +1204,7 @@ static int mway_msd(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, Upl
             SMJ_CHECK(cudaMemsetAsync(d_state + 1, 0, 8, ctx->stream));
             continue;
         }
-        ok = ok && !redo && bucket_join_valid(h, pl.lbits);
+        ok = ok && !redo && smj_bucket_join_valid(h, pl.lbits);
         if (!ok) {
             SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
             return 0;
@@ -1511,12 +1476,12 @@ static int join_level1(const uint64_t *r_, const uint64_t *rcounts512, uint32_t 
         }
         const BucketSet R = {bR, offR, offR + 1, nr}, S = {bS, offS, offS + 1, ns};
         u64 h[16];
-        if ((rc = bucket_collect(ctx, R, S, d_state, d_list))) return rc;
+        if ((rc = smj_bucket_collect(ctx, R, S, d_state, d_list))) return rc;
         t_part = tm.mark();
-        if ((rc = bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
+        if ((rc = smj_bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
         SMJ_CHECK(cudaMemcpyAsync(h, d_state, 128, cudaMemcpyDeviceToHost, ctx->stream));
         SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
-        const int done = bucket_join_valid(h, lbits);
+        const int done = smj_bucket_join_valid(h, lbits);
         if (!done) {
             // heavy on both sides: general path on the same items (partitioning does not matter to it)
             u64 *aR = (u64 *)sc.get(nr * 8), *aS = (u64 *)sc.get(ns * 8), *sr = nullptr, *ss = nullptr;

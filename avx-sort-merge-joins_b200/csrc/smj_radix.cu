@@ -1431,11 +1431,6 @@ __global__ void __launch_bounds__(SAMP_THREADS)
 // First-level bin regions from the sampled histogram, on the device (the host computes the same
 // capacities, smj_msd_caps1, to size the buffer): tab[rel] = {cursors, starts, limits} x 512.
 // One CTA per relation.  Raises flag[2 * rel] when the regions do not fit alloc[rel] items.
-__device__ __host__ inline u64 msd_cap1(u64 k, double scale, int shrink) {
-    u64 cap = (u64)ceil(((double)k + 7.0 * sqrt((double)k + 1.0) + 8.0) * scale);
-    if (shrink) cap = (u64)((double)k * scale * 0.5);  // test hook: bins that cannot hold their items
-    return (cap + 15) & ~15ull;
-}
 __global__ void __launch_bounds__(MSD_NB) k_msd_caps1(const u64 *__restrict__ st, u64 nr, u64 ns,
                                                       u64 alloc_r, u64 alloc_s, int shrink,
                                                       u64 *__restrict__ tab_r, u64 *__restrict__ tab_s,
@@ -1446,7 +1441,7 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_caps1(const u64 *__restrict__ st
     u64      *tab = rel ? tab_s : tab_r;
     if (!tab) return;
     const double scale = nsamp ? fmax(1.0, (double)n / (double)nsamp) : 1.0;
-    const u64    cap   = msd_cap1(st[16 + rel * MSD_NB + b], scale, shrink);
+    const u64    cap   = smj_cap1(st[16 + rel * MSD_NB + b], scale, shrink);
     s_c[b]             = cap;
     __syncthreads();
     for (int o = 1; o < MSD_NB; o <<= 1) {
@@ -1727,8 +1722,11 @@ constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB *
 // entries, or null = back to back) where each begins in a.  Every bucket is partitioned by the
 // 9-bit digit at shift2 into b.  offsets (device, 2^18 + 1 entries) receives the start of every
 // second-level bucket in b (and n): bucket q is b[offsets[q] .. offsets[q + 1]).
+// d_n (device, may be null): the exact number of items when n is only an upper bound (multi-GPU
+// join: what a rank received is known on the device only)
 static int msd_pass_b_common(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts,
-                             u32 nseg, const u64 *d_seg, u64 *b, u32 shift2, u64 *offsets) {
+                             u32 nseg, const u64 *d_seg, u64 *b, u32 shift2, u64 *offsets,
+                             const u64 *d_n = nullptr) {
     const u32  NB2 = MSD_NB * MSD_NB;
     SmjScratch sc(ctx);
     u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_bstart = (u64 *)sc.get(MSD_NB * 8);
@@ -1754,13 +1752,18 @@ static int msd_pass_b_common(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_coun
     SMJ_LAUNCH(ctx, k_scan_local, NB2 / 1024, 1024, 0, d_hist2, (u64)NB2, offsets, d_tot);
     SMJ_LAUNCH(ctx, k_scan_add, NB2 / 1024, 1024, 0, offsets, (u64)NB2, d_tot);
     SMJ_CHECK(cudaMemcpyAsync(d_cur2, offsets, (size_t)NB2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (d_n)
+        SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, d_n, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+        SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<false>, grid2, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2,
                d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0, (u32)(ctx->sm_count * 2));
     return 0;
 }
 
+int smj_msd_pass_a_opt(SmjCtx *ctx, const u64 *in, u64 n, u64 *a, u32 shift1, u64 *d_tab, u32 *d_flag,
+                       u32 kmask, u32 kref, u32 *d_kflag);
 int smj_msd_pass_b(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_counts, const u64 *d_starts, u64 *b,
                    u32 shift2, u64 *offsets) {
     return msd_pass_b_common(ctx, a, n, d_counts, d_starts, 0, nullptr, b, shift2, offsets);
@@ -1774,6 +1777,19 @@ int smj_msd_pass_b_seg(SmjCtx *ctx, const u64 *a, u64 n, u32 nseg, const u64 *d_
     if (nseg == 0 || nseg > (u32)SEG_MAX) return smj_fail_msg("smj_msd_pass_b_seg: bad segment count");
     return msd_pass_b_common(ctx, a, n, nullptr, nullptr, nseg, d_seg, b, shift2, offsets);
 }
+// the same with the segment table AND the item count on the device (n_upper bounds the count)
+int smj_msd_pass_b_seg_dev(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 nseg, const u64 *d_seg, const u64 *d_n,
+                           u64 *b, u32 shift2, u64 *offsets) {
+    if (nseg == 0 || nseg > (u32)SEG_MAX) return smj_fail_msg("smj_msd_pass_b_seg: bad segment count");
+    return msd_pass_b_common(ctx, a, n_upper, nullptr, nullptr, nseg, d_seg, b, shift2, offsets, d_n);
+}
+// first-level pass with caller-built tables on the DEVICE: d_tab = {cursors, starts, limits} x 512,
+// cursors / limits are absolute item addresses (pointer / 8 + offset, possibly peer memory)
+int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab, u32 *d_flag, u32 kmask,
+                       u32 kref, u32 *d_kflag) {
+    return smj_msd_pass_a_opt(ctx, in, n, (u64 *)nullptr, shift1, d_tab, d_flag, kmask, kref, d_kflag);
+}
+u64 smj_smj_cap1(u64 k, double scale) { return smj_cap1(k, scale, 0); }
 
 // ---- optimistic passes -------------------------------------------------------------------------
 // Sample of R and S (see k_msd_sample).  host: SMJ_MSD_SAMPLE_WORDS u64.  Synchronises.
@@ -1815,8 +1831,10 @@ int smj_msd_sample(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u32 
         cudaGetLastError();
         return 1;
     }
-    SMJ_CHECK(cudaMemcpyAsync(host, d_st, SAMP_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (host) {
+        SMJ_CHECK(cudaMemcpyAsync(host, d_st, SAMP_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     return 0;
 }
 size_t smj_msd_sample_bytes(int which) {
@@ -1830,7 +1848,7 @@ size_t smj_msd_sample_bytes(int which) {
 u64 smj_msd_caps1(const u64 *hist, u64 nsamp, u64 n, int shrink) {
     const double scale = nsamp ? std::max(1.0, (double)n / (double)nsamp) : 1.0;
     u64          tot   = 0;
-    for (int b = 0; b < MSD_NB; b++) tot += msd_cap1(hist[b], scale, shrink);
+    for (int b = 0; b < MSD_NB; b++) tot += smj_cap1(hist[b], scale, shrink);
     return tot;
 }
 // device tables of both relations (null = relation not partitioned optimistically)

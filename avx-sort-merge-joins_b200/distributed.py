@@ -17,7 +17,9 @@ The per-rank engine is pluggable so that the orchestration (splitters, count exc
 all-to-all, reduction) can be tested on CPU with the gloo backend; the product engine is
 CudaEngine.
 
-Four exchanges, from the simplest to the ones bench.py uses:
+GroupJoin (the default of bench.py --gpus N) is the library's own device-driven exchange
+(csrc/smj_mgpu.cu).  DistributedJoin keeps the four host-orchestrated exchanges of round 1, from
+the simplest to the most fused, as references and fallbacks (SMJ_EXCHANGE=nccl|p2p|msd|dma):
   step          range partition into send regions + NCCL all-to-all (the reference design)
   step_p2p      range partition whose scatter kernel stores straight into the peers' receive
                 buffers (CUDA IPC over NVLink), then the single-GPU join on what arrived
@@ -222,7 +224,15 @@ class P2PExchange:
                     self.ptrs[rel][g] = q.value
                     self.opened.append(q.value)
         self.ptr_table = np.array(self.ptrs, dtype=np.uint64)  # [rel][rank], for vectorised lookups
+        # capacities of ALL ranks: the "does it fit" decision must be the same on every rank
+        capt = torch.tensor(self.cap, dtype=torch.int64, device=engine.device)
+        allc = [torch.empty_like(capt) for _ in range(world)]
+        dist.all_gather(allc, capt)
+        self.all_caps = np.stack([c.cpu().numpy() for c in allc])  # [rank][rel]
         dist.barrier()
+
+    def check_capacity(self, recv_all) -> None:
+        check_capacity(recv_all, self.all_caps)
 
     def close(self):
         lib = self.e.lib
@@ -233,6 +243,56 @@ class P2PExchange:
         for p in self.local:
             lib.smjdev_ipc_free(p)
         self.opened, self.local = [], []
+
+
+def check_capacity(recv_all, all_caps) -> None:
+    """recv_all[rank][rel] = items every rank would receive, all_caps[rank][rel] = what its buffers
+    hold.  Every rank evaluates this on the SAME all-gathered numbers BEFORE any scatter or copy is
+    enqueued, so either nobody writes or everybody does: no rank can store past the end of a peer's
+    buffer while that peer has already given up (and nobody is left waiting in a collective)."""
+    recv_all, all_caps = np.asarray(recv_all, dtype=np.int64), np.asarray(all_caps, dtype=np.int64)
+    bad = np.argwhere(recv_all > all_caps)
+    if bad.size:
+        p, rel = (int(x) for x in bad[0])
+        raise RuntimeError(f"receive buffer of rank {p} too small for relation {'RS'[rel]}: "
+                           f"{int(recv_all[p][rel])} > {int(all_caps[p][rel])} (same verdict on every rank)")
+
+
+class GroupJoin:
+    """The library's join group (csrc/smj_mgpu.cu, smjdev_group_*) with one process per GPU:
+    torch.distributed only carries the 256-byte handles at set-up; a join is ONE C call per rank,
+    with no collective and no host round trip between the sample and the result (samples, counts
+    and results travel through mailboxes in peer memory, the first partitioning pass stores into
+    the owners' buffers over NVLink)."""
+
+    def __init__(self, engine: "CudaEngine", rank: int, world: int, capacity_r: int, capacity_s: int):
+        self.e, self.rank, self.world = engine, rank, world
+        lib, smj = engine.lib, engine.smj
+        self.group = C.c_void_p()
+        smj.check(lib.smjdev_group_create(rank, world, int(capacity_r), int(capacity_s), C.byref(self.group)),
+                  "group_create")
+        h = C.create_string_buffer(smj.GROUP_HANDLE_BYTES)
+        smj.check(lib.smjdev_group_export(self.group, h), "group_export")
+        mine = torch.from_numpy(np.frombuffer(h.raw, dtype=np.uint8).copy()).to(engine.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)  # also: every rank has been created
+        blob = b"".join(t.cpu().numpy().tobytes() for t in allh)
+        smj.check(lib.smjdev_group_connect(self.group, blob), "group_connect")
+        dist.barrier()
+
+    def step(self, r, nr: int, s, ns: int):
+        """-> (global count, global checksum, item bytes this rank sent, stats)"""
+        smj, lib = self.e.smj, self.e.lib
+        st, sent = smj.smj_join_stats_t(), C.c_uint64(0)
+        smj.check(lib.smjdev_group_join(self.group, r.data_ptr(), nr, s.data_ptr(), ns, C.byref(st), C.byref(sent)),
+                  "group_join")
+        return int(st.matches), int(st.checksum), int(sent.value), st
+
+    def close(self):
+        dist.barrier()
+        self.e.lib.smjdev_group_destroy(self.group)
+        self.group = None
+        dist.barrier()
 
 
 def uniform_splitters(maxkey: int, nparts: int) -> np.ndarray:
@@ -291,9 +351,7 @@ class DistributedJoin:
         dist.all_gather(allc, cnt)
         counts = torch.stack(allc).cpu().numpy()  # [src][rel][dst]; the copy synchronises
         offs, recv = p2p_layout(counts, self.rank)
-        for rel in range(2):
-            if int(recv[rel]) > px.cap[rel]:
-                raise RuntimeError(f"receive buffer too small: {int(recv[rel])} > {px.cap[rel]}")
+        px.check_capacity(counts.sum(axis=0).T)  # [dst][rel]: every rank checks EVERY receiver
         for rel, (t, n) in enumerate(((r, nr), (s, ns))):
             dptr = (C.c_void_p * W)(*px.ptrs[rel])
             doff = (C.c_uint64 * W)(*[int(x) for x in offs[rel]])
@@ -327,9 +385,8 @@ class DistributedJoin:
             return self.step_p2p(r, nr, s, ns, self._fallback, px)
         lo, hi, shift1, hist = pre
         owner, offs, mine_counts = msd_layout(hist, self.rank)
-        for rel in range(2):
-            if int(mine_counts[rel].sum()) > px.cap[rel]:
-                raise RuntimeError(f"receive buffer too small: {int(mine_counts[rel].sum())} > {px.cap[rel]}")
+        tot = np.asarray(hist, dtype=np.int64).sum(axis=0)  # [rel][512]
+        px.check_capacity(np.array([[int(tot[rel][owner == p].sum()) for rel in range(2)] for p in range(W)]))
         # ---- 3. pass A of the partition == the exchange
         for rel, (t, n) in enumerate(((r, nr), (s, ns))):
             dptr = np.ascontiguousarray(px.ptr_table[rel][owner])          # 512 destination pointers
@@ -374,10 +431,9 @@ class DistributedJoin:
             return self.step_p2p(r, nr, s, ns, self._fallback, px)
         lo, hi, shift1, hist = pre
         lay = msd_layout_dma(hist, self.rank)
-        for rel in range(2):
-            if lay["recv"][rel] > px.cap[rel]:
-                raise RuntimeError(f"receive buffer too small: {lay['recv'][rel]} > {px.cap[rel]}")
         first = lay["first"]
+        tot = np.asarray(hist, dtype=np.int64).sum(axis=0)
+        px.check_capacity(np.array([[int(tot[rel][first[p]:first[p + 1]].sum()) for rel in range(2)] for p in range(W)]))
         smj.check(lib.smjdev_exchange_begin(), "exchange_begin")
         # rank g sends to g+1, g+2, ... (mod W): at any moment every receiver has one sender
         order = sorted(lay["copies"], key=lambda c: (c[0], (c[1] - self.rank) % W))

@@ -105,6 +105,18 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
     gettimeofday(&start, NULL);
     memset(&dr, 0, sizeof(dr));
     memset(&ds, 0, sizeof(ds));
+    /* SMJ_NGPUS=G: like the reference fans out over NTHREADS workers inside this call
+     * (src/joins/joincommon.c:105-173), the m-way join fans out over G GPUs: one host thread per
+     * GPU takes a contiguous chunk of R and S, the chunks meet over NVLink (csrc/smj_mgpu.cu) */
+    const char *ng = getenv("SMJ_NGPUS");
+    if (algo == SMJ_ALGO_MWAY && ng && atoi(ng) > 1 && relR->num_tuples && relS->num_tuples) {
+        if (smjdev_join_multi(atoi(ng), (const uint64_t *)relR->tuples, relR->num_tuples,
+                              (const uint64_t *)relS->tuples, relS->num_tuples, &st)) {
+            smj_fatal(name);
+            return NULL;
+        }
+        goto have_result;
+    }
     failed = smjdev_init(-1) || smjdev_event_create(&e0) || smjdev_event_create(&e1) ||
              smjdev_event_record(e0) || stage_in(&dr, relR->tuples, relR->num_tuples, 2) ||
              stage_in(&ds, relS->tuples, relS->num_tuples, 2) || smjdev_event_record(e1) ||
@@ -120,6 +132,7 @@ static result_t *join_common(int algo, relation_t *relR, relation_t *relS, joinc
         return NULL;
     }
     if (dr.owned || ds.owned) st.ms_h2d += ms_h2d; /* (pinned relations: measured by smjdev_join) */
+have_result:
     gettimeofday(&end, NULL);
 
     g_last_stats = st;

@@ -41,16 +41,24 @@ def run(args, smj):
     # engines) | p2p (range partition fused with the exchange) | nccl (all-to-all).  Measured on
     # B200 (128M x 128M): N=2 msd 3.11-3.17 ms, dma 3.28 ms; N=8 msd 1.91 ms, dma 2.50 ms.
     # auto: dma when a rank sends at least 1 GB per step (config 5: 12.7 ms against 17.0 ms), else msd
-    mode = os.environ.get("SMJ_EXCHANGE", "auto")
+    # group (default): the library's device-driven exchange, csrc/smj_mgpu.cu
+    mode = os.environ.get("SMJ_EXCHANGE", "group")
     if mode == "auto":
         mode = "dma" if 2 * count * 8 * (world - 1) / world >= 1e9 else "msd"
-    use_p2p = mode != "nccl"
-    px = None
+    use_p2p = mode not in ("nccl", "group")
+    px, gj = None, None
+    cap = int(count * 1.25) + 65536
     if use_p2p:
-        cap = int(count * 1.25) + 65536
         px = dj_mod.P2PExchange(eng, rank, world, cap, cap)
+    if mode == "group":
+        gj = dj_mod.GroupJoin(eng, rank, world, cap, cap)
+    path = [None]
 
     def one_step(rr, ss):
+        if mode == "group":
+            c_, k_, sent_, st_ = gj.step(rr, count, ss, count)
+            path[0] = (int(st_.path), int(st_.repeats))
+            return c_, k_, sent_
         if mode == "dma":
             return dj.step_msd_dma(rr, count, ss, count, px)
         if mode == "msd":
@@ -103,8 +111,12 @@ def run(args, smj):
     clocks = sampler.stop() if sampler else None
     line = _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kernel_ms, prof, clocks,
                  e2e_s, e2e_steps, launches, cnt, cks)
+    if rank == 0 and line is not None and path[0] is not None:
+        line["config"]["group_path"] = {"path": path[0][0], "exact_repeats": path[0][1]}
     if px is not None:
         px.close()
+    if gj is not None:
+        gj.close()
     dist.barrier()
     dist.destroy_process_group()
     return line
@@ -141,7 +153,11 @@ def _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kern
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": B.workload(5 if n == 2_000_000_000 else 1, n),
                        "distribution": f"relations spread evenly over {world} GPUs",
-                       "parallelism": (f"first MSD partitioning pass into a bucket-major send buffer, contiguous bucket "
+                       "parallelism": (f"join group over {world} GPUs (csrc/smj_mgpu.cu): samples / counts / results through "
+                                       f"mailboxes in peer memory, first MSD partitioning pass stores into the bucket owners' "
+                                       f"buffers over NVLink (CUDA IPC), no collective and no host round trip between sample "
+                                       f"and result" if mode == "group" else
+                                       f"first MSD partitioning pass into a bucket-major send buffer, contiguous bucket "
                                        f"ranges copied to their owners over NVLink by the copy engines (overlapping "
                                        f"the scatter of the other relation) over {world} GPUs" if mode == "dma" else
                                        f"first MSD partitioning pass fused with the exchange (the scatter kernel stores "
@@ -159,7 +175,7 @@ def _line(args, rank, world, n, count, mode, use_p2p, ms_step, value, sent, kern
             "clocks": clocks,
             "e2e": ({"value": 2 * n / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": 2 * n * 8,
                      "d2h_bytes_per_step": 16 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                     "api": "DistributedJoin.step on per-rank pinned host slices"} if e2e_steps else
+                     "api": "GroupJoin.step / DistributedJoin.step on per-rank pinned host slices"} if e2e_steps else
                     {"value": None, "unit": B.UNIT, "skipped": "SMJ_BENCH_NO_E2E"}),
             "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "achieved": 40.0 * 2 * n / (ms_step * 1e-3) / 1e9 / world,

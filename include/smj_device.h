@@ -234,6 +234,48 @@ int smjdev_ipc_export(void *dptr, unsigned char *handle64);
 int smjdev_ipc_open(const unsigned char *handle64, void **peer_ptr);
 int smjdev_ipc_close(void *peer_ptr);
 
+/* ------------------------------------------------------------------ join groups ------ */
+/* The m-way join over the G GPUs of one box (csrc/smj_mgpu.cu).  A GROUP has one member ("rank") per
+ * GPU; a member lives in the host thread that is bound to its GPU (smjdev_init) -- one process per
+ * GPU, or one thread per GPU inside one process.  The first partitioning pass of the join is the
+ * exchange: every rank's scatter kernel stores each item into the receive buffer of the GPU that
+ * owns its key bucket over NVLink; samples, counts and results travel through mailboxes in peer
+ * memory, so that no collective library and no host round trip sits between the sample and the
+ * result.  Replaces the fan-out inside sortmergejoin_initrun (src/joins/joincommon.c:105-173) and the
+ * partition pull of src/joins/sortmergejoin_multiway.c:492-517.
+ *   create   allocates this rank's receive buffers (cap_r / cap_s items) and control block
+ *   export   SMJ_GROUP_HANDLE_BYTES describing them (CUDA IPC handles + plain pointers)
+ *   connect  handles of ALL ranks in rank order (world x SMJ_GROUP_HANDLE_BYTES); call it on every
+ *            rank after every rank has been created (ranks of one process: peer access; other
+ *            processes: CUDA IPC)
+ *   join     collective: every rank passes its slices of R and S (device pointers) and receives the
+ *            GLOBAL {matches, checksum}; *bytes_sent = item bytes this rank stored into other GPUs
+ *   destroy  collective as far as the peers' mappings go: call it on every rank */
+#define SMJ_GROUP_HANDLE_BYTES 256
+int smjdev_group_create(int rank, int world, uint64_t cap_r, uint64_t cap_s, void **group);
+int smjdev_group_export(void *group, unsigned char *handle);
+int smjdev_group_connect(void *group, const unsigned char *handles);
+int smjdev_group_join(void *group, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                      smj_join_stats_t *stats, uint64_t *bytes_sent);
+int smjdev_group_destroy(void *group);
+/* One process driving `ngpus` GPUs (what sortmergejoin_multiway() does under SMJ_NGPUS=G): R and S --
+ * host pointers (pinned or pageable) or device pointers -- are cut into G contiguous chunks like
+ * src/joins/joincommon.c:105-139, one host thread per GPU uploads and joins its chunk through a group
+ * that is kept between calls (smjdev_join_multi_release drops it). */
+int smjdev_join_multi(int ngpus, const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
+                      smj_join_stats_t *stats);
+int smjdev_join_multi_release(void);
+/* The group's layout rule as a plain host function (no GPU needed; the CPU tests replay the exchange
+ * with it): posts = world x 1040 words as the ranks publish them ([0..3] sampled OR_R AND_R OR_S AND_S,
+ * [8..9] sampled items of R / S, [10..11] |R| |S| of the rank, [12] the first-level digit shift the rank
+ * derived, [13..14] its buffer capacities, [16..528) / [528..1040) sampled first-level histograms).
+ * Outputs for rank `me`: owner[512]; start[2][512], cap[2][512] = its region of every bucket inside
+ * the owner's buffer; segstart[2][512 * world] = region start of (bucket b, source g) at b * world + g;
+ * need[world][2] = items the layout needs in every rank's buffers.  Returns the status word: 0 = go. */
+uint32_t smjdev_group_layout_host(int world, int me, const uint64_t *posts, uint32_t my_shift1,
+                                  uint32_t *owner, uint64_t *start, uint64_t *cap, uint64_t *segstart,
+                                  uint64_t *need);
+
 /* ------------------------------------------------------------------ verification ----- */
 /* Device-side property checks for arrays that are too large to bring back to the host.
  * check_order: stats[0] = number of positions i with items[i] < items[i-1] (whole word, or key

@@ -191,3 +191,139 @@ def test_msd_exchanges_gloo(tmp_path, world):
                           str(port), str(script)], capture_output=True, text=True, env=env, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == world
+
+
+WORKER_GROUP = textwrap.dedent('''
+    import ctypes as C, importlib, os, sys
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, os.environ["SMJ_ROOT"]); sys.path.insert(0, os.path.join(os.environ["SMJ_ROOT"], "tests"))
+    import oracle_lib as ol
+    smj = importlib.import_module("avx-sort-merge-joins_b200")
+    dj = importlib.import_module("avx-sort-merge-joins_b200.distributed")
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    o = ol.oracle()
+    n = 1 << 20
+    R, S = o.gen_unique(n, 12345), o.gen_fk(n + n // 3, n, 9)
+    expect = o.join_bruteforce(R, S)
+    sl = lambda a: a[(a.size * rank) // world:(a.size * (rank + 1)) // world]
+    loc = [sl(R), sl(S)]
+    POSTW = 16 + 2 * 512
+
+    def make_post(caps, every=4):
+        """what k_msd_sample + k_xg_post_sample publish: here the sample is every 4th item"""
+        p = np.zeros(POSTW, dtype=np.uint64)
+        samp = [a[::every] for a in loc]
+        p[0], p[1] = np.bitwise_or.reduce(samp[0]), np.bitwise_and.reduce(samp[0])
+        p[2], p[3] = np.bitwise_or.reduce(samp[1]), np.bitwise_and.reduce(samp[1])
+        plan = dj.msd_plan(int(p[0]), int(p[1]), int(p[2]), int(p[3]))
+        shift1 = plan[2] if plan else 0
+        p[8], p[9], p[10], p[11], p[12], p[13], p[14] = samp[0].size, samp[1].size, loc[0].size, loc[1].size, shift1, caps[0], caps[1]
+        if shift1:
+            for rel in range(2):
+                d = ((samp[rel] >> np.uint64(shift1)) & np.uint64(511)).astype(np.int64)
+                p[16 + 512 * rel:16 + 512 * (rel + 1)] = np.bincount(d, minlength=512)
+        return p, shift1
+
+    def gather(vec):
+        t = torch.from_numpy(np.ascontiguousarray(vec).view(np.int64).copy())
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return np.stack([x.numpy() for x in out]).view(np.uint64)
+
+    def layout(posts, shift1):
+        owner = np.zeros(512, dtype=np.uint32); start = np.zeros(1024, dtype=np.uint64); cap = np.zeros(1024, dtype=np.uint64)
+        seg = np.zeros(2 * 512 * world, dtype=np.uint64); need = np.zeros(2 * world, dtype=np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        st = smj.lib.smjdev_group_layout_host(world, rank, np.ascontiguousarray(posts).ctypes.data_as(u64p), shift1,
+                                              owner.ctypes.data_as(C.POINTER(C.c_uint32)), start.ctypes.data_as(u64p),
+                                              cap.ctypes.data_as(u64p), seg.ctypes.data_as(u64p), need.ctypes.data_as(u64p))
+        return st, owner, start.reshape(2, 512), cap.reshape(2, 512), seg.reshape(2, 512, world), need.reshape(world, 2)
+
+    capacity = int(1.4 * (n + n // 3) / world) + 65536
+    post, shift1 = make_post((capacity, capacity))
+    posts = gather(post)
+    status, owner, start, cap, seg, need = layout(posts, shift1)
+    assert status == 0, status
+    assert (np.diff(owner.astype(np.int64)) >= 0).all() and owner.max() == world - 1 and owner.min() == 0
+    assert (need <= capacity).all()
+    # every rank computed the same layout: its own regions are the (b, rank) entries of the segment table
+    assert np.array_equal(start, seg[:, :, rank])
+    # regions of one owner are disjoint and back to back in (bucket, source) order
+    for rel in range(2):
+        for p in range(world):
+            bs = np.nonzero(owner == p)[0]
+            flat = seg[rel, bs, :].reshape(-1).astype(np.int64)
+            assert flat[0] == 0 and (np.diff(flat) >= 0).all() and flat[-1] <= need[p][rel]
+    # ---- replay the exchange: rank g 'stores' its items of bucket b at start[rel][b] of the owner's buffer
+    digit = lambda a: ((a >> np.uint64(shift1)) & np.uint64(511)).astype(np.int64)
+    SENT = np.iinfo(np.int64).min
+    bufs = [np.full(int(need[rank][rel]), SENT, dtype=np.int64) for rel in range(2)]
+    for g in range(world):
+        for rel in range(2):
+            for p in range(world):
+                if g == rank:
+                    d = digit(loc[rel])
+                    pieces = [(int(start[rel][b]), loc[rel][d == b]) for b in np.nonzero(owner == p)[0]]
+                    for off, items in pieces:
+                        assert items.size <= int(cap[rel][int(digit(items[:1])[0])]) if items.size else True  # fits its region
+                    if p == rank:
+                        for off, items in pieces:
+                            bufs[rel][off:off + items.size] = items.view(np.int64)
+                    else:
+                        cat = np.concatenate([it for _, it in pieces]) if pieces else np.zeros(0, dtype=np.uint64)
+                        hdr = np.array([x for off, it in pieces for x in (off, it.size)], dtype=np.int64)
+                        dist.send(torch.tensor([hdr.size, cat.size], dtype=torch.int64), dst=p)
+                        if hdr.size: dist.send(torch.from_numpy(hdr), dst=p)
+                        if cat.size: dist.send(torch.from_numpy(cat.view(np.int64).copy()), dst=p)
+                elif p == rank:
+                    k = torch.zeros(2, dtype=torch.int64); dist.recv(k, src=g)
+                    hdr = torch.zeros(int(k[0]), dtype=torch.int64); cat = torch.zeros(int(k[1]), dtype=torch.int64)
+                    if int(k[0]): dist.recv(hdr, src=g)
+                    if int(k[1]): dist.recv(cat, src=g)
+                    pos = 0
+                    for off, cnt in hdr.numpy().reshape(-1, 2):
+                        assert (bufs[rel][off:off + cnt] == SENT).all()       # nobody else wrote here
+                        bufs[rel][off:off + cnt] = cat.numpy()[pos:pos + cnt]; pos += cnt
+    got = [b[b != SENT].view(np.uint64) for b in bufs]
+    for rel in range(2):  # what arrived belongs to this rank's buckets
+        assert (owner[digit(got[rel])] == rank).all()
+    cnt, cks = o.join_bruteforce(got[0], got[1])
+    res = torch.from_numpy(np.array([cnt, cks], dtype=np.uint64).view(np.int64).copy())
+    dist.all_reduce(res)
+    assert tuple(int(x) for x in res.numpy().view(np.uint64)) == expect
+    # ---- verdicts that must be the same on every rank
+    small, _ = make_post((1000, 1000))                       # buffers too small for the layout
+    st2 = layout(gather(small), shift1)[0]
+    assert st2 & 2, st2
+    odd = post.copy(); odd[12] = shift1 + (1 if rank == 0 else 0)   # rank 0 derived another digit
+    st3 = layout(gather(odd), int(odd[12]))[0]
+    assert st3 & 1, st3
+    try:                                                      # ADVICE r1: capacity checks are global
+        dj.check_capacity(np.array([[10, 10]] * (world - 1) + [[10, 99]]), np.full((world, 2), 50))
+        raise SystemExit("check_capacity did not raise")
+    except RuntimeError as exc:
+        assert f"rank {world - 1}" in str(exc)
+    dist.barrier(); dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_group_layout_gloo(tmp_path, world):
+    """The join group's layout rule (csrc/smj_mgpu.cu: k_xg_layout, here through its host twin
+    smjdev_group_layout_host) across real processes: every rank publishes its sample, all compute
+    the layout from the same posts, the scatter into per-(bucket, source) regions is replayed with
+    gloo sends; regions must be disjoint, what arrives must be exactly the owner's buckets, the
+    per-rank joins must add up to the global join, and capacity / plan disagreements must give the
+    same verdict on every rank."""
+    script = tmp_path / "worker_group.py"
+    script.write_text(WORKER_GROUP)
+    env = dict(os.environ, SMJ_ROOT=ROOT, OMP_NUM_THREADS="1")
+    port = 29620 + world
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
+                          str(port), str(script)], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == world
