@@ -20,6 +20,7 @@
 #include <vector>
 
 int smj_msd_sort(SmjCtx *ctx, const u64 *in, u64 n, u64 *out, int *used);
+int smj_kway_merge(SmjCtx *ctx, u64 *out, const u64 *const *runs, const u64 *lens, u32 nruns, int *used);
 
 namespace {
 
@@ -175,6 +176,27 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
     for (u32 i = 0; i < nruns; i++)
         if (lens[i]) cur.push_back({runs[i], lens[i]});
     if (cur.empty()) return 0;
+    // Whole-word order, 3 .. 256 runs: ONE pass over DRAM (smj_kway.cu: value-range tiles from regular
+    // samples, every tile gathered, sorted in shared memory and written once); it declines tiny inputs
+    // and inputs with piles of equal words.  SMJ_MERGE_PATH=rounds | sort selects the older paths.
+    {
+        const char *env = getenv("SMJ_MERGE_PATH");
+        bool inplace = false;  // a run inside out would be overwritten while other tiles still read it
+        u64  total   = 0;
+        for (const Run &r : cur) total += r.n;
+        for (const Run &r : cur) inplace |= (r.p < out + total && r.p + r.n > out);
+        if (mode == 0 && !env && !inplace) {
+            std::vector<const u64 *> ps;
+            std::vector<u64>         ls;
+            for (const Run &r : cur) {
+                ps.push_back(r.p);
+                ls.push_back(r.n);
+            }
+            int used = 0, rc = smj_kway_merge(ctx, out, ps.data(), ls.data(), (u32)cur.size(), &used);
+            if (rc) return rc;
+            if (used) return 0;
+        }
+    }
     // Many runs, whole-word order, large total: the merged sequence is the sorted union of the runs
     // (ties are bit-identical items), and range-partitioning the union MSD-first (smj_msdsort.cu,
     // 48 B/item) moves fewer bytes than log2(k) merge-path rounds (16 B/item each) from 8 runs on:

@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(32) k_xg_post_result(const XgPeers *__restrict
         if (d_state) {  // heavy buckets the fused join does not cover (smj_bucket_join_valid)
             const u32 nbig = (u32)(d_state[6] & 0xffffffffu), unsupported = (u32)(d_state[6] >> 32);
             if (lbits > 10 ? nbig != 0 : unsupported != 0) status |= ST_HEAVY;
+            if (d_state[10] | d_state[11]) status |= ST_OVERFLOW;  // a second-level slot overflowed
         }
         ctl->res[me][0] = acc[0];
         ctl->res[me][1] = acc[1];
@@ -534,9 +535,12 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     u32 *d_sub = (u32 *)sc.get(smj_msd_sample_bytes(1));
     u64 *d_state = (u64 *)sc.get(128), *acc = (u64 *)sc.get(16);
     u32 *d_list = (u32 *)sc.get((size_t)nb2 * 4);
-    u64 *bR = (u64 *)sc.get(g->cap[0] * 8), *bS = (u64 *)sc.get(g->cap[1] * 8);
+    // (second-level output: sized for the optimistic slots, smj_msd_alloc2 >= capacity)
+    const u64 alloc2[2] = {smj_msd_alloc2(g->cap[0]), smj_msd_alloc2(g->cap[1])};
+    u64 *bR = (u64 *)sc.get(alloc2[0] * 8), *bS = (u64 *)sc.get(alloc2[1] * 8);
     u64 *offR = (u64 *)sc.get((size_t)(nb2 + 1) * 8), *offS = (u64 *)sc.get((size_t)(nb2 + 1) * 8);
-    if (!d_st || !d_sub || !d_state || !acc || !d_list || !bR || !bS || !offR || !offS)
+    u64 *endR = (u64 *)sc.get((size_t)nb2 * 8), *endS = (u64 *)sc.get((size_t)nb2 * 8);
+    if (!d_st || !d_sub || !d_state || !acc || !d_list || !bR || !bS || !offR || !offS || !endR || !endS)
         return smj_fail_msg("smjdev_group_join: out of device memory");
     SMJ_CHECK(cudaMemcpyAsync(d_state, MSD_STATE_INIT, 128, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
@@ -559,29 +563,61 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     // ---- 2. + 3. all-gather of the samples through the mailboxes, layout
     SMJ_LAUNCH(ctx, k_xg_post_sample, W, 256, 0, g->d_peers, me, d_st, nr, ns, (u64)shift1, g->cap[0], g->cap[1], epoch);
     SMJ_LAUNCH(ctx, k_xg_layout, 1, XG_NB, 0, g->d_peers, g->ctl, me, W, epoch, shift1, g->d_lay);
-    // ---- 4. pass A == the exchange, R then S
+    // ---- 4. pass A == the exchange, R then S (main stream); 5. owner side: pass B over the received
+    // segments.  Pass B of R only needs every rank's R scatter: it runs on the second compute stream
+    // while pass A of S is still pushing S over NVLink (SMJ_XG_OVERLAP=0: everything on one stream).
     const u64 *in[2] = {r, s};
     const u64  nn[2] = {nr, ns};
+    const u32  nseg = (u32)(XG_NB * W);
+    u64       *recv[2] = {g->recv[0], g->recv[1]}, *bb[2] = {bR, bS}, *off[2] = {offR, offS};
+    const u32  shift2 = have_plan ? pl.shift2 : 32u;
+    const char *e_tile = getenv("SMJ_XG_TILE"), *e_ovl = getenv("SMJ_XG_OVERLAP");
+    const int  big_tile = e_tile ? atoi(e_tile) >= 16384 : (W > 1);
+    const bool overlap  = (e_ovl ? atoi(e_ovl) != 0 : (W > 1)) && !ctx->profiling;
+    cudaEvent_t ev_lay = smj_pool_event(ctx, 0), ev_aux = smj_pool_event(ctx, 1);
+    if (!ev_lay || !ev_aux) return smj_fail_msg("smjdev_group_join: cudaEventCreate failed");
+    cudaStream_t main_stream = ctx->stream;
+    // Like the single-GPU path, the second level runs without a histogram (equal slots per bucket)
+    // only for relations whose sample shows no duplicate keys; a slot that overflows raises the
+    // status (level-2 flag of d_state) and the join is repeated exactly.  SMJ_XG_EXACT_B=1: always
+    // histogram + scatter.
+    u64       *ends[2] = {endR, endS};
+    const bool no_opt2 = getenv("SMJ_XG_EXACT_B") != nullptr;
+    const bool opt2[2] = {have_plan && !no_opt2 && samp[6] <= 16, have_plan && !no_opt2 && samp[7] <= 16};
+    auto owner_side = [&](int rel) -> int {
+        SMJ_LAUNCH(ctx, k_xg_segs, 1, XG_NB, 0, g->ctl, me, W, rel, epoch, g->d_lay);
+        if (opt2[rel])
+            return smj_msd_pass_b_opt_seg(ctx, recv[rel], g->cap[rel], (u32)W, g->d_lay->seg[rel], bb[rel], alloc2[rel],
+                                          shift2, 1u << pl.lbits, off[rel], ends[rel], flags + 4 + 2 * rel);
+        return smj_msd_pass_b_seg_dev(ctx, recv[rel], g->cap[rel], nseg, g->d_lay->seg[rel], &g->d_lay->n_recv[rel],
+                                      bb[rel], shift2, off[rel]);
+    };
+    if (overlap) SMJ_CHECK(cudaEventRecord(ev_lay, main_stream));
     for (int rel = 0; rel < 2; rel++) {
         if (have_plan && nn[rel] &&
             (rc = smj_msd_pass_a_abs(ctx, in[rel], nn[rel], shift1, &g->d_lay->tab[rel][0][0], flags + 2 * rel, kmask, kref,
-                                     flags + 12 + 2 * rel)))
+                                     flags + 12 + 2 * rel, big_tile)))
             return rc;
         SMJ_LAUNCH(ctx, k_xg_post_counts, W, XG_NB, 0, g->d_peers, me, rel, g->d_lay, flags + 2 * rel,
                    flags + 12 + 2 * rel, epoch);
+        if (rel == 0 && overlap) {
+            // (scratch of this call was allocated on the main stream before ev_lay)
+            SMJ_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ev_lay, 0));
+            ctx->stream = ctx->aux_stream;
+            rc          = owner_side(0);
+            cudaError_t e = cudaEventRecord(ev_aux, ctx->aux_stream);
+            ctx->stream = main_stream;
+            if (rc) return rc;
+            SMJ_CHECK(e);
+        }
     }
-    // ---- 5. owner side: pass B over the received segments, bucket join
-    const u32 nseg = (u32)(XG_NB * W);
-    u64      *recv[2] = {g->recv[0], g->recv[1]}, *bb[2] = {bR, bS}, *off[2] = {offR, offS};
-    const u32 shift2 = have_plan ? pl.shift2 : 32u;
-    for (int rel = 0; rel < 2; rel++) {
-        SMJ_LAUNCH(ctx, k_xg_segs, 1, XG_NB, 0, g->ctl, me, W, rel, epoch, g->d_lay);
-        if ((rc = smj_msd_pass_b_seg_dev(ctx, recv[rel], g->cap[rel], nseg, g->d_lay->seg[rel], &g->d_lay->n_recv[rel],
-                                         bb[rel], shift2, off[rel])))
-            return rc;
-    }
+    if (overlap)
+        SMJ_CHECK(cudaStreamWaitEvent(main_stream, ev_aux, 0));
+    else if ((rc = owner_side(0)))
+        return rc;
+    if ((rc = owner_side(1))) return rc;
     const u32 lo_shift = have_plan ? pl.lo_shift : 32u, lbits = have_plan ? pl.lbits : 1u;
-    const BucketSet R = {bR, offR, offR + 1, g->cap[0]}, S = {bS, offS, offS + 1, g->cap[1]};
+    const BucketSet R = {bR, offR, opt2[0] ? endR : offR + 1, g->cap[0]}, S = {bS, offS, opt2[1] ? endS : offS + 1, g->cap[1]};
     if ((rc = smj_bucket_collect(ctx, R, S, d_state, d_list))) return rc;
     if ((rc = smj_bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
     SMJ_LAUNCH(ctx, k_xg_post_result, W, 32, 0, g->d_peers, me, acc, d_state, lbits, g->d_lay, epoch);
@@ -593,6 +629,9 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));  // host synchronisation 2 of 2
     if (h[2] & ST_TIMEOUT) return smj_fail_msg("smjdev_group_join: a rank of the group did not answer within 4 s");
     if (bytes_sent) *bytes_sent = h[3];
+    if (h[2] != 0 && getenv("SMJ_VERBOSE"))
+        fprintf(stderr, "[smj_b200] group join, rank %d: status 0x%llx (1 plan, 2 capacity, 4 region overflow, 8 key range, "
+                "16 heavy bucket) -> exact repeat\n", me, (unsigned long long)h[2]);
     if (h[2] != 0 || getenv("SMJ_GROUP_EXACT")) {
         // what the sample could not promise: all ranks saw the same status and repeat exactly
         sc.release();

@@ -1204,46 +1204,55 @@ __global__ void __launch_bounds__(256) k_msd_tile_table(const u64 *__restrict__ 
 // bucket bucket[i].  A bucket may come in several segments (multi-GPU: one per source rank).
 // One CTA; seg = {start[nseg], count[nseg], bucket[nseg]}; ntiles_at[MSD_NB] receives the total.
 constexpr int SEG_THREADS = 1024, SEG_PER = 8, SEG_MAX = SEG_THREADS * SEG_PER;
+// Segment q (q = thread * SEG_PER + i would serialise every thread over consecutive segments and their
+// tiles; instead) is handled by thread q % 1024 in round q / 1024, so that loads are coalesced, and
+// the tile entries are written by a flat loop over the TILES (tile -> segment by binary search in the
+// shared-memory prefix array), so that the stores are coalesced too: 49 -> ~10 us for 4096 segments.
 __global__ void __launch_bounds__(SEG_THREADS) k_msd_seg_tiles(const u64 *__restrict__ seg, u32 nseg,
                                                                MsdTile *__restrict__ tiles,
                                                                u64 *__restrict__ ntiles_at) {
-    __shared__ u64 s_w[SEG_THREADS / 32];
-    u64 t[SEG_PER], sum = 0;
-#pragma unroll
-    for (int q = 0; q < SEG_PER; q++) {
-        const u32 i = threadIdx.x * SEG_PER + q;
-        t[q]        = i < nseg ? (seg[nseg + i] + MSD_TILE - 1) / MSD_TILE : 0;
-        sum += t[q];
-    }
-    u64       incl = sum;
+    __shared__ u32 s_pre[SEG_MAX + 1];  // exclusive prefix of the tile counts
+    __shared__ u32 s_w[SEG_THREADS / 32];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32       carry = 0;
+    for (u32 base = 0; base < nseg; base += SEG_THREADS) {
+        const u32 i = base + threadIdx.x;
+        const u32 t = i < nseg ? (u32)((seg[nseg + i] + MSD_TILE - 1) / MSD_TILE) : 0u;
+        u32       incl = t;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 v = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
-        if (lane >= (u32)o) incl += v;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    u64 excl = incl - sum, total = 0;
-    for (u32 w = 0; w < SEG_THREADS / 32; w++) {
-        if (w < warp) excl += s_w[w];
-        total += s_w[w];
-    }
-    if (threadIdx.x == 0) ntiles_at[MSD_NB] = total;
-#pragma unroll
-    for (int q = 0; q < SEG_PER; q++) {
-        const u32 i = threadIdx.x * SEG_PER + q;
-        if (i < nseg) {
-            const u64 start = seg[i], count = seg[nseg + i];
-            for (u64 k = 0; k < t[q]; k++) {
-                MsdTile e;
-                e.start  = start + k * MSD_TILE;
-                e.bucket = (u32)seg[2 * nseg + i];
-                e.valid  = (u32)min((u64)MSD_TILE, count - k * MSD_TILE);
-                tiles[excl + k] = e;
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 v = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += v;
         }
-        excl += t[q];
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u32 excl = incl - t + carry, tot = 0;
+        for (u32 w = 0; w < SEG_THREADS / 32; w++) {
+            if (w < warp) excl += s_w[w];
+            tot += s_w[w];
+        }
+        if (i < nseg) s_pre[i] = excl;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        s_pre[nseg]       = carry;
+        ntiles_at[MSD_NB] = carry;
+    }
+    __syncthreads();
+    const u32 total = s_pre[nseg];
+    for (u32 f = threadIdx.x; f < total; f += SEG_THREADS) {
+        u32 lo = 0, hi = nseg;  // s_pre[lo] <= f < s_pre[hi]
+        while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if (s_pre[mid] <= f) lo = mid; else hi = mid;
+        }
+        const u64 k = f - s_pre[lo], start = seg[lo], count = seg[nseg + lo];
+        MsdTile   e;
+        e.start  = start + k * MSD_TILE;
+        e.bucket = (u32)seg[2 * nseg + lo];
+        e.valid  = (u32)min((u64)MSD_TILE, count - k * MSD_TILE);
+        tiles[f] = e;
     }
 }
 
@@ -1463,6 +1472,11 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_caps1(const u64 *__restrict__ st
 // so every slot starts on a 32-byte sector).  CTA b redoes the (cheap) scans and writes the slot
 // starts and initial cursors of bucket b's sub-buckets; CTA 0 also writes the per-bucket arrays.
 // Raises *flag and plans no tiles when the slots do not fit alloc2 items.
+// SEG = false: bucket b lies contiguously at tab1's start (one optimistic pass A on this GPU).
+// SEG = true: bucket b is the `world` segments b * world .. of seg = {start[nseg], count[nseg],
+// bucket[nseg]} (the regions the ranks of a join group filled); the tile table then comes from
+// k_msd_seg_tiles and tab1 / tiles / tile_prefix are not used.
+template <bool SEG>
 __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restrict__ tab1, u64 alloc2,
                                                             u32 dense_slot,
                                                             u64 *__restrict__ tile_prefix,
@@ -1471,11 +1485,18 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restric
                                                             u64 *__restrict__ base2,
                                                             u64 *__restrict__ starts,
                                                             u64 *__restrict__ cursors,
-                                                            MsdTile *__restrict__ tiles, u32 *flag) {
+                                                            MsdTile *__restrict__ tiles, u32 *flag,
+                                                            const u64 *__restrict__ seg, u32 world) {
     __shared__ u64 s_t[MSD_NB], s_c[MSD_NB], s_d[MSD_NB], s_cap[MSD_NB], s_cnt1[MSD_NB];
     const int b   = threadIdx.x;
-    const u64 st1 = tab1[MSD_NB + b];
-    const u64 c   = min(tab1[b] - st1, tab1[2 * MSD_NB + b] - st1);
+    u64 c = 0;
+    if (SEG) {
+        const u32 nseg = MSD_NB * world;
+        for (u32 g = 0; g < world; g++) c += seg[nseg + (u32)b * world + g];
+    } else {
+        const u64 st1 = tab1[MSD_NB + b];
+        c             = min(tab1[b] - st1, tab1[2 * MSD_NB + b] - st1);
+    }
     const u64 t   = (c + MSD_TILE - 1) / MSD_TILE;
     const u64 avg = (c + MSD_NB - 1) / MSD_NB;
     u64       cap = c ? ((avg + (u64)ceil(7.0 * sqrt((double)avg + 1.0)) + 8 + 3) & ~3ull) : 0ull;
@@ -1506,12 +1527,13 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restric
     __syncthreads();
     const bool fits = s_c[MSD_NB - 1] <= alloc2;
     if (blockIdx.x == 0) {
-        tile_prefix[b]  = fits ? s_t[b] - t : 0;
+        if (!SEG) tile_prefix[b] = fits ? s_t[b] - t : 0;
         bucket_count[b] = c;
         cap2[b]         = cap;
         base2[b]        = s_c[b] - cap * MSD_NB;
         if (b == MSD_NB - 1) {
-            tile_prefix[MSD_NB] = fits ? s_t[b] : 0;
+            if (!SEG) tile_prefix[MSD_NB] = fits ? s_t[b] : 0;
+            if (SEG && !fits) tile_prefix[MSD_NB] = 0;  // (k_msd_seg_tiles ran before: plan no tiles)
             if (!fits) *flag = 1u;
         }
     }
@@ -1519,7 +1541,7 @@ __global__ void __launch_bounds__(MSD_NB) k_msd_level2_plan(const u64 *__restric
     const u64 v     = s_c[blockIdx.x] - mycap * MSD_NB + (u64)b * mycap;
     starts[blockIdx.x * MSD_NB + b]  = v;
     cursors[blockIdx.x * MSD_NB + b] = v;
-    if (fits) {
+    if (!SEG && fits) {
         const u64 mycnt = s_cnt1[blockIdx.x], myt = (mycnt + MSD_TILE - 1) / MSD_TILE;
         msd_write_tiles(tiles, blockIdx.x, s_t[blockIdx.x] - myt, tab1[MSD_NB + blockIdx.x], mycnt);
     }
@@ -1785,9 +1807,18 @@ int smj_msd_pass_b_seg_dev(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 nseg, con
 }
 // first-level pass with caller-built tables on the DEVICE: d_tab = {cursors, starts, limits} x 512,
 // cursors / limits are absolute item addresses (pointer / 8 + offset, possibly peer memory)
+// big_tile: tiles of 16384 items (one CTA of 1024 threads per SM) instead of 8192: a (tile, bin) run
+// is then 256 bytes on average instead of 128.  Into local HBM the smaller tile is faster (two CTAs
+// per SM overlap their phases); into PEER memory the pass is bound by NVLink, whose packets carry up
+// to 256 bytes, and the longer runs cross it faster.
 int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab, u32 *d_flag, u32 kmask,
-                       u32 kref, u32 *d_kflag) {
-    return smj_msd_pass_a_opt(ctx, in, n, (u64 *)nullptr, shift1, d_tab, d_flag, kmask, kref, d_kflag);
+                       u32 kref, u32 *d_kflag, int big_tile) {
+    if (n == 0) return 0;
+    FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
+    const LimitArray lim = {d_tab + 2 * MSD_NB, d_flag, kmask, kref, d_kflag};
+    if (big_tile)
+        return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
+    return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
 }
 u64 smj_smj_cap1(u64 k, double scale) { return smj_cap1(k, scale, 0); }
 
@@ -1904,8 +1935,8 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     const unsigned max_tiles = (unsigned)(n / MSD_TILE + MSD_NB);
     MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
     if (!d_tiles) return smj_fail_msg("smj_msd_pass_b_opt: scratch allocation failed");
-    SMJ_LAUNCH(ctx, k_msd_level2_plan, MSD_NB, MSD_NB, 0, d_tab, alloc2, dense_slot, d_tpref, d_counts, d_cap2, d_base2,
-               starts, ends, d_tiles, d_flag);
+    SMJ_LAUNCH(ctx, k_msd_level2_plan<false>, MSD_NB, MSD_NB, 0, d_tab, alloc2, dense_slot, d_tpref, d_counts, d_cap2,
+               d_base2, starts, ends, d_tiles, d_flag, (const u64 *)nullptr, 0u);
     const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 4, max_tiles);
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
@@ -1915,6 +1946,40 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,
                d_bflag, f2, ends);
+    return 0;
+}
+
+// Optimistic pass B over SEGMENTS (join group): first-level bucket b = the `world` segments b * world ..
+// of d_seg = {start[nseg], count[nseg], bucket[nseg]}, nseg = 512 * world, all on the device; a holds
+// them, n_upper bounds the item count.  Every bucket goes into 512 equal slots of b (alloc2 items),
+// no histogram.  A bucket whose slot overflowed cannot be repaired in place here (its items are not
+// contiguous): *d_flag is raised instead -- also when the slots do not fit alloc2 -- and the caller
+// repeats exactly.  starts / ends: 2^18 entries each, sub-bucket q is b[starts[q] .. ends[q]).
+__global__ void __launch_bounds__(MSD_NB) k_or_flags(const u32 *__restrict__ bflag, u32 *flag) {
+    if (__syncthreads_or(bflag[threadIdx.x] != 0) && threadIdx.x == 0) *flag = 1u;
+}
+int smj_msd_pass_b_opt_seg(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 world, const u64 *d_seg, u64 *b, u64 alloc2,
+                           u32 shift2, u32 dense_slot, u64 *starts, u64 *ends, u32 *d_flag) {
+    const u32 nseg = (u32)MSD_NB * world;
+    if (world == 0 || nseg > (u32)SEG_MAX) return smj_fail_msg("smj_msd_pass_b_opt_seg: bad segment count");
+    SmjScratch sc(ctx);
+    u64 *d_tpref = (u64 *)sc.get((MSD_NB + 1) * 8), *d_cap2 = (u64 *)sc.get(MSD_NB * 8);
+    u64 *d_base2 = (u64 *)sc.get(MSD_NB * 8), *d_counts = (u64 *)sc.get(MSD_NB * 8);
+    u32 *d_bflag = (u32 *)sc.get(MSD_NB * 4);
+    const unsigned max_tiles = (unsigned)(n_upper / MSD_TILE + nseg);
+    MsdTile *d_tiles = (MsdTile *)sc.get((size_t)max_tiles * sizeof(MsdTile));
+    if (!d_tpref || !d_cap2 || !d_base2 || !d_counts || !d_bflag || !d_tiles)
+        return smj_fail_msg("smj_msd_pass_b_opt_seg: scratch allocation failed");
+    SMJ_CHECK(cudaMemsetAsync(d_bflag, 0, MSD_NB * 4, ctx->stream));
+    FieldFn f2 = {shift2, (u32)MSD_NB - 1};
+    SMJ_LAUNCH(ctx, k_msd_seg_tiles, 1, SEG_THREADS, 0, d_seg, nseg, d_tiles, d_tpref);
+    SMJ_LAUNCH(ctx, k_msd_level2_plan<true>, MSD_NB, MSD_NB, 0, (const u64 *)nullptr, alloc2, dense_slot, d_tpref, d_counts,
+               d_cap2, d_base2, starts, ends, d_tiles, d_flag, d_seg, world);
+    if (msd_scatter2_attr(ctx)) return -1;
+    SMJ_ITEMS(ctx, n_upper);
+    SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
+               d_base2, d_cap2, d_bflag, 0, (u32)(ctx->sm_count * 2));
+    SMJ_LAUNCH(ctx, k_or_flags, 1, MSD_NB, 0, d_bflag, d_flag);
     return 0;
 }
 

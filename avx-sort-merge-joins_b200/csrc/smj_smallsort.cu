@@ -14,81 +14,21 @@
 // passes + bit probe cost for a few thousand items is launch latency, not bandwidth.
 // Stable key-only order (scalarsort twins): the network sorts (key << 32 | position) words, which are
 // unique, and the payloads are gathered at the end.
-#include "smj_common.cuh"
+#include "smj_smemsort.cuh"
 
 namespace {
-constexpr int SS_IPT = 16;
-
-__device__ __forceinline__ void ss_cswap(u64 &a, u64 &b, bool asc) {
-    const bool sw = asc ? (a > b) : (a < b);
-    const u64  t  = sw ? b : a;
-    b             = sw ? a : b;
-    a             = t;
-}
-
 template <bool STABLE_KEY>
 __global__ void __launch_bounds__(1024) k_small_sort(const u64 *__restrict__ in, u64 *__restrict__ out, u32 n) {
     extern __shared__ __align__(16) u64 s_ss[];
     const u32 t = threadIdx.x, T = blockDim.x, total = T * SS_IPT;
-    u64       x[SS_IPT];
-    // coalesced load through shared memory; positions past n hold the largest word
+    // coalesced load into shared memory; positions past n hold the largest word
     for (u32 i = t; i < total; i += T) {
         u64 v = ~0ull;
         if (i < n) v = STABLE_KEY ? ((in[i] & 0xffffffff00000000ull) | i) : in[i];
         s_ss[i] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < SS_IPT; j++) x[j] = s_ss[t * SS_IPT + j];
-    // 1. bitonic network on registers (80 compare-exchanges, all indices static)
-#pragma unroll
-    for (int k = 2; k <= SS_IPT; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < SS_IPT; i++) {
-                const int l = i ^ j;
-                if (l > i) ss_cswap(x[i], x[l], (i & k) == 0);
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < SS_IPT; j++) s_ss[t * SS_IPT + j] = x[j];
-    __syncthreads();
-    // 2. merge rounds: runs of L items -> runs of 2L items.  Runs that lie entirely past n hold only
-    // padding, so the rounds stop as soon as one run covers the input.
-    for (u32 L = SS_IPT; L < total && L < n; L <<= 1) {
-        const u32  base = (t * SS_IPT) / (2 * L) * (2 * L), d = t * SS_IPT - base;
-        const u64 *A = s_ss + base, *B = s_ss + base + L;
-        u32        lo = d > L ? d - L : 0, hi = d < L ? d : L;
-        while (lo < hi) {  // merge path, A first on ties
-            const u32 mid = (lo + hi) >> 1;
-            if (A[mid] <= B[d - 1 - mid])
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        u32 ai = lo, bi = d - lo;
-        u64 av = ai < L ? A[ai] : ~0ull, bv = bi < L ? B[bi] : ~0ull;
-#pragma unroll
-        for (int j = 0; j < SS_IPT; j++) {
-            const bool take_a = bi >= L || (ai < L && av <= bv);
-            x[j]              = take_a ? av : bv;
-            if (take_a) {
-                ai++;
-                av = ai < L ? A[ai] : ~0ull;
-            } else {
-                bi++;
-                bv = bi < L ? B[bi] : ~0ull;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < SS_IPT; j++) s_ss[t * SS_IPT + j] = x[j];
-        __syncthreads();
-    }
-    // 3. write
+    ss_sort_in_smem(s_ss, n);
     for (u32 i = t; i < n; i += T) {
         const u64 v = s_ss[i];
         out[i]      = STABLE_KEY ? in[(u32)v] : v;

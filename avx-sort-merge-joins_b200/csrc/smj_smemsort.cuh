@@ -1,0 +1,78 @@
+// smj_smemsort.cuh -- sort of one shared-memory tile by one CTA (internal).
+//
+// The B200 counterpart of the reference's in-cache sort (src/avxsort/avxsort_core.h:1213-1274
+// inregister_sort_keyval32: sorting network on registers; :2056-2214 avxsort_block: bitonic merges
+// that double the run length): every thread sorts 16 items in registers with a bitonic network,
+// then log2(threads) merge rounds in shared memory double the run length -- a thread owns 16
+// consecutive output positions of a pair of runs, finds its start with a merge-path binary search
+// and merges serially INTO REGISTERS; after a barrier the registers replace the shared-memory
+// contents, so one buffer holds the tile.  Used by k_small_sort (smj_smallsort.cu) and by the tiles
+// of the one-pass k-way merge (smj_kway.cu).
+#pragma once
+#include "smj_common.cuh"
+
+constexpr int SS_IPT = 16;
+
+__device__ __forceinline__ void ss_cswap(u64 &a, u64 &b, bool asc) {
+    const bool sw = asc ? (a > b) : (a < b);
+    const u64  t  = sw ? b : a;
+    b             = sw ? a : b;
+    a             = t;
+}
+
+// s[0 .. blockDim.x * 16) holds the tile, positions >= n hold ~0 (the largest word).  On return
+// s[0 .. n) is ascending.  All threads of the CTA call it; ends with a barrier.
+__device__ __forceinline__ void ss_sort_in_smem(u64 *s, u32 n) {
+    const u32 t = threadIdx.x, total = blockDim.x * SS_IPT;
+    u64       x[SS_IPT];
+#pragma unroll
+    for (int j = 0; j < SS_IPT; j++) x[j] = s[t * SS_IPT + j];
+    // bitonic network on registers (80 compare-exchanges, all indices static)
+#pragma unroll
+    for (int k = 2; k <= SS_IPT; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < SS_IPT; i++) {
+                const int l = i ^ j;
+                if (l > i) ss_cswap(x[i], x[l], (i & k) == 0);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SS_IPT; j++) s[t * SS_IPT + j] = x[j];
+    __syncthreads();
+    // merge rounds: runs of L items -> runs of 2L items.  Runs that lie entirely past n hold only
+    // padding, so the rounds stop as soon as one run covers the input.
+    for (u32 L = SS_IPT; L < total && L < n; L <<= 1) {
+        const u32  base = (t * SS_IPT) / (2 * L) * (2 * L), d = t * SS_IPT - base;
+        const u64 *A = s + base, *B = s + base + L;
+        u32        lo = d > L ? d - L : 0, hi = d < L ? d : L;
+        while (lo < hi) {  // merge path, A first on ties
+            const u32 mid = (lo + hi) >> 1;
+            if (A[mid] <= B[d - 1 - mid])
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        u32 ai = lo, bi = d - lo;
+        u64 av = ai < L ? A[ai] : ~0ull, bv = bi < L ? B[bi] : ~0ull;
+#pragma unroll
+        for (int j = 0; j < SS_IPT; j++) {
+            const bool take_a = bi >= L || (ai < L && av <= bv);
+            x[j]              = take_a ? av : bv;
+            if (take_a) {
+                ai++;
+                av = ai < L ? A[ai] : ~0ull;
+            } else {
+                bi++;
+                bv = bi < L ? B[bi] : ~0ull;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SS_IPT; j++) s[t * SS_IPT + j] = x[j];
+        __syncthreads();
+    }
+}

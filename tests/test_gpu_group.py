@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def _cases(orc):
     rng = np.random.default_rng(31)
-    n = 1 << 21
+    n = 2_000_000  # (not a power of two: a sample that misses the one key with the top bit set is a legitimate repeat)
     lo32 = np.uint64(0xFFFFFFFF)
     yield "unique", orc.gen_unique(n, 12345), orc.gen_unique(n, 54321), True
     yield "fk", orc.gen_unique(n, 1), orc.gen_fk(3 * n + 5, n, 2), True

@@ -606,6 +606,7 @@ def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
     out, tmp = smj.DeviceBuffer(total), smj.DeviceBuffer(total)
     ptrs = (C.c_void_p * nruns)(*[b.ptr for b in bufs])
     lens = (C.c_uint64 * nruns)(*[x.size for x in runs])
+    monkeypatch.setenv("SMJ_MERGE_PATH", "sort")  # (unset: the one-pass k-way merge takes these inputs)
     for path in ("msd", "lsd"):  # lsd: the sort declines, the merge rounds run
         monkeypatch.setenv("SMJ_SORT_PATH", path)
         smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, lens, nruns, 0), "multiway_merge")
@@ -623,6 +624,35 @@ def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
     assert np.array_equal(out.to_host(), exp)
     for b in bufs + [out, tmp, cat]:
         b.free()
+
+
+@pytest.mark.parametrize("nruns", [3, 17, 128, 256, 300])
+def test_kway_merge_one_pass(smj, orc, nruns, monkeypatch):
+    """smjdev_multiway_merge in whole-word order takes the one-pass k-way merge (csrc/smj_kway.cu,
+    the counterpart of avx_multiway_merge, src/merge/avx_multiwaymerge.c:199-338): value-range tiles
+    from regular samples, gathered, sorted in shared memory, written once.  Same output as the
+    oracle for runs of very different lengths, empty runs, heavy duplicates (tiles overflow -> the
+    rounds take over) and more than 256 runs (declined)."""
+    rng = np.random.default_rng(nruns)
+    lens = [int(x) for x in rng.integers(0, 2 * 700_000 // nruns, size=nruns)]
+    lens[0], lens[-1] = 0, 400_000 // nruns * 3 + 5
+    shapes = {
+        "uniform": [np.sort(ol.rand_items(rng, n, 1 << 27)) for n in lens],
+        "narrow": [np.sort(ol.rand_items(rng, n, 50, payload_bits=4)) for n in lens],   # piles of equal words
+        "disjoint": [np.sort(ol.rand_items(rng, n, 1 << 16) + (np.uint64(i) << np.uint64(50))) for i, n in enumerate(lens)],
+    }
+    for name, runs in shapes.items():
+        exp = orc.multiway_merge(runs)
+        bufs = [smj.DeviceBuffer.from_host(x) for x in runs]
+        out, tmp = smj.DeviceBuffer(exp.size), smj.DeviceBuffer(exp.size)
+        ptrs = (C.c_void_p * nruns)(*[b.ptr for b in bufs])
+        ln = (C.c_uint64 * nruns)(*[x.size for x in runs])
+        smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, ln, nruns, 0), name)
+        assert np.array_equal(out.to_host(), exp), name
+        for b, x in zip(bufs, runs):
+            assert np.array_equal(b.to_host(), x), "inputs must stay unmodified"
+        for b in bufs + [out, tmp]:
+            b.free()
 
 
 # ------------------------------------------------------------------------------------ materialisation
