@@ -135,6 +135,8 @@ SIGNATURES = {
     "smjdev_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "smjdev_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "smjdev_ipc_close": (C.c_int, [_vp]),
+    "smjdev_sort_key8b": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "smjdev_join_key8b": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_int, C.POINTER(smj_join_stats_t)]),
     "smjdev_group_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
     "smjdev_group_export": (C.c_int, [_vp, C.c_char_p]),
     "smjdev_group_connect": (C.c_int, [_vp, C.c_char_p]),
@@ -164,6 +166,14 @@ SIGNATURES = {
                                                                  C.POINTER(joinconfig_t)]),
     "sortmergejoin_initrun": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
                                                     C.POINTER(joinconfig_t), _vp]),
+    "sortmergejoin_multiway_key8b": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
+                                                           C.POINTER(joinconfig_t)]),
+    "sortmergejoin_multipass_key8b": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
+                                                            C.POINTER(joinconfig_t)]),
+    "sortmergejoin_mpsm_key8b": (C.POINTER(result_t), [C.POINTER(relation_t), C.POINTER(relation_t),
+                                                       C.POINTER(joinconfig_t)]),
+    "scalarsort_tuples_key8b": (None, [C.POINTER(_vp), C.POINTER(_vp), C.c_uint64]),
+    "merge_join_key8b": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "smj_last_join_stats": (C.c_int, [C.POINTER(smj_join_stats_t)]),
     "merge_join": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "merge_join_interpolation": (C.c_uint64, [_vp, _vp, C.c_uint64, C.c_uint64, _vp]),

@@ -118,13 +118,13 @@ __global__ void __launch_bounds__(KW_THREADS) k_kw_tile(const KwRuns *__restrict
     for (u32 j = warp; j < k; j += KW_THREADS / 32) {
         const u64 *src = runs->p[j] + s_lo[j];
         const u32  len = s_len[j], off = s_off[j];
-        for (u32 i = lane; i < len; i += 32) s_tile[off + i] = ld_stream(src + i);
+        for (u32 i = lane; i < len; i += 32) s_tile[SSP(off + i)] = ld_stream(src + i);
     }
-    for (u32 i = size + tid; i < (u32)KW_CAP; i += KW_THREADS) s_tile[i] = ~0ull;
+    for (u32 i = size + tid; i < (u32)KW_CAP; i += KW_THREADS) s_tile[SSP(i)] = ~0ull;
     __syncthreads();
     ss_sort_in_smem(s_tile, size);
     u64 *dst = out + s_base;
-    for (u32 i = tid; i < size; i += KW_THREADS) st_stream(dst + i, s_tile[i]);
+    for (u32 i = tid; i < size; i += KW_THREADS) st_stream(dst + i, s_tile[SSP(i)]);
 }
 }  // namespace
 
@@ -168,9 +168,9 @@ int smj_kway_merge(SmjCtx *ctx, u64 *out, const u64 *const *runs, const u64 *len
         if (rc) return rc;
     }
     SMJ_LAUNCH(ctx, k_kw_partition, (unsigned)div_up((ntiles + 1) * k, 256), 256, 0, d_runs, k, q, ntiles, sorted, d_pos);
-    if (smj_func_smem(ctx, (const void *)k_kw_tile, (size_t)KW_CAP * 8)) return -1;
+    if (smj_func_smem(ctx, (const void *)k_kw_tile, (size_t)SS_WORDS(KW_CAP) * 8)) return -1;
     SMJ_ITEMS(ctx, total);
-    SMJ_LAUNCH(ctx, k_kw_tile, (unsigned)ntiles, KW_THREADS, (size_t)KW_CAP * 8, d_runs, k, d_pos, out, d_flag);
+    SMJ_LAUNCH(ctx, k_kw_tile, (unsigned)ntiles, KW_THREADS, (size_t)SS_WORDS(KW_CAP) * 8, d_runs, k, d_pos, out, d_flag);
     u32 h_flag = 0;
     SMJ_CHECK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -124,26 +124,6 @@ __global__ void __launch_bounds__(256) k_xg_post(const XgPeers *__restrict__ pee
     if (threadIdx.x == 0) st_release_sys(&ctl->flag[phase][me], epoch);
 }
 
-// phase 0: the sample block + sizes, digit and capacities of this rank
-__global__ void __launch_bounds__(256) k_xg_post_sample(const XgPeers *__restrict__ peers, int me,
-                                                        const u64 *__restrict__ st, u64 nr, u64 ns, u64 shift1,
-                                                        u64 cap_r, u64 cap_s, u64 epoch) {
-    XgCtl *ctl = peers->ctl[blockIdx.x];
-    u64   *dst = ctl->post[me];
-    for (u32 i = threadIdx.x; i < (u32)XG_POSTW; i += blockDim.x) {
-        u64 v = st[i];
-        if (i == PW_NR) v = nr;
-        if (i == PW_NS) v = ns;
-        if (i == PW_SHIFT1) v = shift1;
-        if (i == PW_CAPR) v = cap_r;
-        if (i == PW_CAPS) v = cap_s;
-        dst[i] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(&ctl->flag[0][me], epoch);
-}
-
 __device__ __forceinline__ u64 block_excl_scan_512(u64 v, u64 *s_tmp, u64 *total) {
     const int b = threadIdx.x;
     s_tmp[b]    = v;
@@ -161,11 +141,31 @@ __device__ __forceinline__ u64 block_excl_scan_512(u64 v, u64 *s_tmp, u64 *total
 }
 
 // One CTA of 512 threads, thread b = first-level bucket b.  See the file header, step 3.
+// Launched with `world` CTAs: CTA p first publishes this rank's sample in rank p's mailbox (what
+// k_xg_post_sample does); CTA 0 then goes on to compute the layout.  One launch instead of two.
 __global__ void __launch_bounds__(XG_NB) k_xg_layout(const XgPeers *__restrict__ peers, XgCtl *ctl, int me, int world,
-                                                     u64 epoch, u32 my_shift1, XgLayout *__restrict__ lay) {
+                                                     u64 epoch, u32 my_shift1, XgLayout *__restrict__ lay,
+                                                     const u64 *__restrict__ st, u64 nr, u64 ns, u64 cap_r, u64 cap_s) {
     __shared__ u64 s_tmp[XG_NB], s_p[2][XG_NB + 1];
     __shared__ u32 s_first[XG_MAXW + 1], s_owner[XG_NB], s_status;
     const int b = threadIdx.x;
+    {
+        XgCtl *pc  = peers->ctl[blockIdx.x];
+        u64   *dst = pc->post[me];
+        for (u32 i = threadIdx.x; i < (u32)XG_POSTW; i += blockDim.x) {
+            u64 v = st[i];
+            if (i == PW_NR) v = nr;
+            if (i == PW_NS) v = ns;
+            if (i == PW_SHIFT1) v = my_shift1;
+            if (i == PW_CAPR) v = cap_r;
+            if (i == PW_CAPS) v = cap_s;
+            dst[i] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(&pc->flag[0][me], epoch);
+        if (blockIdx.x != 0) return;
+    }
     if (b == 0) s_status = 0;
     if (b <= XG_MAXW) s_first[b] = XG_NB;
     xg_wait(ctl, 0, epoch, world, &lay->abort);
@@ -322,9 +322,13 @@ __global__ void __launch_bounds__(XG_NB) k_xg_segs(XgCtl *ctl, int me, int world
 }
 
 // this rank's partial result + status to everybody
+__device__ __forceinline__ void xg_reduce(XgCtl *ctl, int me, int world, u64 epoch, u32 *abort, u64 *out);
+// `world` CTAs: CTA p posts to rank p; with reduce_out != null CTA 0 then waits for everybody's
+// result and reduces (one launch instead of two)
 __global__ void __launch_bounds__(32) k_xg_post_result(const XgPeers *__restrict__ peers, int me, const u64 *__restrict__ acc,
                                                        const u64 *__restrict__ d_state, u32 lbits,
-                                                       const XgLayout *__restrict__ lay, u64 epoch) {
+                                                       const XgLayout *__restrict__ lay, u64 epoch, XgCtl *my_ctl,
+                                                       int world, u32 *abort, u64 *reduce_out) {
     XgCtl *ctl = peers->ctl[blockIdx.x];
     if (threadIdx.x == 0) {
         u32 status = lay ? lay->status : 0u;
@@ -340,8 +344,9 @@ __global__ void __launch_bounds__(32) k_xg_post_result(const XgPeers *__restrict
         __threadfence_system();
         st_release_sys(&ctl->flag[3][me], epoch);
     }
+    if (reduce_out && blockIdx.x == 0) xg_reduce(my_ctl, me, world, epoch, abort, reduce_out);
 }
-__global__ void __launch_bounds__(32) k_xg_reduce(XgCtl *ctl, int me, int world, u64 epoch, u32 *abort, u64 *out) {
+__device__ __forceinline__ void xg_reduce(XgCtl *ctl, int me, int world, u64 epoch, u32 *abort, u64 *out) {
     xg_wait(ctl, 3, epoch, world, abort);
     if (threadIdx.x == 0) {
         u64 c = 0, x = 0, st = *abort ? ST_TIMEOUT : 0;
@@ -561,8 +566,8 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     const u32 kmask = ~krange, kref = (u32)((samp[1] & samp[3]) >> 32) & kmask;
     u32 *flags = (u32 *)(d_state + 8);  // [0] R overflow, [2] S overflow, [12] R key, [14] S key (one u64 slot each)
     // ---- 2. + 3. all-gather of the samples through the mailboxes, layout
-    SMJ_LAUNCH(ctx, k_xg_post_sample, W, 256, 0, g->d_peers, me, d_st, nr, ns, (u64)shift1, g->cap[0], g->cap[1], epoch);
-    SMJ_LAUNCH(ctx, k_xg_layout, 1, XG_NB, 0, g->d_peers, g->ctl, me, W, epoch, shift1, g->d_lay);
+    SMJ_LAUNCH(ctx, k_xg_layout, W, XG_NB, 0, g->d_peers, g->ctl, me, W, epoch, shift1, g->d_lay, (const u64 *)d_st, nr, ns,
+               g->cap[0], g->cap[1]);
     // ---- 4. pass A == the exchange, R then S (main stream); 5. owner side: pass B over the received
     // segments.  Pass B of R only needs every rank's R scatter: it runs on the second compute stream
     // while pass A of S is still pushing S over NVLink (SMJ_XG_OVERLAP=0: everything on one stream).
@@ -572,7 +577,7 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     u64       *recv[2] = {g->recv[0], g->recv[1]}, *bb[2] = {bR, bS}, *off[2] = {offR, offS};
     const u32  shift2 = have_plan ? pl.shift2 : 32u;
     const char *e_tile = getenv("SMJ_XG_TILE"), *e_ovl = getenv("SMJ_XG_OVERLAP");
-    const int  big_tile = e_tile ? atoi(e_tile) >= 16384 : (W > 1);
+    const int  big_tile = e_tile ? (atoi(e_tile) >= 16384 ? 1 : atoi(e_tile) == 12288 ? 2 : 0) : (W > 1);
     const bool overlap  = (e_ovl ? atoi(e_ovl) != 0 : (W > 1)) && !ctx->profiling;
     cudaEvent_t ev_lay = smj_pool_event(ctx, 0), ev_aux = smj_pool_event(ctx, 1);
     if (!ev_lay || !ev_aux) return smj_fail_msg("smjdev_group_join: cudaEventCreate failed");
@@ -620,8 +625,8 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     const BucketSet R = {bR, offR, opt2[0] ? endR : offR + 1, g->cap[0]}, S = {bS, offS, opt2[1] ? endS : offS + 1, g->cap[1]};
     if ((rc = smj_bucket_collect(ctx, R, S, d_state, d_list))) return rc;
     if ((rc = smj_bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
-    SMJ_LAUNCH(ctx, k_xg_post_result, W, 32, 0, g->d_peers, me, acc, d_state, lbits, g->d_lay, epoch);
-    SMJ_LAUNCH(ctx, k_xg_reduce, 1, 32, 0, g->ctl, me, W, epoch, &g->d_lay->abort, g->d_lay->out);
+    SMJ_LAUNCH(ctx, k_xg_post_result, W, 32, 0, g->d_peers, me, acc, d_state, lbits, g->d_lay, epoch, g->ctl, W,
+               &g->d_lay->abort, g->d_lay->out);
     u64 h[12];
     SMJ_CHECK(cudaMemcpyAsync(h, g->d_lay->out, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaMemcpyAsync(h + 4, g->d_lay->gbits, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -723,8 +728,7 @@ int xg_fallback(XgGroup *g, const u64 *r, u64 nr, const u64 *s, u64 ns, const u6
     const u64 part[2] = {st.matches, st.checksum};
     SMJ_CHECK(cudaMemcpyAsync(d_res, part, 16, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_LAUNCH(ctx, k_xg_post_result, W, 32, 0, g->d_peers, me, d_res, (const u64 *)nullptr, 0u, (const XgLayout *)nullptr,
-               epoch);
-    SMJ_LAUNCH(ctx, k_xg_reduce, 1, 32, 0, g->ctl, me, W, epoch, &g->d_lay->abort, g->d_lay->out);
+               epoch, g->ctl, W, &g->d_lay->abort, g->d_lay->out);
     u64 h[4];
     SMJ_CHECK(cudaMemcpyAsync(h, g->d_lay->out, 32, cudaMemcpyDeviceToHost, ctx->stream));
     SMJ_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -559,11 +559,15 @@ struct LimitSlots {
     const u64 *base2, *cap2;
     u32        bucket, shrink;
     u32       *flag;
+    u32       *any;  // optional: one word that says "some bucket overflowed"
     __device__ __forceinline__ u64 operator()(u32 b) const {
         const u64 cap = cap2[bucket];
         return base2[bucket] + (u64)b * cap + (shrink ? cap / 4 : cap);
     }
-    __device__ __forceinline__ void raise() const { flag[bucket] = 1u; }
+    __device__ __forceinline__ void raise() const {
+        flag[bucket] = 1u;
+        if (any) *any = 1u;
+    }
     __device__ __forceinline__ u32 key_bad(u64) const { return 0; }
     __device__ __forceinline__ void raise_key() const {}
 };
@@ -1284,7 +1288,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
                    const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
                    u64 *cursors2 /* [512][512] */, const u64 *__restrict__ base2,
-                   const u64 *__restrict__ cap2, u32 *flag, int shrink, u32 pf_dist) {
+                   const u64 *__restrict__ cap2, u32 *flag, int shrink, u32 pf_dist, u32 *any_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = (u64 *)smem_raw;
     u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
@@ -1316,7 +1320,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
         const u64 *nsrc = pre ? in + nx.start : nullptr;
         u64       *cur  = cursors2 + (u64)ti.bucket * MSD_NB;
         Lim        lim;
-        if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, flag};
+        if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, flag, any_flag};
         if (ti.valid == (u32)MSD_TILE) {
             if (!have) unstable_load<MSD_THREADS, MSD_IPT, true>(item, in + ti.start, ti.valid);
             unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim>(
@@ -1780,7 +1784,7 @@ static int msd_pass_b_common(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_coun
         SMJ_CHECK(cudaMemcpyAsync(offsets + NB2, &n, 8, cudaMemcpyHostToDevice, ctx->stream));
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<false>, grid2, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2,
-               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0, (u32)(ctx->sm_count * 2));
+               d_cur2, (const u64 *)nullptr, (const u64 *)nullptr, (u32 *)nullptr, 0, (u32)(ctx->sm_count * 2), (u32 *)nullptr);
     return 0;
 }
 
@@ -1816,6 +1820,8 @@ int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab
     if (n == 0) return 0;
     FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
     const LimitArray lim = {d_tab + 2 * MSD_NB, d_flag, kmask, kref, d_kflag};
+    if (big_tile == 2)  // experiment: 12288-item tiles, two CTAs per SM (register-starved: spills)
+        return launch_unstable_shape<512, 24, 2, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
     if (big_tile)
         return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
     return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
@@ -1941,7 +1947,7 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
     SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
-               d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2));
+               d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2), (u32 *)nullptr);
     SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,
@@ -1955,9 +1961,6 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
 // no histogram.  A bucket whose slot overflowed cannot be repaired in place here (its items are not
 // contiguous): *d_flag is raised instead -- also when the slots do not fit alloc2 -- and the caller
 // repeats exactly.  starts / ends: 2^18 entries each, sub-bucket q is b[starts[q] .. ends[q]).
-__global__ void __launch_bounds__(MSD_NB) k_or_flags(const u32 *__restrict__ bflag, u32 *flag) {
-    if (__syncthreads_or(bflag[threadIdx.x] != 0) && threadIdx.x == 0) *flag = 1u;
-}
 int smj_msd_pass_b_opt_seg(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 world, const u64 *d_seg, u64 *b, u64 alloc2,
                            u32 shift2, u32 dense_slot, u64 *starts, u64 *ends, u32 *d_flag) {
     const u32 nseg = (u32)MSD_NB * world;
@@ -1978,8 +1981,7 @@ int smj_msd_pass_b_opt_seg(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 world, co
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n_upper);
     SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
-               d_base2, d_cap2, d_bflag, 0, (u32)(ctx->sm_count * 2));
-    SMJ_LAUNCH(ctx, k_or_flags, 1, MSD_NB, 0, d_bflag, d_flag);
+               d_base2, d_cap2, d_bflag, 0, (u32)(ctx->sm_count * 2), d_flag);
     return 0;
 }
 

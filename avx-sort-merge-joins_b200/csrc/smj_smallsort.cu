@@ -25,12 +25,12 @@ __global__ void __launch_bounds__(1024) k_small_sort(const u64 *__restrict__ in,
     for (u32 i = t; i < total; i += T) {
         u64 v = ~0ull;
         if (i < n) v = STABLE_KEY ? ((in[i] & 0xffffffff00000000ull) | i) : in[i];
-        s_ss[i] = v;
+        s_ss[SSP(i)] = v;
     }
     __syncthreads();
     ss_sort_in_smem(s_ss, n);
     for (u32 i = t; i < n; i += T) {
-        const u64 v = s_ss[i];
+        const u64 v = s_ss[SSP(i)];
         out[i]      = STABLE_KEY ? in[(u32)v] : v;
     }
 }
@@ -43,13 +43,13 @@ int smj_small_sort(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, bool stable_key)
     if (n > 16384) return smj_fail_msg("smj_small_sort: input too large");
     unsigned threads = 32;
     while ((u64)threads * SS_IPT < n) threads <<= 1;
-    const size_t smem = (size_t)threads * SS_IPT * 8;
+    const size_t smem = (size_t)SS_WORDS(threads * SS_IPT) * 8;
     SMJ_ITEMS(ctx, n);
     if (stable_key) {
-        if (smj_func_smem(ctx, (const void *)k_small_sort<true>, 1024 * SS_IPT * 8)) return -1;
+        if (smj_func_smem(ctx, (const void *)k_small_sort<true>, (size_t)SS_WORDS(1024 * SS_IPT) * 8)) return -1;
         SMJ_LAUNCH(ctx, k_small_sort<true>, 1, threads, smem, in, out, (u32)n);
     } else {
-        if (smj_func_smem(ctx, (const void *)k_small_sort<false>, 1024 * SS_IPT * 8)) return -1;
+        if (smj_func_smem(ctx, (const void *)k_small_sort<false>, (size_t)SS_WORDS(1024 * SS_IPT) * 8)) return -1;
         SMJ_LAUNCH(ctx, k_small_sort<false>, 1, threads, smem, in, out, (u32)n);
     }
     return 0;

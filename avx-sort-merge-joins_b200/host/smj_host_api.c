@@ -740,3 +740,126 @@ uint64_t scalar_multiway_merge_bitand(tuple_t *output, relation_t **parts, uint3
     (void)bufntuples;
     return multiway_common(output, parts, nparts, 1, "scalar_multiway_merge_bitand");
 }
+
+/* ------------------------------------------------------------------------------------------
+ * KEY_8B build: 16-byte tuples {int64 payload; int64 key} (src/types.h:23-29).  Such a build of the
+ * reference runs scalar sort and merge only (src/main.c:871-877); the three join entry points, the
+ * key sort and merge_join are provided here under a _key8b suffix (include/smj_b200_key8b.h maps
+ * the reference's names onto them when KEY_8B is defined).
+ * ---------------------------------------------------------------------------------------- */
+#include "../../include/smj_b200_key8b.h"
+
+static int stage16(devbuf_t *b, const void *p, uint64_t n, int copy) {
+    b->d = NULL;
+    b->owned = 0;
+    if (n == 0) return 0;
+    if (is_device_ptr(p)) {
+        b->d = (uint64_t *)p;
+        return 0;
+    }
+    b->d = (uint64_t *)smjdev_malloc(n * 16);
+    if (!b->d) return -1;
+    b->owned = 1;
+    return copy ? smjdev_upload(b->d, p, n * 16) : 0;
+}
+
+static result_t *join16_common(relation16_t *relR, relation16_t *relS, joinconfig_t *cfg, const char *name) {
+    struct timeval   start, end;
+    devbuf_t         dr, ds;
+    smj_join_stats_t st;
+    int              nthreads = cfg->NTHREADS > 0 ? cfg->NTHREADS : 1;
+    gettimeofday(&start, NULL);
+    memset(&dr, 0, sizeof(dr));
+    memset(&ds, 0, sizeof(ds));
+    int failed = smjdev_init(-1) || stage16(&dr, relR->tuples, relR->num_tuples, 1) ||
+                 stage16(&ds, relS->tuples, relS->num_tuples, 1) ||
+                 smjdev_join_key8b(dr.d, relR->num_tuples, ds.d, relS->num_tuples, 0, &st);
+    stage_free(&dr);
+    stage_free(&ds);
+    if (failed) {
+        smj_fatal(name);
+        return NULL;
+    }
+    gettimeofday(&end, NULL);
+    g_last_stats = st;
+    g_have_stats = 1;
+    result_t *res = (result_t *)malloc(sizeof(result_t));
+    if (res) res->resultlist = (threadresult_t *)calloc((size_t)nthreads, sizeof(threadresult_t));
+    if (!res || !res->resultlist) {
+        free(res);
+        perror("[ERROR] result_t allocation failed");
+        if (!getenv("SMJ_NO_EXIT")) exit(EXIT_FAILURE);
+        return NULL;
+    }
+    for (int i = 0; i < nthreads; i++) res->resultlist[i].threadid = (uint32_t)i;
+    res->resultlist[0].nresults = (int64_t)st.matches;
+    res->totalresults           = (int64_t)st.matches;
+    res->nthreads               = nthreads;
+    if (!quiet()) print_timing(relS->num_tuples, &start, &end, stderr);
+    return res;
+}
+
+result_t *sortmergejoin_multiway_key8b(relation16_t *relR, relation16_t *relS, joinconfig_t *joincfg) {
+    if ((joincfg->NTHREADS & (joincfg->NTHREADS - 1)) != 0) {
+        fprintf(stdout, "[ERROR] m-way sort-merge join runs with a power of 2 #threads.\n");
+        return 0;
+    }
+    return join16_common(relR, relS, joincfg, "sortmergejoin_multiway_key8b");
+}
+result_t *sortmergejoin_multipass_key8b(relation16_t *relR, relation16_t *relS, joinconfig_t *joincfg) {
+    if ((joincfg->NTHREADS & (joincfg->NTHREADS - 1)) != 0) {
+        fprintf(stdout, "[ERROR] m-pass sort-merge join runs with a power of 2 #threads.\n");
+        return 0;
+    }
+    return join16_common(relR, relS, joincfg, "sortmergejoin_multipass_key8b");
+}
+result_t *sortmergejoin_mpsm_key8b(relation16_t *relR, relation16_t *relS, joinconfig_t *joincfg) {
+    return join16_common(relR, relS, joincfg, "sortmergejoin_mpsm_key8b");
+}
+
+/* src/scalarsort/scalarsort.c:41-51 for 16-byte tuples: the INPUT buffer ends up sorted on the key,
+ * the pointers are swapped */
+void scalarsort_tuples_key8b(tuple16_t **inputptr, tuple16_t **outputptr, uint64_t nitems) {
+    tuple16_t *in = *inputptr, *out = *outputptr;
+    if (nitems) {
+        devbuf_t din, dout;
+        memset(&din, 0, sizeof(din));
+        memset(&dout, 0, sizeof(dout));
+        int dev    = is_device_ptr(in);
+        int failed = smjdev_init(-1) || stage16(&din, in, nitems, 1) ||
+                     !(dout.d = (uint64_t *)smjdev_malloc(nitems * 16)) ||
+                     smjdev_sort_key8b(din.d, dout.d, nitems) ||
+                     (dev ? smjdev_memcpy_d2d(in, dout.d, nitems * 16) || smjdev_sync()
+                          : smjdev_download(in, dout.d, nitems * 16));
+        stage_free(&din);
+        smjdev_free(dout.d);
+        if (failed) {
+            smj_fatal("scalarsort_tuples_key8b");
+            return;
+        }
+    }
+    *inputptr  = out;
+    *outputptr = in;
+}
+
+/* src/joins/joincommon.c:239-312 for key-sorted 16-byte tuples */
+uint64_t merge_join_key8b(tuple16_t *rtuples, tuple16_t *stuples, const uint64_t numR, const uint64_t numS,
+                          void *output) {
+    devbuf_t         dr, ds;
+    smj_join_stats_t st;
+    (void)output;
+    if (numR == 0 || numS == 0) return 0;
+    memset(&dr, 0, sizeof(dr));
+    memset(&ds, 0, sizeof(ds));
+    int failed = smjdev_init(-1) || stage16(&dr, rtuples, numR, 1) || stage16(&ds, stuples, numS, 1) ||
+                 smjdev_join_key8b(dr.d, numR, ds.d, numS, 1, &st);
+    stage_free(&dr);
+    stage_free(&ds);
+    if (failed) {
+        smj_fatal("merge_join_key8b");
+        return 0;
+    }
+    g_last_stats = st;
+    g_have_stats = 1;
+    return st.matches;
+}

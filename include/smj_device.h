@@ -234,6 +234,15 @@ int smjdev_ipc_export(void *dptr, unsigned char *handle64);
 int smjdev_ipc_open(const unsigned char *handle64, void **peer_ptr);
 int smjdev_ipc_close(void *peer_ptr);
 
+/* ------------------------------------------------------------------ KEY_8B ----------- */
+/* 16-byte tuples {int64 payload; int64 key} (the reference's KEY_8B build, src/types.h:23-29).
+ * sort: by signed key, equal keys in input order; in != out.  join: count and checksum (64-bit
+ * analogue of the 8-byte checksum, see csrc/smj_key8b.cu) of R join S; presorted != 0 when both
+ * inputs are already key-sorted (merge_join).  Device pointers. */
+int smjdev_sort_key8b(const void *in, void *out, uint64_t n);
+int smjdev_join_key8b(const void *r, uint64_t nr, const void *s, uint64_t ns, int presorted,
+                      smj_join_stats_t *stats);
+
 /* ------------------------------------------------------------------ join groups ------ */
 /* The m-way join over the G GPUs of one box (csrc/smj_mgpu.cu).  A GROUP has one member ("rank") per
  * GPU; a member lives in the host thread that is bound to its GPU (smjdev_init) -- one process per

@@ -683,3 +683,57 @@ void orc_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, dou
     }
     free(own);
 }
+
+/* ------------------------------------------------------------------ KEY_8B (16-byte tuples) -- */
+/* The reference's KEY_8B build (src/types.h:23-29: int64 key and payload; scalar sort and merge
+ * only, src/main.c:871-877): std::sort on the key (scalarsort.c:35-51) and the merge_join loop of
+ * joincommon.c:239-312 over 16-byte tuples.  The checksum is the 64-bit analogue of the 8-byte one:
+ * A(r) = key * 0x9E3779B97F4A7C15 + payload * 0xC2B2AE3D27D4EB4F + 1, B(s) = key * 0x165667B19E3779F9 +
+ * payload * 0x27D4EB2F165667C5 + 1 (wrapping), summed over matched pairs. */
+typedef struct {
+    int64_t payload, key;
+} orc_tup16;
+
+static void orc_sort16_rec(orc_tup16 *a, orc_tup16 *tmp, uint64_t n) { /* stable merge sort on the signed key */
+    if (n < 2) return;
+    const uint64_t h = n / 2;
+    orc_sort16_rec(a, tmp, h);
+    orc_sort16_rec(a + h, tmp, n - h);
+    uint64_t i = 0, j = h, k = 0;
+    while (i < h && j < n) tmp[k++] = (a[j].key < a[i].key) ? a[j++] : a[i++];
+    while (i < h) tmp[k++] = a[i++];
+    while (j < n) tmp[k++] = a[j++];
+    memcpy(a, tmp, n * sizeof(orc_tup16));
+}
+void orc_sort16(void *items, uint64_t n) {
+    orc_tup16 *tmp = (orc_tup16 *)malloc((n ? n : 1) * sizeof(orc_tup16));
+    orc_sort16_rec((orc_tup16 *)items, tmp, n);
+    free(tmp);
+}
+void orc_join16(const void *r_, uint64_t nr, const void *s_, uint64_t ns, uint64_t *count, uint64_t *checksum) {
+    orc_tup16 *r = (orc_tup16 *)malloc((nr ? nr : 1) * sizeof(orc_tup16));
+    orc_tup16 *s = (orc_tup16 *)malloc((ns ? ns : 1) * sizeof(orc_tup16));
+    memcpy(r, r_, nr * sizeof(orc_tup16));
+    memcpy(s, s_, ns * sizeof(orc_tup16));
+    orc_sort16(r, nr);
+    orc_sort16(s, ns);
+    uint64_t i = 0, j = 0, cnt = 0, cks = 0;
+    while (i < nr && j < ns) {
+        if (r[i].key < s[j].key) i++;
+        else if (r[i].key > s[j].key) j++;
+        else {
+            const int64_t k = r[i].key;
+            uint64_t      sa = 0, sb = 0, cr = 0, cs = 0;
+            for (; i < nr && r[i].key == k; i++, cr++)
+                sa += (uint64_t)r[i].key * 0x9E3779B97F4A7C15ull + (uint64_t)r[i].payload * 0xC2B2AE3D27D4EB4Full + 1ull;
+            for (; j < ns && s[j].key == k; j++, cs++)
+                sb += (uint64_t)s[j].key * 0x165667B19E3779F9ull + (uint64_t)s[j].payload * 0x27D4EB2F165667C5ull + 1ull;
+            cnt += cr * cs;
+            cks += sa * sb;
+        }
+    }
+    *count = cnt;
+    *checksum = cks;
+    free(r);
+    free(s);
+}

@@ -80,6 +80,10 @@ void orc_zipf_lut(double *lut, uint32_t A, double theta);
 void orc_gen_zipf(uint64_t *out, uint64_t first, uint64_t count, uint32_t A, double theta, uint64_t seed,
                   uint64_t alphabet_seed, const double *lut);
 void orc_gen_fk_from(uint64_t *out, uint64_t n, const uint64_t *src, uint64_t src_n, uint64_t seed);
+/* KEY_8B build (16-byte tuples {int64 payload; int64 key}, src/types.h:23-29): stable sort on the
+ * signed key; join count + checksum (64-bit analogue of the 8-byte checksum) */
+void orc_sort16(void *items, uint64_t n);
+void orc_join16(const void *r, uint64_t nr, const void *s, uint64_t ns, uint64_t *count, uint64_t *checksum);
 uint64_t orc_cks_a(uint64_t r);
 uint64_t orc_cks_b(uint64_t s);
 #endif

@@ -50,3 +50,12 @@ def refmat():
     if r is None:
         pytest.skip("oracle/_ref/libsmj_ref_mat.so not built (needs /root/reference: make -C oracle ref)")
     return r
+
+
+@pytest.fixture(scope="session")
+def refk8():
+    import oracle_lib
+    r = oracle_lib.reference_key8b()
+    if r is None:
+        pytest.skip("oracle/_ref/libsmj_ref_key8b.so not built (needs /root/reference: make -C oracle ref)")
+    return r

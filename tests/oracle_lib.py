@@ -89,6 +89,8 @@ class Oracle:
         L.orc_join_materialize.restype = C.c_uint64
         L.orc_gen_unique.argtypes = [_vp, C.c_uint64, C.c_uint64]
         L.orc_gen_fk.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_uint64]
+        L.orc_sort16.argtypes = [_vp, C.c_uint64]
+        L.orc_join16.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, _u64p, _u64p]
         L.orc_gen_fk_from.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64]
         L.orc_gen_zipf_ref.argtypes = [_vp, C.c_uint32, C.c_uint32, C.c_double, _vp, _vp]
         L.orc_zipf_weight.argtypes = [C.c_uint32, C.c_double]
@@ -187,6 +189,18 @@ class Oracle:
         out = np.empty(n, dtype=np.uint64)
         self.lib.orc_gen_fk(_p(out), n, maxkey, seed)
         return out
+
+    # KEY_8B: relations are int64 arrays of shape (n, 2) = {payload, key}
+    def sort16(self, t: np.ndarray) -> np.ndarray:
+        out = np.ascontiguousarray(t, dtype=np.int64).copy()
+        self.lib.orc_sort16(_p(out), out.shape[0])
+        return out
+
+    def join16(self, r: np.ndarray, s: np.ndarray):
+        r, s = np.ascontiguousarray(r, dtype=np.int64), np.ascontiguousarray(s, dtype=np.int64)
+        cnt, cks = C.c_uint64(0), C.c_uint64(0)
+        self.lib.orc_join16(_p(r), r.shape[0], _p(s), s.shape[0], C.byref(cnt), C.byref(cks))
+        return cnt.value, cks.value
 
     def gen_fk_from(self, n: int, src: np.ndarray, seed: int) -> np.ndarray:
         src = np.ascontiguousarray(src, dtype=np.uint64)
@@ -484,9 +498,83 @@ class ReferenceMat:
         return total, outs
 
 
+REF_K8_SO = os.path.join(ORACLE_DIR, "_ref", "libsmj_ref_key8b.so")
+
+
+class ReferenceKey8B:
+    """The UNMODIFIED reference compiled with -DKEY_8B (oracle/Makefile `ref`): 16-byte tuples
+    {int64 payload; int64 key}, scalar sort and merge only (src/main.c:871-877)."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_K8_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_K8_SO)
+        self.f = {k: getattr(L, Reference.SYMS[k]) for k in
+                  ("sortmergejoin_multiway", "sortmergejoin_multipass", "numa_shuffle_init", "cpu_mapping_init",
+                   "scalarsort_tuples", "merge_join")}
+        for k in ("sortmergejoin_multiway", "sortmergejoin_multipass"):
+            self.f[k].argtypes = [C.POINTER(_Rel), C.POINTER(_Rel), C.POINTER(_Cfg)]
+            self.f[k].restype = C.POINTER(_Res)
+        self.f["scalarsort_tuples"].argtypes = [C.POINTER(_vp), C.POINTER(_vp), C.c_uint64]
+        self.f["scalarsort_tuples"].restype = None
+        self.f["merge_join"].argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, _vp]
+        self.f["merge_join"].restype = C.c_uint64
+        self.f["numa_shuffle_init"].argtypes = [C.c_int, C.c_int]
+        with silence_stdout():
+            self.f["cpu_mapping_init"]()
+
+    @staticmethod
+    def _aligned(t: np.ndarray, extra_tuples: int) -> np.ndarray:
+        n = t.shape[0]
+        buf = aligned_u64(2 * (n + extra_tuples) + 16)
+        buf[:2 * n] = np.ascontiguousarray(t, dtype=np.int64).reshape(-1).view(np.uint64)
+        return buf
+
+    def join(self, r: np.ndarray, s: np.ndarray, which: str = "sortmergejoin_multiway", nthreads: int = 2,
+             fanout: int = 128) -> int:
+        pad = nthreads * fanout * 8 + 64
+        rr, ss = self._aligned(r, pad), self._aligned(s, pad)
+        relr, rels = _Rel(rr.ctypes.data, r.shape[0]), _Rel(ss.ctypes.data, s.shape[0])
+        cfg = _Cfg(nthreads, fanout, 1, 1, 1 << 22, 2)  # SCALARSORT, SCALARMERGE
+        with silence_all():
+            self.f["numa_shuffle_init"](2, nthreads)
+            res = self.f[which](C.byref(relr), C.byref(rels), C.byref(cfg))
+        return res.contents.totalresults if res else -1
+
+    def sort(self, t: np.ndarray) -> np.ndarray:
+        n = t.shape[0]
+        a, b = self._aligned(t, 8), aligned_u64(2 * n + 32)
+        pa, pb = _vp(a.ctypes.data), _vp(b.ctypes.data)
+        self.f["scalarsort_tuples"](C.byref(pa), C.byref(pb), n)
+        res = a if pb.value == a.ctypes.data else b
+        return res[:2 * n].view(np.int64).reshape(n, 2).copy()
+
+    def merge_join(self, r: np.ndarray, s: np.ndarray) -> int:
+        rr, ss = self._aligned(r, 8), self._aligned(s, 8)
+        return self.f["merge_join"](rr.ctypes.data, ss.ctypes.data, r.shape[0], s.shape[0], None)
+
+
+def rand_tuples16(rng: np.random.Generator, n: int, key_lo: int, key_hi: int) -> np.ndarray:
+    """(n, 2) int64 {payload, key}: keys uniform in [key_lo, key_hi], payloads any int64"""
+    t = np.empty((n, 2), dtype=np.int64)
+    t[:, 0] = rng.integers(-2**62, 2**62, size=n, dtype=np.int64)
+    t[:, 1] = rng.integers(key_lo, key_hi + 1, size=n, dtype=np.int64)
+    return t
+
+
 _ORACLE = None
 _REF = None
 _REF_MAT = None
+_REF_K8 = None
+
+
+def reference_key8b() -> "ReferenceKey8B | None":
+    global _REF_K8
+    if _REF_K8 is None and ReferenceKey8B.available():
+        _REF_K8 = ReferenceKey8B()
+    return _REF_K8
 
 
 def reference_mat() -> "ReferenceMat | None":

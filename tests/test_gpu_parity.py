@@ -952,3 +952,79 @@ def test_run_sorts_share_one_bit_probe(smj, orc):
             assert (st.matches, st.checksum) == exp, (algo, runs)
     dr.free()
     ds.free()
+
+
+def test_tputbench_tool(smj):
+    """tools/tputbench.py, the counterpart of the reference's tputbench / numabench
+    (src/bench/tputbench.c:249-1170: per-phase throughput in its TPUT / MEMTPUT convention + the copy
+    paths), runs as a program and reports every phase."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(smj.LIB_PATH))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "tputbench.py"), "--n", "4000000", "--reps", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    for phase in ("partition_7bits", "sort", "multiway_merge_128_runs", "multiway_merge_128_runs_rounds",
+                  "merge_join_scan", "mway_join_total"):
+        assert res["phases"][phase]["TPUT_Mtuples_s"] > 0 and res["phases"][phase]["MEMTPUT_GBs"] > 0, phase
+    for path in ("hbm_d2d_GBs_read_plus_write", "pcie_h2d_pinned_GBs", "pcie_d2h_pinned_GBs", "pcie_h2d_pageable_staged_GBs"):
+        assert res["copies"][path] > 0, path
+
+
+# ------------------------------------------------------------------------------------ KEY_8B (16-byte tuples)
+def _key8b_cases(rng):
+    n = 200_003
+    uniq = np.empty((n, 2), dtype=np.int64)
+    uniq[:, 1] = rng.permutation(n) + 1
+    uniq[:, 0] = np.arange(n)
+    yield "fk", uniq, ol.rand_tuples16(rng, 3 * n + 1, 1, n)
+    yield "dups", ol.rand_tuples16(rng, n, 1, n // 50), ol.rand_tuples16(rng, n // 2, 1, n // 50)
+    yield "wide", ol.rand_tuples16(rng, n, (1 << 40), (1 << 40) + 3000), ol.rand_tuples16(rng, n, (1 << 40), (1 << 40) + 3000)
+    yield "signed", ol.rand_tuples16(rng, n, -5000, 5000), ol.rand_tuples16(rng, n, -5000, 5000)
+    yield "high_only", (ol.rand_tuples16(rng, n, 0, 900) * np.array([1, 1 << 32])), (ol.rand_tuples16(rng, n, 0, 900) * np.array([1, 1 << 32]))
+    yield "all_equal", ol.rand_tuples16(rng, 3000, 7, 7), ol.rand_tuples16(rng, 2000, 7, 7)
+    yield "small", ol.rand_tuples16(rng, 1, 3, 3), ol.rand_tuples16(rng, 5, 1, 5)
+    yield "disjoint", ol.rand_tuples16(rng, n, 1, 1000), ol.rand_tuples16(rng, n, 2000, 3000)
+
+
+def test_key8b_join_and_sort(smj, orc):
+    """16-byte tuples (the reference's KEY_8B build, src/types.h:23-29) through the _key8b entry
+    points with host buffers: count and checksum of all three joins and of merge_join against the
+    oracle (pinned against the reference's KEY_8B build in test_oracle_vs_ref.py), the stable key
+    sort, signed keys and keys beyond 32 bits."""
+    rng = np.random.default_rng(88)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for name, r, s in _key8b_cases(rng):
+        r, s = np.ascontiguousarray(r, dtype=np.int64), np.ascontiguousarray(s, dtype=np.int64)
+        exp = orc.join16(r, s)
+        cfg = smj.joinconfig_t(4, 128, 1, 1, 1 << 20, smj.NUMA_NEXT)
+        for fn in ("sortmergejoin_multiway_key8b", "sortmergejoin_multipass_key8b", "sortmergejoin_mpsm_key8b"):
+            relr, rels = smj.relation_t(r.ctypes.data, r.shape[0]), smj.relation_t(s.ctypes.data, s.shape[0])
+            res = getattr(smj.lib, fn)(C.byref(relr), C.byref(rels), C.byref(cfg))
+            assert res and res.contents.totalresults == exp[0], (name, fn)
+            st = smj.smj_join_stats_t()
+            assert smj.lib.smj_last_join_stats(C.byref(st)) == 0 and (st.matches, st.checksum) == exp, (name, fn)
+            libc.free(C.cast(res.contents.resultlist, C.c_void_p))
+            libc.free(C.cast(res, C.c_void_p))
+        # scalarsort_tuples: the input buffer ends up key-sorted (stable here), pointers swapped
+        a, b = s.copy(), np.zeros_like(s)
+        pa, pb = C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)
+        smj.lib.scalarsort_tuples_key8b(C.byref(pa), C.byref(pb), s.shape[0])
+        assert pb.value == a.ctypes.data and pa.value == b.ctypes.data
+        assert np.array_equal(a, orc.sort16(s)), name
+        sr = orc.sort16(r)
+        assert smj.lib.merge_join_key8b(sr.ctypes.data, a.ctypes.data, r.shape[0], s.shape[0], None) == exp[0], name
+    # device-resident relations
+    r, s = ol.rand_tuples16(rng, 1 << 20, 1, 1 << 19), ol.rand_tuples16(rng, (1 << 21) + 3, 1, 1 << 19)
+    dr, ds = smj.DeviceBuffer(2 * r.shape[0]), smj.DeviceBuffer(2 * s.shape[0])
+    smj.check(smj.lib.smjdev_memcpy_h2d(dr.ptr, r.ctypes.data, r.nbytes))
+    smj.check(smj.lib.smjdev_memcpy_h2d(ds.ptr, s.ctypes.data, s.nbytes))
+    st = smj.smj_join_stats_t()
+    smj.check(smj.lib.smjdev_join_key8b(dr.ptr, r.shape[0], ds.ptr, s.shape[0], 0, C.byref(st)))
+    assert (st.matches, st.checksum) == orc.join16(r, s)
+    dr.free()
+    ds.free()
