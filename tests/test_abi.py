@@ -14,9 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_functions():
     names = set()
-    for h in ("smj_b200.h", "smj_device.h"):
+    for h in ("smj_b200.h", "smj_device.h", "smj_b200_key8b.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        txt = re.sub(r"^#define.*$", "", txt, flags=re.M)  # (the KEY_8B name-mapping macros)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", txt):
             if m.group(1) not in ("defined", "sizeof", "ALIGN_NUMTUPLES", "CACHELINEPADDING"):
                 names.add(m.group(1))
