@@ -122,7 +122,31 @@ def run(args, smj):
     return line
 
 
+def _bind_to_gpu_numa_node(local: int) -> str:
+    """Pinned host slices should live on the NUMA node the GPU hangs off: eight ranks that all pin
+    memory on node 0 (torchrun's default affinity) share one memory controller and one socket's PCIe
+    root.  Best effort: moves this process to the cpus of the GPU's node before the buffers are
+    allocated (first touch), if the cpuset allows it."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} cpus)"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+
+
 def _e2e(args, r, s, count, dev, one_step, sync_all, n):
+    _bind_to_gpu_numa_node(dev.index)
     hr = torch.empty(count, dtype=torch.int64).pin_memory()
     hs = torch.empty(count, dtype=torch.int64).pin_memory()
     hr.copy_(r[:count])

@@ -606,7 +606,7 @@ def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
     out, tmp = smj.DeviceBuffer(total), smj.DeviceBuffer(total)
     ptrs = (C.c_void_p * nruns)(*[b.ptr for b in bufs])
     lens = (C.c_uint64 * nruns)(*[x.size for x in runs])
-    monkeypatch.setenv("SMJ_MERGE_PATH", "sort")  # (unset: the one-pass k-way merge takes these inputs)
+    monkeypatch.setenv("SMJ_MERGE_PATH", "sort")
     for path in ("msd", "lsd"):  # lsd: the sort declines, the merge rounds run
         monkeypatch.setenv("SMJ_SORT_PATH", path)
         smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, lens, nruns, 0), "multiway_merge")
@@ -628,11 +628,12 @@ def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
 
 @pytest.mark.parametrize("nruns", [3, 17, 128, 256, 300])
 def test_kway_merge_one_pass(smj, orc, nruns, monkeypatch):
-    """smjdev_multiway_merge in whole-word order takes the one-pass k-way merge (csrc/smj_kway.cu,
+    """smjdev_multiway_merge under SMJ_MERGE_PATH=kway takes the one-pass k-way merge (csrc/smj_kway.cu,
     the counterpart of avx_multiway_merge, src/merge/avx_multiwaymerge.c:199-338): value-range tiles
     from regular samples, gathered, sorted in shared memory, written once.  Same output as the
     oracle for runs of very different lengths, empty runs, heavy duplicates (tiles overflow -> the
     rounds take over) and more than 256 runs (declined)."""
+    monkeypatch.setenv("SMJ_MERGE_PATH", "kway")
     rng = np.random.default_rng(nruns)
     lens = [int(x) for x in rng.integers(0, 2 * 700_000 // nruns, size=nruns)]
     lens[0], lens[-1] = 0, 400_000 // nruns * 3 + 5
@@ -968,6 +969,7 @@ def test_tputbench_tool(smj):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     for phase in ("partition_7bits", "sort", "multiway_merge_128_runs", "multiway_merge_128_runs_rounds",
+                  "multiway_merge_128_runs_kway",
                   "merge_join_scan", "mway_join_total"):
         assert res["phases"][phase]["TPUT_Mtuples_s"] > 0 and res["phases"][phase]["MEMTPUT_GBs"] > 0, phase
     for path in ("hbm_d2d_GBs_read_plus_write", "pcie_h2d_pinned_GBs", "pcie_d2h_pinned_GBs", "pcie_h2d_pageable_staged_GBs"):
