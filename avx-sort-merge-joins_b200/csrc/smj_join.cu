@@ -843,6 +843,52 @@ __global__ void __launch_bounds__(256) k_collect_big(const u64 *__restrict__ rs_
     }
 }
 
+// The S side of every listed (heavy) bucket is cut into chunks of BIG_CHUNK tuples; pref[q] = first
+// chunk of the q-th listed bucket, pref[nbig] = number of chunks.  One CTA.  (The prefix array lives
+// in the upper half of the list array: more than 2^17 - 1 heavy buckets go to the general path.)
+constexpr u32 BIG_CHUNK = 1u << 14;
+__global__ void __launch_bounds__(1024) k_big_chunks(const u64 *__restrict__ ss_, const u64 *__restrict__ se_,
+                                                     const u32 *__restrict__ list, u32 *__restrict__ info,
+                                                     u32 *__restrict__ pref, u32 pref_cap) {
+    __shared__ u32 s_w[32];
+    const u32 nbig = info[0], lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (nbig + 1 > pref_cap) {
+        if (threadIdx.x == 0) info[1] = 1u;
+        return;
+    }
+    u32 carry = 0;
+    for (u32 base = 0; base < nbig; base += 1024) {
+        const u32 q = base + threadIdx.x;
+        u32       c = 0;
+        if (q < nbig) {
+            const u32 b = list[q];
+            c           = (u32)((se_[b] - ss_[b] + BIG_CHUNK - 1) / BIG_CHUNK);
+        }
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 v = __shfl_up_sync(SMJ_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += v;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        u32 excl = incl - c + carry, tot = 0;
+        for (u32 w = 0; w < 32; w++) {
+            if (w < warp) excl += s_w[w];
+            tot += s_w[w];
+        }
+        if (q < nbig) pref[q] = excl;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pref[nbig] = carry;
+}
+
+// Every warp of the grid takes an equal, contiguous share of the chunks: it builds the {count, sum A}
+// table of the chunk's bucket from the (small) R side -- once per bucket, consecutive chunks of one
+// bucket reuse it -- and streams the chunk's S tuples past it.  Work is proportional to the heavy S
+// tuples (the first version gave every bucket to ALL warps: every warp rebuilt every table, 11 ms of
+// the 26 ms of a Zipf(1.0) join).
 __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__restrict__ r,
                                                                    const u64 *__restrict__ rs_,
                                                                    const u64 *__restrict__ re_,
@@ -851,6 +897,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
                                                                    const u64 *__restrict__ se_,
                                                                    const u32 *__restrict__ list,
                                                                    const u32 *__restrict__ info,
+                                                                   const u32 *__restrict__ pref,
                                                                    u32 lo_shift, u32 lbits,
                                                                    u64 *__restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -861,38 +908,53 @@ __global__ void __launch_bounds__(BJ_WARPS * 32) k_big_bucket_join(const u64 *__
     const u64 gw = (u64)blockIdx.x * BJ_WARPS + warp, nw = (u64)gridDim.x * BJ_WARPS;
     if (info[1]) return;  // a bucket heavy on both sides: the host takes the general path
     const u32 nbig = info[0];
+    if (nbig == 0) return;
+    const u64 total = pref[nbig], per = (total + nw - 1) / nw;
+    const u64 c0 = gw * per, c1 = min(total, c0 + per);
     u64       my_cnt = 0, my_cks = 0;
-    for (u32 q = 0; q < nbig; q++) {
-        const u32 b  = list[q];
-        const u64 r0 = rs_[b], r1 = re_[b], s0 = ss_[b], s1 = se_[b];
-        const u64 len = s1 - s0, j0 = s0 + (len * gw) / nw, j1 = s0 + (len * (gw + 1)) / nw;
-        if (j0 == j1) continue;
-        for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;
-        __syncwarp();
-        for (u64 i = r0 + lane; i < r1; i += 32) {
-            const u64 x    = r[i];
-            const u32 slot = (u32)(x >> lo_shift) & mask;
-            atomicAdd(&t_cnt[slot], 1u);
-            atomicAdd(&t_sum[slot], smj_cks_a(x));
+    u32       q = 0, have_b = 0xffffffffu;
+    if (c0 < c1) {  // listed bucket of the first chunk
+        u32 lo = 0, hi = nbig;
+        while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if ((u64)pref[mid] <= c0) lo = mid; else hi = mid;
         }
-        __syncwarp();
-        for (u64 j = j0 + lane; j < j1; j += 128) {
-            u64 y[4];
+        q = lo;
+    }
+    for (u64 c = c0; c < c1; c++) {
+        while ((u64)pref[q + 1] <= c) q++;
+        const u32 b  = list[q];
+        const u64 s0 = ss_[b], s1 = se_[b];
+        const u64 j0 = s0 + (c - pref[q]) * BIG_CHUNK, j1 = min(s1, j0 + BIG_CHUNK);
+        if (b != have_b) {
+            const u64 r0 = rs_[b], r1 = re_[b];
+            for (u32 i = lane; i < slots * 3 / 2; i += 32) ((u64 *)t_sum)[i] = 0;
+            __syncwarp();
+            for (u64 i = r0 + lane; i < r1; i += 32) {
+                const u64 x    = r[i];
+                const u32 slot = (u32)(x >> lo_shift) & mask;
+                atomicAdd(&t_cnt[slot], 1u);
+                atomicAdd(&t_sum[slot], smj_cks_a(x));
+            }
+            __syncwarp();
+            have_b = b;
+        }
+        for (u64 j = j0 + lane; j < j1; j += 256) {
+            u64 y[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) y[u] = (j + 32 * u < j1) ? ld_stream(s + j + 32 * u) : 0ull;
+            for (int u = 0; u < 8; u++) y[u] = (j + 32 * u < j1) ? ld_stream(s + j + 32 * u) : 0ull;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 if (j + 32 * u < j1) {
                     const u32 slot = (u32)(y[u] >> lo_shift) & mask;
-                    const u32 c    = t_cnt[slot];
-                    if (c) {
-                        my_cnt += c;
+                    const u32 cc   = t_cnt[slot];
+                    if (cc) {
+                        my_cnt += cc;
                         my_cks += t_sum[slot] * smj_cks_b(y[u]);
                     }
                 }
             }
         }
-        __syncwarp();
     }
     my_cnt = warp_reduce_add(my_cnt);
     my_cks = warp_reduce_add(my_cks);
@@ -954,8 +1016,11 @@ int smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_
     SMJ_ITEMS(ctx, R.n + S.n);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts, R.ends,
                S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
+    u32 *d_pref = d_list + nb2 / 2;  // (the list of heavy buckets is short: its upper half holds the chunk prefix)
+    SMJ_LAUNCH(ctx, k_big_chunks, 1, 1024, 0, S.starts, S.ends, d_list, (u32 *)(d_state + 6), d_pref, nb2 / 2);
+    SMJ_ITEMS(ctx, S.n);
     SMJ_LAUNCH(ctx, k_big_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts,
-               R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), lo_shift, lbits, acc);
+               R.ends, S.items, S.starts, S.ends, d_list, (u32 *)(d_state + 6), (const u32 *)d_pref, lo_shift, lbits, acc);
     return 0;
 }
 bool smj_bucket_join_valid(const u64 *h_state, u32 lbits) {

@@ -2,8 +2,8 @@
 //
 // The reference only counts unless it is built with JOIN_MATERIALIZE, and then its merge_join
 // appends one tuple <S.key, S.payload> per matching (r, s) pair to a per-thread chained buffer
-// (src/joins/joincommon.c:256-278; the build is broken there, tuple_buffer.h is missing, so the
-// semantics are restated from the loop itself).  Here:
+// (src/joins/joincommon.c:256-278; that build lacks tuple_buffer.h in the reference's tree -- the
+// parity tests compile it with a stand-in header, oracle/shim/, and compare the emitted tuples).  Here:
 //
 //   1. R and S are sorted by key (LSD radix sort, smj_lsd_sort).
 //   2. S is cut into chunks of 1024 tuples; k_mat_bounds finds, for every chunk, the range of R

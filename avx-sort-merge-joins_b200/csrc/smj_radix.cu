@@ -30,6 +30,11 @@ namespace {
 
 constexpr int RADIX_NB = 512;  // stride of every per-digit table; a pass uses 2^8 or 2^9 bins
 
+inline int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // ---------------------------------------------------------------------------------------
 // OR / AND of all items: tells which bit positions vary at all (constant bits need no pass)
 // ---------------------------------------------------------------------------------------
@@ -572,6 +577,16 @@ struct LimitSlots {
     __device__ __forceinline__ void raise_key() const {}
 };
 
+// Asynchronous copies global -> shared (LDGSTS): the next tile of a persistent CTA lands in the
+// staging buffer slot by slot, behind the output loop that has just emptied the slot, so that its
+// DRAM latency is hidden behind this tile's stores and costs no registers.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // the tile's items, thread-strided: item[j] = src[j * THREADS + thread]
 template <int THREADS, int IPT, bool FULL>
 __device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__restrict__ src, u32 valid) {
@@ -585,7 +600,11 @@ __device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__res
 // is zero again on return (after a __syncthreads() of the caller).  next_src != null: the CTA's
 // next tile (a FULL one) is requested into item[] as soon as the registers are free, i.e. before
 // this tile is written out, so its DRAM latency hides behind the output phase.
-template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit>
+// NEXT = 0: next_src (if any) is loaded into item[] before the output loop (register prefetch);
+// NEXT = 1: next_src (a FULL tile; this tile must be FULL too) is copied asynchronously into s_items,
+// every slot right after the output loop has read it; the caller waits (cp_async_wait_all +
+// __syncthreads) and reads item[] from s_items.
+template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit, int NEXT = 0>
 __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restrict__ out, const F &fn,
                                                  u64 *cursors, u32 valid, u64 *s_items, u32 *s_cnt,
                                                  u64 *s_goff, u32 *s_wsum, const LIM &lim,
@@ -675,13 +694,15 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;  // ready for the next tile
-    if (next_src) unstable_load<THREADS, IPT, true>(item, next_src, (u32)TILE);
+    if (NEXT == 0 && next_src) unstable_load<THREADS, IPT, true>(item, next_src, (u32)TILE);
     if (FULL) {
 #pragma unroll 4
         for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
             const u64 x = s_items[i], g = s_goff[fn(x)];
             if (!LIM::on || g != SKIP64) st_stream(out + g + i, x);
+            if (NEXT == 1 && next_src) cp_async8(s_items + i, next_src + i);
         }
+        if (NEXT == 1 && next_src) cp_async_commit();
     } else {
         for (u32 i = threadIdx.x; i < valid; i += THREADS) {
             const u64 x = s_items[i], g = s_goff[fn(x)];
@@ -702,7 +723,7 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
                                                             s_goff, s_wsum, lim, nullptr);
 }
 
-template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM>
+template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM, bool ASYNC = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n,
                         const __grid_constant__ F fn,
@@ -730,10 +751,15 @@ __global__ void __launch_bounds__(THREADS, MINB)
         while (true) {
             const u64  next = tile + gridDim.x;
             const u64 *nsrc = next < nfull ? in + next * TILE : nullptr;
-            unstable_process<THREADS, IPT, BITS, F, true, AGG, LIM>(item, out, fn, cursors, (u32)TILE, s_items,
-                                                                    s_cnt, s_goff, s_wsum, lim, nsrc);
+            unstable_process<THREADS, IPT, BITS, F, true, AGG, LIM, ASYNC ? 1 : 0>(item, out, fn, cursors, (u32)TILE,
+                                                                                   s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
+            if (ASYNC && nsrc) cp_async_wait_all();
             __syncthreads();
             if (!nsrc) break;
+            if (ASYNC) {
+#pragma unroll
+                for (int j = 0; j < IPT; j++) item[j] = s_items[threadIdx.x + j * THREADS];
+            }
             tile = next;
         }
     }
@@ -756,6 +782,13 @@ int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64
     const unsigned grid = host_in ? (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB)
                                   : (unsigned)div_up(n, TILE);
     SMJ_ITEMS(ctx, n);
+    if (LIM::on && !host_in && env_int("SMJ_SCATTER_ASYNC", 0)) {  // persistent CTAs, next tile by cp.async
+        if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, true>, SMEM)) return -1;
+        SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, true>),
+                   (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB), THREADS, SMEM, in, out, n, fn, bases,
+                   lim, 0u);
+        return 0;
+    }
     const u32 pf_dist = host_in ? 0u : (u32)(ctx->sm_count * MINB);  // resident CTAs = tiles in flight
     SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>), grid, THREADS, SMEM, in, out,
                n, fn, bases, lim, pf_dist);
@@ -791,10 +824,6 @@ int launch_onesweep_cfg(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, const
     return 0;
 }
 
-inline int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
 // SMJ_RANK_MODE=0 selects the ballot ranking, 1 (default) the shared-memory bitmask ranking
 inline int rank_mode() {
     static int mode = env_int("SMJ_RANK_MODE", 1);
@@ -1283,7 +1312,7 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict
 // slot goes to the dump area and raises flag[bucket] (see LimitSlots); flagged buckets are
 // repartitioned exactly by the k_msd_fix_* kernels, on the device, without asking the host.
 // Persistent CTAs over the tile table; a full next tile is requested while this one is written.
-template <bool OPT>
+template <bool OPT, bool ASYNC = false>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
                    const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
@@ -1317,13 +1346,22 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
             nx  = tiles[tn];
             pre = nx.valid == (u32)MSD_TILE;
         }
+        // (asynchronous staging needs this tile and the next one to be full tiles)
+        if (ASYNC && ti.valid != (u32)MSD_TILE) pre = false;
         const u64 *nsrc = pre ? in + nx.start : nullptr;
         u64       *cur  = cursors2 + (u64)ti.bucket * MSD_NB;
         Lim        lim;
         if constexpr (OPT) lim = LimitSlots{base2, cap2, ti.bucket, (u32)shrink, flag, any_flag};
         if (ti.valid == (u32)MSD_TILE) {
-            if (!have) unstable_load<MSD_THREADS, MSD_IPT, true>(item, in + ti.start, ti.valid);
-            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim>(
+            if (!have) {
+                unstable_load<MSD_THREADS, MSD_IPT, true>(item, in + ti.start, ti.valid);
+            } else if (ASYNC) {  // the previous iteration copied this tile into the staging buffer
+                cp_async_wait_all();
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < MSD_IPT; j++) item[j] = s_items[threadIdx.x + j * MSD_THREADS];
+            }
+            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim, ASYNC ? 1 : 0>(
                 item, out, fn2, cur, ti.valid, s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
         } else {
             unstable_load<MSD_THREADS, MSD_IPT, false>(item, in + ti.start, ti.valid);
@@ -1739,6 +1777,7 @@ static int msd_scatter2_attr(SmjCtx *ctx) {
     constexpr size_t SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
     if (smj_func_smem(ctx, (const void *)k_msd_scatter2<false>, SMEM)) return -1;
     if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true>, SMEM)) return -1;
+    if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true, true>, SMEM)) return -1;
     return smj_func_smem(ctx, (const void *)k_msd_fix_scatter, SMEM);
 }
 constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
@@ -1946,8 +1985,15 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 4, max_tiles);
     if (msd_scatter2_attr(ctx)) return -1;
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
-               d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2), (u32 *)nullptr);
+    // SMJ_SCATTER_ASYNC=1: persistent CTAs (two per SM), the next tile of a CTA is copied into the
+    // staging buffer with cp.async behind the output loop; else one CTA per tile
+    if (env_int("SMJ_SCATTER_ASYNC", 0)) {
+        SMJ_LAUNCH(ctx, (k_msd_scatter2<true, true>), (unsigned)std::min<u64>(max_tiles, (u64)ctx->sm_count * 2), MSD_THREADS,
+                   MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends, d_base2, d_cap2, d_bflag, shrink, 0u, (u32 *)nullptr);
+    } else {
+        SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
+                   d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2), (u32 *)nullptr);
+    }
     SMJ_LAUNCH(ctx, k_msd_fix_hist, grid, MSD_THREADS, 0, a, d_tab + MSD_NB, d_counts, d_bflag, f2, d_hist2);
     SMJ_LAUNCH(ctx, k_msd_fix_offsets, MSD_NB, MSD_NB, 0, d_bflag, d_hist2, d_base2, starts, ends, d_nfixed);
     SMJ_LAUNCH(ctx, k_msd_fix_scatter, grid, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tab + MSD_NB, d_counts,

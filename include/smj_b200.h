@@ -48,7 +48,7 @@ result_t *sortmergejoin_initrun(relation_t *relR, relation_t *relS, joinconfig_t
 
 /* The reference's JOIN_MATERIALIZE build of the same entry point (src/joins/joincommon.c:256-278
  * emits one tuple <S.key, S.payload> per matching pair into per-thread chained buffers; that build
- * does not compile in the reference, tuple_buffer.h is missing, so it is a separate function here
+ * needs a header the reference's tree lacks, tuple_buffer.h, so it is a separate function here
  * instead of a compile-time switch).  result->resultlist[0].results is a malloc()ed tuple_t array
  * of result->totalresults tuples in unspecified order; the caller frees it, resultlist and
  * result. */

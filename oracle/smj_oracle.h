@@ -61,9 +61,9 @@ int orc_join_mway(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns
  * <S.key, S.payload> for every matching pair; layout 1 emits R.payload << 32 | S.payload instead.
  * Sorts copies of r and s, then the literal loop.  out may be NULL (count only); at most cap items
  * are written, in the loop's order.  Returns the number of matching pairs.
- * PARITY UNPINNED for the emitted tuples: the reference's JOIN_MATERIALIZE build does not compile
- * (tuple_buffer.h is missing), so this loop is checked against numpy only; the COUNT it returns is
- * pinned like every other join count. */
+ * Pinned: oracle/Makefile compiles the unmodified reference with -DJOIN_MATERIALIZE (the header its
+ * tree lacks, tuple_buffer.h, is supplied by oracle/shim/) and tests/test_oracle_vs_ref.py /
+ * tests/golden/ref_golden_r2.npz compare the emitted tuples as multisets. */
 uint64_t orc_join_materialize(const uint64_t *r, uint64_t nr, const uint64_t *s, uint64_t ns,
                               int layout, uint64_t *out, uint64_t cap);
 
