@@ -534,6 +534,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // value in [-8192, 2^62).  A bin whose reservation did not fit is marked with SKIP64, which is not
 // such a value (an all-ones marker would collide with the legitimate offset -1).
 constexpr u64 SKIP64 = 1ull << 62;
+// MEASUREMENT HOOK ONLY (tools/p2p_scatter_bw.py): reservations rounded up to this many items, which
+// leaves holes in the output; 1 (no rounding) everywhere else.
+__constant__ u32 c_dbg_reserve_align = 1;
 
 struct NoLimit {
     static constexpr bool on = false, keys = false;
@@ -657,7 +660,8 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
         if (b <= last_bin && cntb[q]) {
             // the limit is requested before the atomic, so that the two round trips to L2 overlap
             const u64 limit = LIM::on ? lim(b) : ~0ull;
-            gbase[q]        = atomicAdd(&cursors[b], (u64)cntb[q]);
+            const u32 al    = c_dbg_reserve_align;
+            gbase[q]        = atomicAdd(&cursors[b], (u64)((cntb[q] + al - 1) & ~(al - 1)));
             if (LIM::on && gbase[q] + cntb[q] > limit) {  // does not fit: store nothing, raise the flag
                 gbase[q] = SKIP64;
                 lim.raise();
@@ -2077,6 +2081,25 @@ int smj_msd_scatter_to(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *const
     if (!d_cur) return smj_fail_msg("smj_msd_scatter_to: scratch");
     SMJ_CHECK(cudaMemcpyAsync(d_cur, h_cur, RADIX_NB * 8, cudaMemcpyHostToDevice, ctx->stream));
     FieldFn f1 = {shift1, (u32)MSD_NB - 1};
+    // measurement hooks (tools/p2p_scatter_bw.py): 8-bit digit (256 bins: runs twice as long) and / or
+    // 16384-item tiles
+    const int bits = env_int("SMJ_SCATTER_TO_BITS", 9), big = env_int("SMJ_SCATTER_TO_BIG", 0);
+    const u32 al = (u32)env_int("SMJ_SCATTER_TO_ALIGN", 1);
+    SMJ_CHECK(cudaMemcpyToSymbolAsync(c_dbg_reserve_align, &al, 4, 0, cudaMemcpyHostToDevice, ctx->stream));
+    struct Reset {  // back to exact reservations for every other caller
+        SmjCtx *c;
+        ~Reset() {
+            const u32 one = 1;
+            cudaMemcpyToSymbolAsync(c_dbg_reserve_align, &one, 4, 0, cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+    } reset{ctx};
+    if (bits == 8) {
+        f1.mask = 255;
+        if (big) return launch_unstable_shape<1024, 16, 1, 8, FieldFn, false, NoLimit>(ctx, in, (u64 *)nullptr, n, f1, d_cur, NoLimit());
+        return launch_unstable<8>(ctx, in, (u64 *)nullptr, n, f1, d_cur);
+    }
+    if (big) return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, NoLimit>(ctx, in, (u64 *)nullptr, n, f1, d_cur, NoLimit());
     return launch_unstable<9>(ctx, in, (u64 *)nullptr, n, f1, d_cur);
 }
 
