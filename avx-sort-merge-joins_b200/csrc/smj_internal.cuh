@@ -37,7 +37,7 @@ int smj_msd_counts_opt(SmjCtx *ctx, const u64 *d_tab, u64 *d_counts);
 int smj_msd_pass_b_seg_dev(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 nseg, const u64 *d_seg, const u64 *d_n,
                            u64 *b, u32 shift2, u64 *offsets);
 int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab, u32 *d_flag, u32 kmask,
-                       u32 kref, u32 *d_kflag, int big_tile);
+                       u32 kref, u32 *d_kflag, int big_tile, int max_grid);
 int smj_msd_pass_b_opt_seg(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 world, const u64 *d_seg, u64 *b, u64 alloc2,
                            u32 shift2, u32 dense_slot, u64 *starts, u64 *ends, u32 *d_flag);
 constexpr u64 SMJ_SMALL_SORT_MAX = 16384;  // the reference's in-cache block (src/avxsort/avxsort.c:17)

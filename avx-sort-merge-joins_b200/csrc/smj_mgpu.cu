@@ -579,6 +579,9 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     const char *e_tile = getenv("SMJ_XG_TILE"), *e_ovl = getenv("SMJ_XG_OVERLAP");
     const int  big_tile = e_tile ? (atoi(e_tile) >= 16384 ? 1 : atoi(e_tile) == 12288 ? 2 : 0) : (W > 1);
     const bool overlap  = (e_ovl ? atoi(e_ovl) != 0 : (W > 1)) && !ctx->profiling;
+    // the exchange of S is NVLink-bound: it may leave part of the SMs to the owner side of R
+    const char *e_grid = getenv("SMJ_XG_GRID");
+    const int  xg_grid = e_grid ? atoi(e_grid) : ctx->sm_count * 5 / 8;  // measured at N = 2: 148 / 110 / 90 / 74 CTAs -> 2.19 / 2.01 / 1.98 / 2.05 ms
     cudaEvent_t ev_lay = smj_pool_event(ctx, 0), ev_aux = smj_pool_event(ctx, 1);
     if (!ev_lay || !ev_aux) return smj_fail_msg("smjdev_group_join: cudaEventCreate failed");
     cudaStream_t main_stream = ctx->stream;
@@ -601,7 +604,7 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     for (int rel = 0; rel < 2; rel++) {
         if (have_plan && nn[rel] &&
             (rc = smj_msd_pass_a_abs(ctx, in[rel], nn[rel], shift1, &g->d_lay->tab[rel][0][0], flags + 2 * rel, kmask, kref,
-                                     flags + 12 + 2 * rel, big_tile)))
+                                     flags + 12 + 2 * rel, big_tile, (rel == 1 && overlap) ? xg_grid : 0)))
             return rc;
         SMJ_LAUNCH(ctx, k_xg_post_counts, W, XG_NB, 0, g->d_peers, me, rel, g->d_lay, flags + 2 * rel,
                    flags + 12 + 2 * rel, epoch);

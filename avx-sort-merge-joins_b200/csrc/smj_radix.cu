@@ -773,8 +773,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
                                                               s_goff, s_wsum, lim);
 }
 
+// max_grid != 0: at most that many (persistent) CTAs, so that the pass leaves SMs to kernels of
+// another stream (join group: the owner side of R runs under the NVLink-bound exchange of S)
 template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM>
-int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim) {
+int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim, unsigned max_grid = 0) {
     constexpr int    NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM = (size_t)TILE * 8 + NB * 4 + NB * 8;
     if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>, SMEM)) return -1;
@@ -791,6 +793,11 @@ int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64
         SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, true>),
                    (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB), THREADS, SMEM, in, out, n, fn, bases,
                    lim, 0u);
+        return 0;
+    }
+    if (max_grid && max_grid < grid) {
+        SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>), max_grid, THREADS, SMEM, in, out,
+                   n, fn, bases, lim, 0u);
         return 0;
     }
     const u32 pf_dist = host_in ? 0u : (u32)(ctx->sm_count * MINB);  // resident CTAs = tiles in flight
@@ -1859,14 +1866,15 @@ int smj_msd_pass_b_seg_dev(SmjCtx *ctx, const u64 *a, u64 n_upper, u32 nseg, con
 // per SM overlap their phases); into PEER memory the pass is bound by NVLink, whose packets carry up
 // to 256 bytes, and the longer runs cross it faster.
 int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab, u32 *d_flag, u32 kmask,
-                       u32 kref, u32 *d_kflag, int big_tile) {
+                       u32 kref, u32 *d_kflag, int big_tile, int max_grid) {
     if (n == 0) return 0;
     FieldFn          f1  = {shift1, (u32)MSD_NB - 1};
     const LimitArray lim = {d_tab + 2 * MSD_NB, d_flag, kmask, kref, d_kflag};
     if (big_tile == 2)  // experiment: 12288-item tiles, two CTAs per SM (register-starved: spills)
         return launch_unstable_shape<512, 24, 2, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
     if (big_tile)
-        return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
+        return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim,
+                                                                                 (unsigned)max_grid);
     return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
 }
 u64 smj_smj_cap1(u64 k, double scale) { return smj_cap1(k, scale, 0); }

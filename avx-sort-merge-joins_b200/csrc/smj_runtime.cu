@@ -419,15 +419,26 @@ int smjdev_ipc_close(void *peer_ptr) {
 // Staged transfers for ORDINARY (pageable) host memory.  The reference's callers malloc their
 // relations (src/main.c:516-528); a plain cudaMemcpy from such memory runs at ~11 GB/s on the
 // B200 host because the driver stages it single-threaded.  Here several host threads copy
-// 8 MiB chunks into a ring of pinned bounce buffers and each chunk is DMA-ed as soon as it is
+// 4 MiB chunks into a ring of pinned bounce buffers and each chunk is DMA-ed as soon as it is
 // staged, so memcpy and PCIe traffic overlap and the host side is parallel.
 // ---------------------------------------------------------------------------------------
 #include <atomic>
 #include <thread>
 
 namespace {
-constexpr int    STG_SLOTS = 12;
-constexpr size_t STG_CHUNK = 8u << 20;
+constexpr int    STG_SLOTS = 16;
+constexpr size_t STG_MIN_BYTES = 32u << 20;  // smaller transfers: one plain cudaMemcpyAsync
+// bytes per bounce buffer; $SMJ_STAGE_CHUNK_KB (read once, before the first staged transfer).  16 x 4 MiB:
+// the ring about fits the host's last-level cache (measured, 2 x 1 GB uploads + join: 8 MiB 48.8 ms,
+// 4 MiB 44.6, 2 MiB 45.9, 1 MiB 49.6, 512 KiB 68 ms; 8 or 14 staging threads make no difference)
+size_t stg_chunk() {
+    static const size_t v = [] {
+        const char *e = getenv("SMJ_STAGE_CHUNK_KB");
+        const long  kb = e ? atol(e) : 0;
+        return kb >= 64 && kb <= (64 << 10) ? (size_t)kb << 10 : (size_t)4 << 20;
+    }();
+    return v;
+}
 struct Stager {
     bool                   ready = false;
     void                  *bounce[STG_SLOTS];
@@ -450,7 +461,7 @@ Stager *stager_of(SmjCtx *c) {
 int stager_init(Stager *st) {
     if (st->ready) return 0;
     for (int i = 0; i < STG_SLOTS; i++) {
-        SMJ_CHECK(cudaHostAlloc(&st->bounce[i], STG_CHUNK, cudaHostAllocPortable));
+        SMJ_CHECK(cudaHostAlloc(&st->bounce[i], stg_chunk(), cudaHostAllocPortable));
         SMJ_CHECK(cudaEventCreateWithFlags(&st->ev[i], cudaEventDisableTiming));
     }
     SMJ_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
@@ -476,6 +487,7 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
     // the device buffer may have been produced (or allocated) on the compute stream
     SMJ_CHECK(cudaEventRecord(st->fence, c->stream));
     SMJ_CHECK(cudaStreamWaitEvent(st->stream, st->fence, 0));
+    const size_t STG_CHUNK = stg_chunk();
     const size_t nchunks = (bytes + STG_CHUNK - 1) / STG_CHUNK;
     for (int i = 0; i < STG_SLOTS; i++) st->done[i].store((long long)i - STG_SLOTS);
     std::atomic<size_t> next{0};
@@ -528,7 +540,7 @@ int smjdev_upload(void *dst, const void *src, size_t bytes) {
     SmjCtx *c = smj_ctx();
     if (!c) return -1;
     if (bytes == 0) return 0;
-    if (smjdev_pointer_kind(src) != 0 || bytes < 4 * STG_CHUNK || getenv("SMJ_NO_STAGING")) {
+    if (smjdev_pointer_kind(src) != 0 || bytes < STG_MIN_BYTES || getenv("SMJ_NO_STAGING")) {
         SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
         return 0;
     }
@@ -539,7 +551,7 @@ int smjdev_download(void *dst, const void *src, size_t bytes) {
     SmjCtx *c = smj_ctx();
     if (!c) return -1;
     if (bytes == 0) return 0;
-    if (smjdev_pointer_kind(dst) != 0 || bytes < 4 * STG_CHUNK || getenv("SMJ_NO_STAGING")) {
+    if (smjdev_pointer_kind(dst) != 0 || bytes < STG_MIN_BYTES || getenv("SMJ_NO_STAGING")) {
         SMJ_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
         SMJ_CHECK(cudaStreamSynchronize(c->stream));
         return 0;
