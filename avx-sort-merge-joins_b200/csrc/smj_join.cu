@@ -41,29 +41,6 @@ struct MjRec {
 
 __device__ __forceinline__ u32 key_of(u64 x) { return (u32)(x >> 32); }
 
-// first index in [lo,hi) whose key is >= k
-__device__ __forceinline__ u32 lower_key(const u64 *a, u32 lo, u32 hi, u32 k) {
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (key_of(a[mid]) < k)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-// first index in [lo,hi) whose key is > k
-__device__ __forceinline__ u32 upper_key(const u64 *a, u32 lo, u32 hi, u32 k) {
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (key_of(a[mid]) <= k)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
 // merge path on keys, R before S on ties: number of R items among the first diag merged items
 __global__ void __launch_bounds__(256) k_mj_partition(const u64 *__restrict__ r, u64 nr,
                                                       const u64 *__restrict__ s, u64 ns, u64 tiles,
@@ -83,17 +60,32 @@ __global__ void __launch_bounds__(256) k_mj_partition(const u64 *__restrict__ r,
     diag_r[t] = lo;
 }
 
-// One tile of the merged order.  Every thread finds its 8-item slice of the merge path and walks
-// it with two cursors; when it meets the FIRST S item of a key run it multiplies the sizes (and
-// checksum sums) of the R run ending at its R cursor and of the S run starting there.
-__global__ void __launch_bounds__(MJ_THREADS) k_mj_tile(const u64 *__restrict__ r, u64 nr,
-                                                        const u64 *__restrict__ s, u64 ns,
-                                                        const u64 *__restrict__ diag_r,
-                                                        MjRec *__restrict__ recs,
-                                                        unsigned char *__restrict__ rec_valid,
-                                                        u64 *__restrict__ acc, int semi) {
-    __shared__ u64 s_it[MJ_TILE];  // R piece followed by S piece
-    __shared__ u64 s_red[10][MJ_THREADS / 32];
+// One tile of the merged order (R piece and S piece of the merge path, 4096 items together).
+//
+// Keys whose runs may continue in a neighbouring tile (the tile's first / last key) are taken out
+// first: they are a prefix / suffix of the sorted pieces, four warps add them up into the boundary
+// records for k_mj_fixup, and the S piece the walk sees is SHORTENED by them, so that the walk needs
+// no per-item test for them.
+//
+// The walk: every thread finds its 16-item slice of the merge path (R before S on ties) and merges
+// with two register-cached heads, one shared-memory load per step.  It carries the R RUN that ends
+// at its R cursor -- {key, items, sum of A} -- which is all an S item needs: an S item of that key
+// adds run_items to the count and run_sumA * B(s) to the checksum (sum over S items of a key =
+// sumA * sumB).  No head-of-run detection, no searches, duplicates on either side cost nothing
+// extra.  A thread that starts inside an R run first walks back to the run's start (one step for
+// unique keys).  Shared-memory index i lives at word i + i / 16: lanes whose cursors are ~8 or ~16
+// items apart would otherwise meet in one or two banks (round 1: 146 M of 241 M wavefronts were
+// bank conflicts).
+#define MJP(i) ((i) + ((i) >> 4))
+__global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict__ r, u64 nr,
+                                                           const u64 *__restrict__ s, u64 ns,
+                                                           const u64 *__restrict__ diag_r,
+                                                           MjRec *__restrict__ recs,
+                                                           unsigned char *__restrict__ rec_valid,
+                                                           u64 *__restrict__ acc, int semi) {
+    __shared__ u64 s_it[MJP(MJ_TILE) + 1];  // R piece followed by S piece
+    __shared__ u64 s_red[2][MJ_THREADS / 32];
+    __shared__ u64 s_edge[4][2];  // {items, sum} of: R prefix, S prefix (key kf), R suffix, S suffix (key kl)
 
     const u64 t  = blockIdx.x;
     const u64 d0 = t * (u64)MJ_TILE;
@@ -103,30 +95,58 @@ __global__ void __launch_bounds__(MJ_THREADS) k_mj_tile(const u64 *__restrict__ 
     const u32 la = (u32)(r1 - r0), lb = (u32)(s1 - s0), cnt = la + lb;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+#pragma unroll 8
     for (u32 i = threadIdx.x; i < cnt; i += MJ_THREADS)
-        s_it[i] = (i < la) ? ld_stream(r + r0 + i) : ld_stream(s + s0 + (i - la));
+        s_it[MJP(i)] = (i < la) ? ld_stream(r + r0 + i) : ld_stream(s + s0 + (i - la));
     __syncthreads();
-    const u64 *sR = s_it, *sS = s_it + la;
+#define SR(i) s_it[MJP(i)]
+#define SS(j) s_it[MJP(la + (j))]
 
     // ---- the tile's first / last key: their runs may continue in the neighbouring tiles
-    const u32 kf = min(la ? key_of(sR[0]) : 0xffffffffu, lb ? key_of(sS[0]) : 0xffffffffu);
-    const u32 kl = max(la ? key_of(sR[la - 1]) : 0u, lb ? key_of(sS[lb - 1]) : 0u);
+    const u32 kf = min(la ? key_of(SR(0)) : 0xffffffffu, lb ? key_of(SS(0)) : 0xffffffffu);
+    const u32 kl = max(la ? key_of(SR(la - 1)) : 0u, lb ? key_of(SS(lb - 1)) : 0u);
     const bool first_open = (r0 > 0 && key_of(r[r0 - 1]) == kf) || (s0 > 0 && key_of(s[s0 - 1]) == kf);
     const bool last_open  = (r1 < nr && key_of(r[r1]) == kl) || (s1 < ns && key_of(s[s1]) == kl);
     // a key whose run is not complete inside this tile is left to k_mj_fixup
     const bool ex_f = first_open || (kf == kl && last_open);
     const bool ex_l = (kl != kf) && last_open;
+    if (ex_f | ex_l) {  // block-uniform; about every second tile when both sides have the key
+        if (warp < 4 && ((warp < 2) ? ex_f : ex_l)) {
+            const bool is_r = !(warp & 1), pre = warp < 2;
+            const u32  len = is_r ? la : lb, base = is_r ? 0u : la, k = pre ? kf : kl;
+            u64        c = 0, sum = 0;
+            for (u32 i = lane; i < len; i += 32) {  // the run is a prefix / suffix of the sorted piece
+                const u64 x = s_it[MJP(base + (pre ? i : len - 1 - i))];
+                if (key_of(x) != k) break;
+                c++;
+                sum += is_r ? smj_cks_a(x) : smj_cks_b(x);
+            }
+            c   = warp_reduce_add(c);
+            sum = warp_reduce_add(sum);
+            if (lane == 0) {
+                s_edge[warp][0] = c;
+                s_edge[warp][1] = sum;
+            }
+        } else if (warp < 4 && lane == 0) {
+            s_edge[warp][0] = 0;
+            s_edge[warp][1] = 0;
+        }
+        __syncthreads();
+    }
+    // the S piece without its open runs
+    const u32 sx  = ex_f ? (u32)s_edge[1][0] : 0u;
+    const u32 lbw = lb - sx - (ex_l ? (u32)s_edge[3][0] : 0u);
+    const u32 cw  = la + lbw;
+#define SW(j) s_it[MJP(la + sx + (j))]
 
     u64 my_cnt = 0, my_cks = 0;
-    u64 f_cr = 0, f_cs = 0, f_sa = 0, f_sb = 0, l_cr = 0, l_cs = 0, l_sa = 0, l_sb = 0;
-
-    const u32 d = min((u32)(threadIdx.x * MJ_IPT), cnt);
+    const u32 d = min((u32)(threadIdx.x * MJ_IPT), cw);
     u32       ai, bi;
     {  // merge path on keys inside the tile, R before S on ties
-        u32 lo = d > lb ? d - lb : 0, hi = d < la ? d : la;
+        u32 lo = d > lbw ? d - lbw : 0, hi = d < la ? d : la;
         while (lo < hi) {
-            u32 mid = (lo + hi) >> 1;
-            if (key_of(sR[mid]) <= key_of(sS[d - 1 - mid]))
+            const u32 mid = (lo + hi) >> 1;
+            if (key_of(SR(mid)) <= key_of(SW(d - 1 - mid)))
                 lo = mid + 1;
             else
                 hi = mid;
@@ -134,117 +154,81 @@ __global__ void __launch_bounds__(MJ_THREADS) k_mj_tile(const u64 *__restrict__ 
         ai = lo;
         bi = d - lo;
     }
-    // Heads of the two pieces and the last items passed are kept in registers: one shared-memory
-    // load per step (the classic serial merge), everything else is register compares.
-    u64  a_it = (ai < la) ? sR[ai] : 0ull, b_it = (bi < lb) ? sS[bi] : 0ull;
-    u64  last_r      = (ai > 0) ? sR[ai - 1] : 0ull;       // last R item before the cursor
-    bool has_last_r  = ai > 0;
-    u32  last_r2_key = (ai > 1) ? key_of(sR[ai - 2]) : 0u;  // and the one before it
-    bool has_last_r2 = ai > 1;
-    u32  prev_s_key  = (bi > 0) ? key_of(sS[bi - 1]) : 0u;
-    bool has_prev_s  = bi > 0;
+    // the R run that ends at the cursor
+    u32 run_key = 0, run_cnt = 0;
+    u64 run_sa = 0;
+    if (ai > 0 && d < cw) {
+        const u64 x = SR(ai - 1);
+        run_key = key_of(x), run_cnt = 1, run_sa = smj_cks_a(x);
+        for (u32 i = ai - 1; i > 0; i--) {
+            const u64 y = SR(i - 1);
+            if (key_of(y) != run_key) break;
+            run_cnt++;
+            run_sa += smj_cks_a(y);
+        }
+    }
+    u64 a_it = (ai < la) ? SR(ai) : 0ull, b_it = (bi < lbw) ? SW(bi) : 0ull;
+    const u32 steps = min((u32)MJ_IPT, cw - d);
 #pragma unroll 1
-    for (int step = 0; step < MJ_IPT; step++) {
-        if (d + step >= cnt) break;
-        // The body is written with selects instead of an R branch and an S branch: the lanes of
-        // a warp disagree on take_r at almost every step and would otherwise run both sides.
-        const bool take_r = (bi >= lb) || (ai < la && key_of(a_it) <= key_of(b_it));
+    for (u32 step = 0; step < steps; step++) {
+        // selects instead of an R branch and an S branch: the lanes of a warp disagree on take_r at
+        // almost every step and would otherwise run both sides
+        const bool take_r = (bi >= lbw) || (ai < la && key_of(a_it) <= key_of(b_it));
         const u64  x      = take_r ? a_it : b_it;
         const u32  k      = key_of(x);
-        bool       open   = false;
-        if (ex_f | ex_l) {  // block-uniform and rare: a run crosses the tile boundary
-            if (ex_f && k == kf) {
-                open = true;
-                if (take_r) {
-                    f_cr++;
-                    f_sa += smj_cks_a(x);
-                } else {
-                    f_cs++;
-                    f_sb += smj_cks_b(x);
-                }
-            } else if (ex_l && k == kl) {
-                open = true;
-                if (take_r) {
-                    l_cr++;
-                    l_sa += smj_cks_a(x);
-                } else {
-                    l_cs++;
-                    l_sb += smj_cks_b(x);
-                }
-            }
-        }
+        const bool same   = k == run_key;
         // advance the cursor that was taken and load its next head (one shared-memory load)
-        const u32 nidx = take_r ? ai + 1 : la + bi + 1;
-        const u32 nend = take_r ? la : cnt;
-        const u64 nxt  = (nidx < nend) ? s_it[nidx] : 0ull;
-        // an S item that starts an S run and whose key equals the last R item passed
-        const bool head = !take_r && !open && !(has_prev_s && prev_s_key == k) && has_last_r &&
-                          key_of(last_r) == k;
-        if (head) {
-            const bool multi = (has_last_r2 && last_r2_key == k) || (bi + 1 < lb && key_of(nxt) == k);
-            if (!multi) {
-                my_cnt += 1;
-                my_cks += smj_cks_a(last_r) * smj_cks_b(x);
-            } else {  // duplicates: the R run is [lo, ai), the S run [bi, j2)
-                u32 lo = ai - 1;
-                if (has_last_r2 && last_r2_key == k) lo = lower_key(sR, 0, lo, k);
-                u32 j2 = bi + 1;
-                if (j2 < lb && key_of(nxt) == k) j2 = upper_key(sS, j2, lb, k);
-                const u32 cr = ai - lo, cs = j2 - bi;
-                my_cnt += semi ? (u64)cs : (u64)cr * (u64)cs;
-                u64 sa = 0, sb = 0;
-                for (u32 i = lo; i < ai; i++) sa += smj_cks_a(sR[i]);
-                for (u32 j = bi; j < j2; j++) sb += smj_cks_b(sS[j]);
-                my_cks += sa * sb;
-            }
-        }
+        ai += take_r ? 1u : 0u;
+        bi += take_r ? 0u : 1u;
+        const u32 nidx = take_r ? ai : la + sx + bi;
+        const u32 nend = take_r ? la : la + sx + lbw;
+        const u64 nxt  = (nidx < nend) ? s_it[MJP(nidx)] : 0ull;
         if (take_r) {
-            last_r2_key = key_of(last_r);
-            has_last_r2 = has_last_r;
-            last_r      = x;
-            has_last_r  = true;
-            ai++;
-            a_it = nxt;
+            run_sa  = (same ? run_sa : 0ull) + smj_cks_a(x);
+            run_cnt = same ? run_cnt + 1u : 1u;
+            run_key = k;
+            a_it    = nxt;
         } else {
-            prev_s_key = k;
-            has_prev_s = true;
-            bi++;
+            if (same) {
+                my_cnt += semi ? (run_cnt ? 1ull : 0ull) : (u64)run_cnt;
+                my_cks += run_sa * smj_cks_b(x);
+            }
             b_it = nxt;
         }
     }
+#undef SR
+#undef SS
+#undef SW
 
-    // ---- block reduction: count / checksum always, the boundary partial sums only when needed
-    const int nred  = (ex_f | ex_l) ? 10 : 2;
-    u64       v[10] = {my_cnt, my_cks, f_cr, f_cs, f_sa, f_sb, l_cr, l_cs, l_sa, l_sb};
-#pragma unroll
-    for (int q = 0; q < 10; q++) {
-        if (q < nred) {
-            u64 x = warp_reduce_add(v[q]);
-            if (lane == 0) s_red[q][warp] = x;
-        }
+    // ---- block reduction of count / checksum; the boundary records come from s_edge
+    my_cnt = warp_reduce_add(my_cnt);
+    my_cks = warp_reduce_add(my_cks);
+    if (lane == 0) {
+        s_red[0][warp] = my_cnt;
+        s_red[1][warp] = my_cks;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        u64 tot[10];
-        for (int q = 0; q < 10; q++) {
-            tot[q] = 0;
-            if (q < nred)
-                for (int w = 0; w < MJ_THREADS / 32; w++) tot[q] += s_red[q][w];
+        u64 c = 0, x = 0;
+        for (int w = 0; w < MJ_THREADS / 32; w++) {
+            c += s_red[0][w];
+            x += s_red[1][w];
         }
-        if (tot[0]) atomicAdd(acc, tot[0]);
-        if (tot[1]) atomicAdd(acc + 1, tot[1]);
+        if (c) atomicAdd(acc, c);
+        if (x) atomicAdd(acc + 1, x);
         rec_valid[2 * t]     = ex_f ? 1 : 0;
         rec_valid[2 * t + 1] = ex_l ? 1 : 0;
         if (ex_f) {
-            MjRec rec = {kf, tot[2], tot[3], tot[4], tot[5]};
+            MjRec rec = {kf, s_edge[0][0], s_edge[1][0], s_edge[0][1], s_edge[1][1]};
             recs[2 * t] = rec;
         }
         if (ex_l) {
-            MjRec rec = {kl, tot[6], tot[7], tot[8], tot[9]};
+            MjRec rec = {kl, s_edge[2][0], s_edge[3][0], s_edge[2][1], s_edge[3][1]};
             recs[2 * t + 1] = rec;
         }
     }
 }
+#undef MJP
 
 // Stitch the per-tile boundary records: consecutive valid records with the same key form one run.
 constexpr int FX_THREADS = 512;

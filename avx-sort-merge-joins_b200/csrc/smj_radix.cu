@@ -590,6 +590,20 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Bulk copies shared -> global (TMA, UBLKCP): one instruction of ONE thread writes a whole run of a
+// bin; the copy engine reads shared memory and issues the stores, so the run costs the LSU pipe
+// nothing.  Addresses and size are multiples of 16 bytes.  The writes of the generic proxy (STS)
+// have to be made visible to the asynchronous proxy first (fence_proxy_async + barrier).
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u32 bytes) {
+    const u32 s = (u32)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk copies of this thread have READ their source (the shared-memory buffer may be reused)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // the tile's items, thread-strided: item[j] = src[j * THREADS + thread]
 template <int THREADS, int IPT, bool FULL>
 __device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__restrict__ src, u32 valid) {
@@ -607,7 +621,12 @@ __device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__res
 // NEXT = 1: next_src (a FULL tile; this tile must be FULL too) is copied asynchronously into s_items,
 // every slot right after the output loop has read it; the caller waits (cp_async_wait_all +
 // __syncthreads) and reads item[] from s_items.
-template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit, int NEXT = 0>
+// BULK (FULL tiles only; s_items has TILE + NB slots): every bin's run is staged at a slot of the
+// same 16-byte phase as its destination and leaves as one bulk copy issued by the bin's thread
+// (plus at most one plain store at either end); the caller must bulk_wait_read() + __syncthreads()
+// before s_items is written again and before the CTA exits.
+template <int THREADS, int IPT, int BITS, class F, bool FULL, bool AGG = false, class LIM = NoLimit, int NEXT = 0,
+          bool BULK = false>
 __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restrict__ out, const F &fn,
                                                  u64 *cursors, u32 valid, u64 *s_items, u32 *s_cnt,
                                                  u64 *s_goff, u32 *s_wsum, const LIM &lim,
@@ -678,10 +697,16 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
     __syncthreads();
     u32 excl = incl - tsum;
     for (u32 w = 0; w < warp; w++) excl += s_wsum[w];
+    u32 spos[BPT];
 #pragma unroll
     for (int q = 0; q < BPT; q++) {
         const u32 b = threadIdx.x * BPT + q;
-        if (b < NB) {
+        if (BULK && FULL) {
+            // one spare slot per bin: the run starts on the slot whose 16-byte phase is the destination's
+            const u32 first = excl + b;
+            spos[q]         = first + ((first ^ (u32)((uintptr_t)(out + gbase[q]) >> 3)) & 1u);
+            if (b < NB) s_cnt[b] = spos[q];
+        } else if (b < NB) {
             s_cnt[b]  = excl;  // tile position of the bin's first item
             s_goff[b] = (LIM::on && gbase[q] == SKIP64) ? SKIP64 : gbase[q] - (u64)excl;
         }
@@ -696,10 +721,29 @@ __device__ __forceinline__ void unstable_process(u64 (&item)[IPT], u64 *__restri
             s_items[s_cnt[fn(item[j])] + r] = item[j];
         }
     }
+    if (BULK && FULL) fence_proxy_async();
     __syncthreads();
     for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;  // ready for the next tile
     if (NEXT == 0 && next_src) unstable_load<THREADS, IPT, true>(item, next_src, (u32)TILE);
-    if (FULL) {
+    if (BULK && FULL) {
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            u32 c = cntb[q];
+            if (!c || threadIdx.x * BPT + q > last_bin || (LIM::on && gbase[q] == SKIP64)) continue;
+            u64       *dst = out + gbase[q];
+            const u64 *src = s_items + spos[q];
+            if ((uintptr_t)dst & 8) {  // odd first item
+                st_stream(dst, *src);
+                dst++, src++, c--;
+            }
+            if (c & 1) {  // odd last item
+                c--;
+                st_stream(dst + c, src[c]);
+            }
+            if (c) bulk_s2g(dst, src, c * 8);
+        }
+        bulk_commit();
+    } else if (FULL) {
 #pragma unroll 4
         for (u32 i = threadIdx.x; i < (u32)TILE; i += THREADS) {
             const u64 x = s_items[i], g = s_goff[fn(x)];
@@ -727,7 +771,7 @@ __device__ __forceinline__ void unstable_tile(const u64 *__restrict__ in, u64 *_
                                                             s_goff, s_wsum, lim, nullptr);
 }
 
-template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM, bool ASYNC = false>
+template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM, bool ASYNC = false, bool BULK = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     k_onesweep_unstable(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n,
                         const __grid_constant__ F fn,
@@ -736,9 +780,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
     constexpr int NB   = 1 << BITS;
     constexpr int TILE = THREADS * IPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_items = (u64 *)smem_raw;           // TILE staged items
-    u32 *s_cnt   = (u32 *)(s_items + TILE);   // [NB]
-    u64 *s_goff  = (u64 *)(s_cnt + NB);       // [NB]
+    u64 *s_items = (u64 *)smem_raw;                            // TILE staged items (BULK: + NB spare slots)
+    u32 *s_cnt   = (u32 *)(s_items + TILE + (BULK ? NB : 0));  // [NB]
+    u64 *s_goff  = (u64 *)(s_cnt + NB);                        // [NB]
     __shared__ u32 s_wsum[32];
     for (int i = threadIdx.x; i < NB; i += THREADS) s_cnt[i] = 0;
     __syncthreads();
@@ -755,9 +799,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
         while (true) {
             const u64  next = tile + gridDim.x;
             const u64 *nsrc = next < nfull ? in + next * TILE : nullptr;
-            unstable_process<THREADS, IPT, BITS, F, true, AGG, LIM, ASYNC ? 1 : 0>(item, out, fn, cursors, (u32)TILE,
-                                                                                   s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
+            unstable_process<THREADS, IPT, BITS, F, true, AGG, LIM, ASYNC ? 1 : 0, BULK>(
+                item, out, fn, cursors, (u32)TILE, s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
             if (ASYNC && nsrc) cp_async_wait_all();
+            if (BULK) bulk_wait_read();
             __syncthreads();
             if (!nsrc) break;
             if (ASYNC) {
@@ -776,7 +821,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 // max_grid != 0: at most that many (persistent) CTAs, so that the pass leaves SMs to kernels of
 // another stream (join group: the owner side of R runs under the NVLink-bound exchange of S)
 template <int THREADS, int IPT, int MINB, int BITS, class F, bool AGG, class LIM>
-int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim, unsigned max_grid = 0) {
+int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64 *bases, LIM lim, unsigned max_grid = 0,
+                          int bulk = -1 /* -1: $SMJ_SCATTER_BULK decides */) {
     constexpr int    NB = 1 << BITS, TILE = THREADS * IPT;
     constexpr size_t SMEM = (size_t)TILE * 8 + NB * 4 + NB * 8;
     if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM>, SMEM)) return -1;
@@ -788,6 +834,18 @@ int launch_unstable_shape(SmjCtx *ctx, const u64 *in, u64 *out, u64 n, F fn, u64
     const unsigned grid = host_in ? (unsigned)std::min<u64>(div_up(n, TILE), (u64)ctx->sm_count * MINB)
                                   : (unsigned)div_up(n, TILE);
     SMJ_ITEMS(ctx, n);
+    if constexpr (!AGG) {
+        if (bulk >= 0 ? bulk != 0 : env_int("SMJ_SCATTER_BULK", 0) != 0) {  // runs leave shared memory as bulk copies (TMA)
+            constexpr size_t SMEM_B = SMEM + NB * 8;
+            if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, false, true>, SMEM_B))
+                return -1;
+            const bool     persist = host_in || (max_grid && max_grid < grid);
+            const unsigned g = persist ? (max_grid && max_grid < grid ? max_grid : grid) : grid;
+            SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, false, true>), g, THREADS, SMEM_B, in,
+                       out, n, fn, bases, lim, persist ? 0u : (u32)(ctx->sm_count * MINB));
+            return 0;
+        }
+    }
     if (LIM::on && !host_in && env_int("SMJ_SCATTER_ASYNC", 0)) {  // persistent CTAs, next tile by cp.async
         if (smj_func_smem(ctx, (const void *)k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, true>, SMEM)) return -1;
         SMJ_LAUNCH(ctx, (k_onesweep_unstable<THREADS, IPT, MINB, BITS, F, AGG, LIM, true>),
@@ -1323,7 +1381,7 @@ __global__ void __launch_bounds__(MSD_THREADS) k_msd_hist2(const u64 *__restrict
 // slot goes to the dump area and raises flag[bucket] (see LimitSlots); flagged buckets are
 // repartitioned exactly by the k_msd_fix_* kernels, on the device, without asking the host.
 // Persistent CTAs over the tile table; a full next tile is requested while this one is written.
-template <bool OPT, bool ASYNC = false>
+template <bool OPT, bool ASYNC = false, bool BULK = false>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
     k_msd_scatter2(const u64 *__restrict__ in, u64 *__restrict__ out, const MsdTile *__restrict__ tiles,
                    const u64 *__restrict__ tile_prefix, const __grid_constant__ FieldFn fn2,
@@ -1331,7 +1389,7 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
                    const u64 *__restrict__ cap2, u32 *flag, int shrink, u32 pf_dist, u32 *any_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = (u64 *)smem_raw;
-    u32 *s_cnt   = (u32 *)(s_items + MSD_TILE);
+    u32 *s_cnt   = (u32 *)(s_items + MSD_TILE + (BULK ? MSD_NB : 0));
     u64 *s_goff  = (u64 *)(s_cnt + MSD_NB);
     __shared__ u32 s_wsum[32];
     // the tile entry is requested together with the tile count (the table has an entry, possibly
@@ -1372,8 +1430,9 @@ __global__ void __launch_bounds__(MSD_THREADS, 2)
 #pragma unroll
                 for (int j = 0; j < MSD_IPT; j++) item[j] = s_items[threadIdx.x + j * MSD_THREADS];
             }
-            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim, ASYNC ? 1 : 0>(
+            unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, true, false, Lim, ASYNC ? 1 : 0, BULK>(
                 item, out, fn2, cur, ti.valid, s_items, s_cnt, s_goff, s_wsum, lim, nsrc);
+            if (BULK) bulk_wait_read();
         } else {
             unstable_load<MSD_THREADS, MSD_IPT, false>(item, in + ti.start, ti.valid);
             unstable_process<MSD_THREADS, MSD_IPT, 9, FieldFn, false, false, Lim>(
@@ -1789,6 +1848,7 @@ static int msd_scatter2_attr(SmjCtx *ctx) {
     if (smj_func_smem(ctx, (const void *)k_msd_scatter2<false>, SMEM)) return -1;
     if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true>, SMEM)) return -1;
     if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true, true>, SMEM)) return -1;
+    if (smj_func_smem(ctx, (const void *)k_msd_scatter2<true, false, true>, SMEM + MSD_NB * 8)) return -1;
     return smj_func_smem(ctx, (const void *)k_msd_fix_scatter, SMEM);
 }
 constexpr size_t MSD_SCATTER_SMEM = (size_t)MSD_TILE * 8 + MSD_NB * 4 + MSD_NB * 8;
@@ -1872,9 +1932,12 @@ int smj_msd_pass_a_abs(SmjCtx *ctx, const u64 *in, u64 n, u32 shift1, u64 *d_tab
     const LimitArray lim = {d_tab + 2 * MSD_NB, d_flag, kmask, kref, d_kflag};
     if (big_tile == 2)  // experiment: 12288-item tiles, two CTAs per SM (register-starved: spills)
         return launch_unstable_shape<512, 24, 2, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
+    // Peer destinations: the runs of a bin leave as bulk copies (one TMA instruction per run instead of
+    // an LDS + LDS + STG per item); measured at N = 2: pass A 1.206 -> 1.157 ms.  (Into local HBM the
+    // same variant is SLOWER, 0.46 -> 0.54 ms: 512 small copies per tile bound the copy engine.)
     if (big_tile)
         return launch_unstable_shape<1024, 16, 1, 9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim,
-                                                                                 (unsigned)max_grid);
+                                                                                 (unsigned)max_grid, env_int("SMJ_XG_BULK", 1));
     return launch_unstable<9, FieldFn, false, LimitArray>(ctx, in, (u64 *)nullptr, n, f1, d_tab, lim);
 }
 u64 smj_smj_cap1(u64 k, double scale) { return smj_cap1(k, scale, 0); }
@@ -2002,6 +2065,9 @@ int smj_msd_pass_b_opt(SmjCtx *ctx, const u64 *a, u64 n, const u64 *d_tab, u64 *
     if (env_int("SMJ_SCATTER_ASYNC", 0)) {
         SMJ_LAUNCH(ctx, (k_msd_scatter2<true, true>), (unsigned)std::min<u64>(max_tiles, (u64)ctx->sm_count * 2), MSD_THREADS,
                    MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends, d_base2, d_cap2, d_bflag, shrink, 0u, (u32 *)nullptr);
+    } else if (env_int("SMJ_SCATTER_BULK", 0)) {
+        SMJ_LAUNCH(ctx, (k_msd_scatter2<true, false, true>), max_tiles, MSD_THREADS, MSD_SCATTER_SMEM + MSD_NB * 8, a, b, d_tiles,
+                   d_tpref, f2, ends, d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2), (u32 *)nullptr);
     } else {
         SMJ_LAUNCH(ctx, k_msd_scatter2<true>, max_tiles, MSD_THREADS, MSD_SCATTER_SMEM, a, b, d_tiles, d_tpref, f2, ends,
                    d_base2, d_cap2, d_bflag, shrink, (u32)(ctx->sm_count * 2), (u32 *)nullptr);

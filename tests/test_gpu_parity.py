@@ -1053,3 +1053,27 @@ def test_scatter_async_staging_variant(smj, orc, monkeypatch):
     s = ol.rand_items(rng, 3_000_000, (1 << 28) - 1)
     st = _device_mway_stats(smj, r, s)
     assert (st.matches, st.checksum) == orc.join_bruteforce(r, s)
+
+
+def test_scatter_bulk_store_variant(smj, orc, monkeypatch):
+    """SMJ_SCATTER_BULK=1: every bin's run leaves the staging buffer as one bulk copy (TMA,
+    cp.async.bulk shared -> global) plus at most one plain store at either end -- the variant the
+    NVLink exchange pass of the join group uses by default.  Same join results (full and ragged
+    tiles, both levels, skipped runs of the overflow -> repair paths) as the oracle."""
+    monkeypatch.setenv("SMJ_SCATTER_BULK", "1")
+    rng = np.random.default_rng(99)
+    for n_r, n_s in ((1 << 21, (1 << 21) + 12345), (3_000_017, 2_500_001), (1 << 20, 1 << 20)):
+        r, s = orc.gen_unique(n_r, 5), orc.gen_fk(n_s, n_r, 6)
+        st = _device_mway_stats(smj, r, s)
+        assert (st.matches, st.checksum) == orc.join_bruteforce(r, s)
+        assert st.path == smj.PATH_MSD_OPT
+    r, s = orc.gen_unique(1 << 22, 7), orc.gen_unique(1 << 22, 8)
+    for hook in ("shrink1", "shrink2"):
+        monkeypatch.setenv("SMJ_MSD_TEST", hook)
+        st = _device_mway_stats(smj, r, s)
+        assert (st.matches, st.checksum) == orc.join_bruteforce(r, s), hook
+    monkeypatch.delenv("SMJ_MSD_TEST")
+    r = ol.rand_items(rng, 3_000_000, (1 << 28) - 1)
+    s = ol.rand_items(rng, 3_000_000, (1 << 28) - 1)
+    st = _device_mway_stats(smj, r, s)
+    assert (st.matches, st.checksum) == orc.join_bruteforce(r, s)
