@@ -176,19 +176,17 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
     for (u32 i = 0; i < nruns; i++)
         if (lens[i]) cur.push_back({runs[i], lens[i]});
     if (cur.empty()) return 0;
-    // SMJ_MERGE_PATH=kway: whole-word order, 3 .. 256 runs in ONE pass over DRAM (smj_kway.cu: value-range
-    // tiles from regular samples, every tile gathered, sorted in shared memory and written once; it
-    // declines tiny inputs and inputs with piles of equal words).  Measured on B200 it moves the
-    // fewest bytes (16 B/item + samples) but is bound by the shared-memory sort of the tiles
-    // (128 runs x 1 M: 5.7 ms against 2.1 ms for the range partition below and 6.2 ms for the
-    // rounds; profiles/r02_kway_tile.txt), so it is not the default.
+    // Whole-word order, 3 .. 256 runs: ONE pass over DRAM (smj_kway.cu: value-range tiles from regular
+    // samples, every tile gathered, put in order in shared memory by an interpolating counting sort
+    // and written once; 16 B/item + samples).  It declines tiny inputs and inputs with piles of equal
+    // words; then, or under SMJ_MERGE_PATH=sort / rounds, the paths below run.
     {
         const char *env = getenv("SMJ_MERGE_PATH");
         bool inplace = false;  // a run inside out would be overwritten while other tiles still read it
         u64  total   = 0;
         for (const Run &r : cur) total += r.n;
         for (const Run &r : cur) inplace |= (r.p < out + total && r.p + r.n > out);
-        if (mode == 0 && env && env[0] == 'k' && !inplace) {
+        if (mode == 0 && !(env && (env[0] == 's' || env[0] == 'r')) && !inplace) {
             std::vector<const u64 *> ps;
             std::vector<u64>         ls;
             for (const Run &r : cur) {

@@ -628,11 +628,13 @@ def test_multiway_merge_many_runs_via_partition(smj, orc, monkeypatch):
 
 @pytest.mark.parametrize("nruns", [3, 17, 128, 256, 300])
 def test_kway_merge_one_pass(smj, orc, nruns, monkeypatch):
-    """smjdev_multiway_merge under SMJ_MERGE_PATH=kway takes the one-pass k-way merge (csrc/smj_kway.cu,
-    the counterpart of avx_multiway_merge, src/merge/avx_multiwaymerge.c:199-338): value-range tiles
-    from regular samples, gathered, sorted in shared memory, written once.  Same output as the
-    oracle for runs of very different lengths, empty runs, heavy duplicates (tiles overflow -> the
-    rounds take over) and more than 256 runs (declined)."""
+    """smjdev_multiway_merge takes the one-pass k-way merge (csrc/smj_kway.cu, the counterpart of
+    avx_multiway_merge, src/merge/avx_multiwaymerge.c:199-338): value-range tiles from regular
+    samples, gathered (three gather shapes: k <= 8, k < 64, k >= 64), put in order in shared memory
+    by the interpolating counting sort -- or, for tiles whose values are not evenly spread (the
+    "disjoint" shape) and under SMJ_KWAY_TILE=sort, by the comparison sort -- and written once.
+    Same output as the oracle for runs of very different lengths, empty runs, heavy duplicates
+    (tiles overflow -> another path takes over) and more than 256 runs (declined)."""
     monkeypatch.setenv("SMJ_MERGE_PATH", "kway")
     rng = np.random.default_rng(nruns)
     lens = [int(x) for x in rng.integers(0, 2 * 700_000 // nruns, size=nruns)]
@@ -648,8 +650,12 @@ def test_kway_merge_one_pass(smj, orc, nruns, monkeypatch):
         out, tmp = smj.DeviceBuffer(exp.size), smj.DeviceBuffer(exp.size)
         ptrs = (C.c_void_p * nruns)(*[b.ptr for b in bufs])
         ln = (C.c_uint64 * nruns)(*[x.size for x in runs])
-        smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, ln, nruns, 0), name)
-        assert np.array_equal(out.to_host(), exp), name
+        for tile in ("count", "sort"):
+            monkeypatch.setenv("SMJ_KWAY_TILE", tile)
+            smj.check(smj.lib.smjdev_memset(out.ptr, 0, exp.size * 8), "memset")
+            smj.check(smj.lib.smjdev_multiway_merge(out.ptr, tmp.ptr, ptrs, ln, nruns, 0), name)
+            assert np.array_equal(out.to_host(), exp), (name, tile)
+        monkeypatch.delenv("SMJ_KWAY_TILE")
         for b, x in zip(bufs, runs):
             assert np.array_equal(b.to_host(), x), "inputs must stay unmodified"
         for b in bufs + [out, tmp]:

@@ -87,8 +87,8 @@ def main():
     ptrs = (C.c_void_p * runs)(*[runbuf.ptr + 8 * per * i for i in range(runs)])
     lens = (C.c_uint64 * runs)(*[per] * runs)
     ms = timed(lambda: smj.check(lib.smjdev_multiway_merge(a.ptr, b.ptr, ptrs, lens, runs, 0)), args.reps)
-    phase("multiway_merge_128_runs", ms, per * runs)  # default: range partition of the union (MSD sort)
-    for how in ("kway", "rounds"):  # one-pass k-way merge (csrc/smj_kway.cu) / log2(k) pairwise rounds
+    phase("multiway_merge_128_runs", ms, per * runs)  # default: one-pass k-way merge (csrc/smj_kway.cu)
+    for how in ("sort", "rounds"):  # range partition of the union (MSD sort) / log2(k) pairwise rounds
         os.environ["SMJ_MERGE_PATH"] = how
         ms = timed(lambda: smj.check(lib.smjdev_multiway_merge(a.ptr, b.ptr, ptrs, lens, runs, 0)), args.reps)
         phase("multiway_merge_128_runs_" + how, ms, per * runs)
