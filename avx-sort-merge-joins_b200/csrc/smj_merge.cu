@@ -85,7 +85,11 @@ template <int MODE>
 __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restrict__ jobs,
                                                          u32 njobs, u64 total_tiles,
                                                          const u64 *__restrict__ diag_a) {
-    __shared__ u64 s_in[MP_TILE];
+    // logical position i lives at word MPP(i) = i + i / 8: a thread's 8 consecutive outputs and the
+    // cursors of neighbouring threads (a few items apart in either piece) would otherwise fall on one
+    // or two banks (the write-back alone was an 8-way conflict)
+    __shared__ u64 s_in[MP_TILE + MP_TILE / 8 + 1];
+#define MPP(i) ((i) + ((i) >> 3))
     const u64      t  = blockIdx.x;
     const u32      ji = find_job(jobs, njobs, t);
     const MergeJob j  = jobs[ji];
@@ -99,28 +103,46 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
     const u32 la = (u32)(a1 - a0), lb = (u32)(b1 - b0), cnt = la + lb;
 
     for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS)
-        s_in[i] = (i < la) ? ld_stream(j.a + a0 + i) : ld_stream(j.b + b0 + (i - la));
+        s_in[MPP(i)] = (i < la) ? ld_stream(j.a + a0 + i) : ld_stream(j.b + b0 + (i - la));
     __syncthreads();
 
-    const u64 *sa = s_in, *sb = s_in + la;
-    const u32  d  = min((u32)(threadIdx.x * MP_IPT), cnt);
-    u32        ai = (u32)merge_path<MODE>(sa, (u64)la, sb, (u64)lb, (u64)d);
-    u32        bi = d - ai;
-    u64        r[MP_IPT];
+    const u32 d = min((u32)(threadIdx.x * MP_IPT), cnt);
+    u32       ai, bi;
+    {  // merge path inside the tile
+        u32 lo = d > lb ? d - lb : 0, hi = d < la ? d : la;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (a_goes_first<MODE>(s_in[MPP(mid)], s_in[MPP(la + d - 1 - mid)]))
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        ai = lo;
+        bi = d - lo;
+    }
+    u64 r[MP_IPT];
+    // heads in registers: one shared-memory load per output item
+    u64 ha = ai < la ? s_in[MPP(ai)] : 0ull, hb = bi < lb ? s_in[MPP(la + bi)] : 0ull;
 #pragma unroll
     for (int k = 0; k < MP_IPT; k++) {
         r[k] = 0;
         if (d + k < cnt) {
-            bool take_a = (bi >= lb) || (ai < la && a_goes_first<MODE>(sa[ai], sb[bi]));
-            r[k]        = take_a ? sa[ai++] : sb[bi++];
+            const bool take_a = (bi >= lb) || (ai < la && a_goes_first<MODE>(ha, hb));
+            r[k]              = take_a ? ha : hb;
+            ai += take_a ? 1u : 0u;
+            bi += take_a ? 0u : 1u;
+            const u32 nidx = take_a ? ai : la + bi, nend = take_a ? la : cnt;
+            const u64 nxt  = nidx < nend ? s_in[MPP(nidx)] : 0ull;
+            if (take_a) ha = nxt; else hb = nxt;
         }
     }
     __syncthreads();  // everyone is done reading the inputs: reuse the buffer for the output
 #pragma unroll
     for (int k = 0; k < MP_IPT; k++)
-        if (d + k < cnt) s_in[d + k] = r[k];
+        if (d + k < cnt) s_in[MPP(d + k)] = r[k];
     __syncthreads();
-    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[i]);
+    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[MPP(i)]);
+#undef MPP
 }
 
 int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
@@ -179,14 +201,18 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
     // Whole-word order, 3 .. 256 runs: ONE pass over DRAM (smj_kway.cu: value-range tiles from regular
     // samples, every tile gathered, put in order in shared memory by an interpolating counting sort
     // and written once; 16 B/item + samples).  It declines tiny inputs and inputs with piles of equal
-    // words; then, or under SMJ_MERGE_PATH=sort / rounds, the paths below run.
+    // words; then, or under SMJ_MERGE_PATH=sort / rounds, the paths below run (SMJ_MERGE_PATH=kway
+    // forces it for 3 and 4 runs too).
     {
         const char *env = getenv("SMJ_MERGE_PATH");
         bool inplace = false;  // a run inside out would be overwritten while other tiles still read it
         u64  total   = 0;
         for (const Run &r : cur) total += r.n;
         for (const Run &r : cur) inplace |= (r.p < out + total && r.p + r.n > out);
-        if (mode == 0 && !(env && (env[0] == 's' || env[0] == 'r')) && !inplace) {
+        // (3 or 4 runs are two merge-path rounds of 0.61 ms per 128 M items: faster than the one pass,
+        // 1.22 against 1.45 ms; from 5 runs on the one pass wins, 8 runs 1.54 against 1.83 ms)
+        const bool want = env ? env[0] == 'k' : cur.size() >= 5;
+        if (mode == 0 && want && !inplace) {
             std::vector<const u64 *> ps;
             std::vector<u64>         ls;
             for (const Run &r : cur) {
