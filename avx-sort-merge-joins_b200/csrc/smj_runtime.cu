@@ -440,8 +440,9 @@ size_t stg_chunk() {
     return v;
 }
 struct Stager {
-    bool                   ready = false;
-    void                  *bounce[STG_SLOTS];
+    bool                   ready = false, ready_down = false;
+    void                  *bounce[STG_SLOTS];       // uploads
+    void                  *bounce_down[STG_SLOTS];  // downloads (the host READS these: never write-combined)
     cudaEvent_t            ev[STG_SLOTS];
     std::atomic<long long> done[STG_SLOTS];  // index of the last chunk whose event was recorded
     cudaStream_t           stream = nullptr;
@@ -460,10 +461,16 @@ Stager *stager_of(SmjCtx *c) {
 // st->mu held
 int stager_init(Stager *st) {
     if (st->ready) return 0;
+    // $SMJ_STAGE_WC=1: write-combined bounce buffers for uploads (the host only writes them, front to
+    // back; the DMA engine reads them without snooping the caches)
+    const char *wc = getenv("SMJ_STAGE_WC");
+    const unsigned flags = cudaHostAllocPortable | ((wc && atoi(wc)) ? cudaHostAllocWriteCombined : 0u);
     for (int i = 0; i < STG_SLOTS; i++) {
-        SMJ_CHECK(cudaHostAlloc(&st->bounce[i], stg_chunk(), cudaHostAllocPortable));
+        SMJ_CHECK(cudaHostAlloc(&st->bounce[i], stg_chunk(), flags));
+        st->bounce_down[i] = (flags & cudaHostAllocWriteCombined) ? nullptr : st->bounce[i];
         SMJ_CHECK(cudaEventCreateWithFlags(&st->ev[i], cudaEventDisableTiming));
     }
+    st->ready_down = !(flags & cudaHostAllocWriteCombined);
     SMJ_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
     SMJ_CHECK(cudaEventCreateWithFlags(&st->fence, cudaEventDisableTiming));
     st->ready = true;
@@ -473,8 +480,8 @@ int stager_init(Stager *st) {
 int stager_threads(size_t nchunks) {
     unsigned hw = std::thread::hardware_concurrency();
     const char *e = getenv("SMJ_STAGE_THREADS");
-    int t = e ? atoi(e) : (int)(hw ? hw / 2 : 4);
-    t     = std::max(1, std::min(t, 8));
+    int t = e ? atoi(e) : std::min((int)(hw ? hw / 2 : 4), 8);
+    t     = std::max(1, std::min(t, 32));
     return (int)std::min<size_t>((size_t)t, nchunks);
 }
 
@@ -484,6 +491,10 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
     std::lock_guard<std::mutex> lk(st->mu);
     int rc = stager_init(st);
     if (rc) return rc;
+    if (dir == 1 && !st->ready_down) {  // (write-combined upload ring: downloads get a ring of their own)
+        for (int i = 0; i < STG_SLOTS; i++) SMJ_CHECK(cudaHostAlloc(&st->bounce_down[i], stg_chunk(), cudaHostAllocPortable));
+        st->ready_down = true;
+    }
     // the device buffer may have been produced (or allocated) on the compute stream
     SMJ_CHECK(cudaEventRecord(st->fence, c->stream));
     SMJ_CHECK(cudaStreamWaitEvent(st->stream, st->fence, 0));
@@ -510,10 +521,10 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
                 e = cudaMemcpyAsync(dev + off, st->bounce[slot], len, cudaMemcpyHostToDevice, st->stream);
                 if (e == cudaSuccess) e = cudaEventRecord(st->ev[slot], st->stream);
             } else if (e == cudaSuccess) {
-                e = cudaMemcpyAsync(st->bounce[slot], dev + off, len, cudaMemcpyDeviceToHost, st->stream);
+                e = cudaMemcpyAsync(st->bounce_down[slot], dev + off, len, cudaMemcpyDeviceToHost, st->stream);
                 if (e == cudaSuccess) e = cudaEventRecord(st->ev[slot], st->stream);
                 if (e == cudaSuccess) e = cudaEventSynchronize(st->ev[slot]);
-                if (e == cudaSuccess) memcpy(host + off, st->bounce[slot], len);
+                if (e == cudaSuccess) memcpy(host + off, st->bounce_down[slot], len);
             }
             if (e != cudaSuccess) err.store((int)e);
             st->done[slot].store((long long)i);

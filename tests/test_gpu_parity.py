@@ -975,7 +975,7 @@ def test_tputbench_tool(smj):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     for phase in ("partition_7bits", "sort", "multiway_merge_128_runs", "multiway_merge_128_runs_rounds",
-                  "multiway_merge_128_runs_kway",
+                  "multiway_merge_128_runs_sort",
                   "merge_join_scan", "mway_join_total"):
         assert res["phases"][phase]["TPUT_Mtuples_s"] > 0 and res["phases"][phase]["MEMTPUT_GBs"] > 0, phase
     for path in ("hbm_d2d_GBs_read_plus_write", "pcie_h2d_pinned_GBs", "pcie_d2h_pinned_GBs", "pcie_h2d_pageable_staged_GBs"):
