@@ -260,6 +260,24 @@ def test_merge_join(smj, orc, nr, ns, kmax):
     ds.free()
 
 
+@pytest.mark.parametrize("nr,ns,kmax", [(6_000_000, 5_000_000, 4_000_000), (5_000_000, 4_500_000, 700)])
+def test_merge_join_many_tiles(smj, orc, nr, ns, kmax):
+    """More than 2048 tiles of the merge-path scan: the boundary records are stitched in two levels
+    (k_mj_fixup with a grid, then one CTA over the open records of its threads).  Mostly unique
+    keys (about every second tile boundary cuts a key) and 700 heavy keys (runs that span whole
+    tiles), count and checksum against the oracle's run formula."""
+    rng = np.random.default_rng(nr + kmax)
+    r = orc.sort(ol.rand_items(rng, nr, kmax))
+    s = orc.sort(ol.rand_items(rng, ns, kmax))
+    exp = orc.merge_join_runs(r, s)
+    dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+    cnt, cks = C.c_uint64(), C.c_uint64()
+    smj.check(smj.lib.smjdev_merge_join(dr.ptr, nr, ds.ptr, ns, C.byref(cnt), C.byref(cks)))
+    assert (cnt.value, cks.value) == exp
+    dr.free()
+    ds.free()
+
+
 def test_merge_join_interpolation(smj, orc):
     rng = np.random.default_rng(9)
     r = orc.sort(ol.make_unique(rng, 40000))
