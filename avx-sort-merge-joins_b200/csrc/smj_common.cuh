@@ -154,6 +154,63 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ---- bulk copies global -> shared (TMA, UBLKCP) completing on an mbarrier ------------------------
+// One thread arms the barrier with the number of bytes in flight and issues the copies; the copy
+// engine writes shared memory and counts the bytes off; everybody waits on the barrier's phase.
+// The copy costs the LSU pipe and the issue slots nothing (a tile staged with LDG + STS costs two
+// instructions per item and thread).  Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals) {
+    const u32 b = (u32)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    const u32 b = (u32)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst), b = (u32)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    const u32 b = (u32)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+// Staging of a contiguous global range src[0 .. n) (8-byte items, any 8-byte alignment) so that item i
+// lands at dst_even[mis + i], mis = (src is 16-byte aligned ? 0 : 1); dst_even is 16-byte aligned.
+// The 16-byte granules of the copy may include the item before src[0] (same 16-byte word, inside the
+// array); an odd last item is not part of the bulk copy (its granule would end past the array) and is
+// copied with plain instructions.  ONE thread, after mbar_init + a CTA barrier:
+//     bytes = a.bytes() + b.bytes();  a.plain(); b.plain();          // plain stores before the arrive
+//     mbar_arrive_expect_tx(bar, bytes);  a.issue(bar); b.issue(bar);
+// everybody: mbar_wait(bar, phase).
+struct BulkStage {
+    u64       *dst_even;
+    const u64 *src;
+    u32        n, mis;
+    __device__ __forceinline__ BulkStage(u64 *d, const u64 *s_, u32 n_)
+        : dst_even(d), src(s_), n(n_), mis((u32)(((uintptr_t)s_ >> 3) & 1)) {}
+    __device__ __forceinline__ u32 bytes() const { return n ? ((n + mis) & ~1u) * 8u : 0u; }
+    __device__ __forceinline__ void plain() const {
+        if (n && ((n + mis) & 1u)) dst_even[n + mis - 1] = src[n - 1];
+    }
+    __device__ __forceinline__ void issue(u64 *bar) const {
+        if (bytes()) bulk_g2s(dst_even, src - mis, bytes(), bar);
+    }
+};
+
 __device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
     u64 v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

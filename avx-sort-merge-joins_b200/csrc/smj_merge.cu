@@ -25,8 +25,8 @@ int smj_kway_merge(SmjCtx *ctx, u64 *out, const u64 *const *runs, const u64 *len
 namespace {
 
 constexpr int MP_THREADS = 512;
-constexpr int MP_IPT     = 8;
-constexpr int MP_TILE    = MP_THREADS * MP_IPT;  // 4096 items = 32 KB of shared memory
+constexpr int MP_IPT     = 9;  // odd: see k_mp_merge
+constexpr int MP_TILE    = MP_THREADS * MP_IPT;  // 4608 items = 36 KB of shared memory
 
 struct MergeJob {
     const u64 *a;
@@ -81,15 +81,17 @@ __global__ void __launch_bounds__(256) k_mp_partition(const MergeJob *__restrict
     diag_a[t]           = merge_path<MODE>(j.a, j.na, j.b, j.nb, diag);
 }
 
+// The two pieces of a tile are contiguous ranges of A and of B: ONE thread stages them with two bulk
+// copies (TMA, completion on an mbarrier) instead of an LDG + STS per item and thread.  The layout in
+// shared memory is therefore plain (no padding); bank conflicts are avoided by the ODD number of items
+// per thread: the write-back of a thread's 9 consecutive outputs and the cursors of neighbouring
+// threads (4.5 items apart in either piece) spread over the banks by themselves.
 template <int MODE>
 __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restrict__ jobs,
                                                          u32 njobs, u64 total_tiles,
                                                          const u64 *__restrict__ diag_a) {
-    // logical position i lives at word MPP(i) = i + i / 8: a thread's 8 consecutive outputs and the
-    // cursors of neighbouring threads (a few items apart in either piece) would otherwise fall on one
-    // or two banks (the write-back alone was an 8-way conflict)
-    __shared__ u64 s_in[MP_TILE + MP_TILE / 8 + 1];
-#define MPP(i) ((i) + ((i) >> 3))
+    __shared__ __align__(16) u64 s_in[MP_TILE + 4];  // A piece at [misA ..), B piece at [offB ..)
+    __shared__ __align__(8) u64 s_bar;
     const u64      t  = blockIdx.x;
     const u32      ji = find_job(jobs, njobs, t);
     const MergeJob j  = jobs[ji];
@@ -101,10 +103,23 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
     const u64 a0 = diag_a[t], a1 = last ? j.na : diag_a[t + 1];
     const u64 b0 = d0 - a0, b1 = d1 - a1;
     const u32 la = (u32)(a1 - a0), lb = (u32)(b1 - b0), cnt = la + lb;
+    const u64 *ga = j.a + a0, *gb = j.b + b0;
+    const u32 misA = la ? (u32)(((uintptr_t)ga >> 3) & 1) : 0u, misB = lb ? (u32)(((uintptr_t)gb >> 3) & 1) : 0u;
+    const u32 evenB = (misA + la + 1) & ~1u;  // 16-byte aligned start of B's staging area
+    const u32 offA = misA, offB = evenB + misB;
 
-    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS)
-        s_in[MPP(i)] = (i < la) ? ld_stream(j.a + a0 + i) : ld_stream(j.b + b0 + (i - la));
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const BulkStage sa_(s_in, ga, la), sb_(s_in + evenB, gb, lb);
+        const u32       bytes = sa_.bytes() + sb_.bytes();
+        sa_.plain();
+        sb_.plain();
+        mbar_arrive_expect_tx(&s_bar, bytes);
+        sa_.issue(&s_bar);
+        sb_.issue(&s_bar);
+    }
+    mbar_wait(&s_bar, 0);
 
     const u32 d = min((u32)(threadIdx.x * MP_IPT), cnt);
     u32       ai, bi;
@@ -112,7 +127,7 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
         u32 lo = d > lb ? d - lb : 0, hi = d < la ? d : la;
         while (lo < hi) {
             const u32 mid = (lo + hi) >> 1;
-            if (a_goes_first<MODE>(s_in[MPP(mid)], s_in[MPP(la + d - 1 - mid)]))
+            if (a_goes_first<MODE>(s_in[offA + mid], s_in[offB + d - 1 - mid]))
                 lo = mid + 1;
             else
                 hi = mid;
@@ -122,7 +137,7 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
     }
     u64 r[MP_IPT];
     // heads in registers: one shared-memory load per output item
-    u64 ha = ai < la ? s_in[MPP(ai)] : 0ull, hb = bi < lb ? s_in[MPP(la + bi)] : 0ull;
+    u64 ha = ai < la ? s_in[offA + ai] : 0ull, hb = bi < lb ? s_in[offB + bi] : 0ull;
 #pragma unroll
     for (int k = 0; k < MP_IPT; k++) {
         r[k] = 0;
@@ -131,18 +146,17 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restr
             r[k]              = take_a ? ha : hb;
             ai += take_a ? 1u : 0u;
             bi += take_a ? 0u : 1u;
-            const u32 nidx = take_a ? ai : la + bi, nend = take_a ? la : cnt;
-            const u64 nxt  = nidx < nend ? s_in[MPP(nidx)] : 0ull;
+            const bool more = take_a ? ai < la : bi < lb;
+            const u64  nxt  = more ? s_in[take_a ? offA + ai : offB + bi] : 0ull;
             if (take_a) ha = nxt; else hb = nxt;
         }
     }
     __syncthreads();  // everyone is done reading the inputs: reuse the buffer for the output
 #pragma unroll
     for (int k = 0; k < MP_IPT; k++)
-        if (d + k < cnt) s_in[MPP(d + k)] = r[k];
+        if (d + k < cnt) s_in[d + k] = r[k];
     __syncthreads();
-    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[MPP(i)]);
-#undef MPP
+    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[i]);
 }
 
 int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
