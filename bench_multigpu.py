@@ -100,6 +100,9 @@ def run(args, smj):
     kernel_ms = sum(p["ms"] for p in prof.values()) / args.steps
     value = 2 * n / (ms_step * 1e-3) / 1e6
     assert cnt == n
+    # the CPU oracle's full-size result for this workload (bench.py: ORACLE_RESULT), when it is known
+    if n in B.ORACLE_RESULT:
+        assert (cnt, cks) == B.ORACLE_RESULT[n], f"count / checksum {(cnt, cks)} differ from the oracle's {B.ORACLE_RESULT[n]}"
 
     # ---- end to end: each rank's slices start in pinned host memory
     if os.environ.get("SMJ_BENCH_NO_E2E"):  # very large --size: the pinned copies do not fit the host
