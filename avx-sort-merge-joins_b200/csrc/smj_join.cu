@@ -30,8 +30,8 @@
 namespace {
 
 constexpr int MJ_THREADS = 256;
-constexpr int MJ_IPT     = 16;
-constexpr int MJ_TILE    = MJ_THREADS * MJ_IPT;                 // 4096 merged items per CTA
+constexpr int MJ_IPT     = 18;                                   // see k_mj_tile
+constexpr int MJ_TILE    = MJ_THREADS * MJ_IPT;                 // 4608 merged items per CTA
 
 struct MjRec {
     u64 key;
@@ -67,23 +67,32 @@ __global__ void __launch_bounds__(256) k_mj_partition(const u64 *__restrict__ r,
 // records for k_mj_fixup, and the S piece the walk sees is SHORTENED by them, so that the walk needs
 // no per-item test for them.
 //
-// The walk: every thread finds its 16-item slice of the merge path (R before S on ties) and merges
+// The walk: every thread finds its 18-item slice of the merge path (R before S on ties) and merges
 // with two register-cached heads, one shared-memory load per step.  It carries the R RUN that ends
 // at its R cursor -- {key, items, sum of A} -- which is all an S item needs: an S item of that key
 // adds run_items to the count and run_sumA * B(s) to the checksum (sum over S items of a key =
 // sumA * sumB).  No head-of-run detection, no searches, duplicates on either side cost nothing
 // extra.  A thread that starts inside an R run first walks back to the run's start (one step for
-// unique keys).  Shared-memory index i lives at word i + i / 16: lanes whose cursors are ~8 or ~16
-// items apart would otherwise meet in one or two banks (round 1: 146 M of 241 M wavefronts were
-// bank conflicts).
-#define MJP(i) ((i) + ((i) >> 4))
-__global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict__ r, u64 nr,
+// unique keys).
+// The two pieces are contiguous ranges of R and of S: ONE thread stages them with two bulk copies
+// (TMA, completion on an mbarrier; an LDG + STS per item and thread was a sixth of the kernel's
+// instructions).  The layout in shared memory is therefore plain, and bank conflicts are avoided by
+// the number of items per thread: with 18, the cursors of neighbouring threads are ~9 items apart in
+// either piece and fall on different banks (with 16 they met in two banks: round 1, 146 M of 241 M
+// wavefronts were conflicts).  An EVEN number also keeps a warp convergent on primary-key joins,
+// where R and S items alternate in the merged order and every slice then starts with an R item
+// (17 items per thread: the lanes disagree at every step and the walk costs 76 instead of 52
+// instructions per step).  Measured, 128 M x 128 M / 32 M x 320 M: 16 items, padded layout, plain
+// loads 0.92 / 1.55 ms; 17 items + TMA 1.00 / 1.44; 18 items + TMA 0.82 / 1.41.
+
+__global__ void __launch_bounds__(MJ_THREADS, 6) k_mj_tile(const u64 *__restrict__ r, u64 nr,
                                                            const u64 *__restrict__ s, u64 ns,
                                                            const u64 *__restrict__ diag_r,
                                                            MjRec *__restrict__ recs,
                                                            unsigned char *__restrict__ rec_valid,
                                                            u64 *__restrict__ acc, int semi) {
-    __shared__ u64 s_it[MJP(MJ_TILE) + 1];  // R piece followed by S piece
+    __shared__ __align__(16) u64 s_it[MJ_TILE + 4];  // R piece at [offR ..), S piece at [offS ..)
+    __shared__ __align__(8) u64 s_bar;
     __shared__ u64 s_red[2][MJ_THREADS / 32];
     __shared__ u64 s_edge[4][2];  // {items, sum} of: R prefix, S prefix (key kf), R suffix, S suffix (key kl)
 
@@ -92,15 +101,27 @@ __global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict
     const u64 d1 = min(d0 + (u64)MJ_TILE, nr + ns);
     const u64 r0 = diag_r[t], r1 = diag_r[t + 1];
     const u64 s0 = d0 - r0, s1 = d1 - r1;
-    const u32 la = (u32)(r1 - r0), lb = (u32)(s1 - s0), cnt = la + lb;
+    const u32 la = (u32)(r1 - r0), lb = (u32)(s1 - s0);
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-#pragma unroll 8
-    for (u32 i = threadIdx.x; i < cnt; i += MJ_THREADS)
-        s_it[MJP(i)] = (i < la) ? ld_stream(r + r0 + i) : ld_stream(s + s0 + (i - la));
+    const u64 *gr = r + r0, *gs = s + s0;
+    const u32 misR = la ? (u32)(((uintptr_t)gr >> 3) & 1) : 0u, misS = lb ? (u32)(((uintptr_t)gs >> 3) & 1) : 0u;
+    const u32 evenS = (misR + la + 1) & ~1u;  // 16-byte aligned start of S's staging area
+    const u32 offR = misR, offS = evenS + misS;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
-#define SR(i) s_it[MJP(i)]
-#define SS(j) s_it[MJP(la + (j))]
+    if (threadIdx.x == 0) {
+        const BulkStage st_r(s_it, gr, la), st_s(s_it + evenS, gs, lb);
+        const u32       bytes = st_r.bytes() + st_s.bytes();
+        st_r.plain();
+        st_s.plain();
+        mbar_arrive_expect_tx(&s_bar, bytes);
+        st_r.issue(&s_bar);
+        st_s.issue(&s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+#define SR(i) s_it[offR + (i)]
+#define SS(j) s_it[offS + (j)]
 
     // ---- the tile's first / last key: their runs may continue in the neighbouring tiles
     const u32 kf = min(la ? key_of(SR(0)) : 0xffffffffu, lb ? key_of(SS(0)) : 0xffffffffu);
@@ -113,10 +134,10 @@ __global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict
     if (ex_f | ex_l) {  // block-uniform; about every second tile when both sides have the key
         if (warp < 4 && ((warp < 2) ? ex_f : ex_l)) {
             const bool is_r = !(warp & 1), pre = warp < 2;
-            const u32  len = is_r ? la : lb, base = is_r ? 0u : la, k = pre ? kf : kl;
+            const u32  len = is_r ? la : lb, base = is_r ? offR : offS, k = pre ? kf : kl;
             u64        c = 0, sum = 0;
             for (u32 i = lane; i < len; i += 32) {  // the run is a prefix / suffix of the sorted piece
-                const u64 x = s_it[MJP(base + (pre ? i : len - 1 - i))];
+                const u64 x = s_it[base + (pre ? i : len - 1 - i)];
                 if (key_of(x) != k) break;
                 c++;
                 sum += is_r ? smj_cks_a(x) : smj_cks_b(x);
@@ -137,7 +158,7 @@ __global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict
     const u32 sx  = ex_f ? (u32)s_edge[1][0] : 0u;
     const u32 lbw = lb - sx - (ex_l ? (u32)s_edge[3][0] : 0u);
     const u32 cw  = la + lbw;
-#define SW(j) s_it[MJP(la + sx + (j))]
+#define SW(j) s_it[offS + sx + (j)]
 
     u64 my_cnt = 0, my_cks = 0;
     const u32 d = min((u32)(threadIdx.x * MJ_IPT), cw);
@@ -180,9 +201,9 @@ __global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict
         // advance the cursor that was taken and load its next head (one shared-memory load)
         ai += take_r ? 1u : 0u;
         bi += take_r ? 0u : 1u;
-        const u32 nidx = take_r ? ai : la + sx + bi;
-        const u32 nend = take_r ? la : la + sx + lbw;
-        const u64 nxt  = (nidx < nend) ? s_it[MJP(nidx)] : 0ull;
+        const u32 nidx = take_r ? offR + ai : offS + sx + bi;
+        const u32 nend = take_r ? offR + la : offS + sx + lbw;
+        const u64 nxt  = (nidx < nend) ? s_it[nidx] : 0ull;
         if (take_r) {
             run_sa  = (same ? run_sa : 0ull) + smj_cks_a(x);
             run_cnt = same ? run_cnt + 1u : 1u;
@@ -228,7 +249,6 @@ __global__ void __launch_bounds__(MJ_THREADS, 4) k_mj_tile(const u64 *__restrict
         }
     }
 }
-#undef MJP
 
 // Stitch the per-tile boundary records: consecutive valid records with the same key form one run.
 // Every thread walks a contiguous chunk of the records: complete runs inside the chunk are

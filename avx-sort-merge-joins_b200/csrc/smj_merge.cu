@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_mp_partition(const MergeJob *__restrict
 // per thread: the write-back of a thread's 9 consecutive outputs and the cursors of neighbouring
 // threads (4.5 items apart in either piece) spread over the banks by themselves.
 template <int MODE>
-__global__ void __launch_bounds__(MP_THREADS) k_mp_merge(const MergeJob *__restrict__ jobs,
+__global__ void __launch_bounds__(MP_THREADS, 4) k_mp_merge(const MergeJob *__restrict__ jobs,
                                                          u32 njobs, u64 total_tiles,
                                                          const u64 *__restrict__ diag_a) {
     __shared__ __align__(16) u64 s_in[MP_TILE + 4];  // A piece at [misA ..), B piece at [offB ..)
