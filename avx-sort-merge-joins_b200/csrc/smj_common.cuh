@@ -154,6 +154,38 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// Bulk copies shared -> global (TMA, UBLKCP): one instruction of ONE thread writes a whole run of a
+// bin; the copy engine reads shared memory and issues the stores, so the run costs the LSU pipe
+// nothing.  Addresses and size are multiples of 16 bytes.  The writes of the generic proxy (STS)
+// have to be made visible to the asynchronous proxy first (fence_proxy_async + barrier).
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u32 bytes) {
+    const u32 s = (u32)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk copies of this thread have READ their source (the shared-memory buffer may be reused)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Stores the contiguous shared-memory range src[0 .. n) (8-byte items; src and dst have the same
+// 16-byte phase) to global memory: one bulk copy for the 16-byte aligned middle, plain stores for an
+// odd first / last item.  ONE thread, after every writer of the range has executed
+// fence_proxy_async() and a CTA barrier; it must bulk_wait_read() before the range is overwritten
+// or the CTA exits.
+__device__ __forceinline__ void bulk_store_items(u64 *dst, const u64 *src, u32 n) {
+    if (n && ((uintptr_t)dst & 8)) {
+        __stcs(dst, *src);
+        dst++, src++, n--;
+    }
+    if (n & 1) {
+        n--;
+        __stcs(dst + n, src[n]);
+    }
+    if (n) bulk_s2g(dst, src, n * 8u);
+    bulk_commit();
+}
+
 // ---- bulk copies global -> shared (TMA, UBLKCP) completing on an mbarrier ------------------------
 // One thread arms the barrier with the number of bytes in flight and issues the copies; the copy
 // engine writes shared memory and counts the bytes off; everybody waits on the barrier's phase.

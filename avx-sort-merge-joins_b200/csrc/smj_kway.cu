@@ -159,15 +159,15 @@ __global__ void __launch_bounds__(KW_THREADS) k_kw_tile(const KwRuns *__restrict
 constexpr int KC_SLOT_BITS = 13, KC_SLOTS = 1 << KC_SLOT_BITS, KC_PER = KC_SLOTS / KW_THREADS, KC_MAXRUN = 64;
 // a thread's KC_PER = 16 consecutive slots lie 17 words from its neighbour's (no bank conflicts in the scan)
 #define KCP(sl) ((sl) + ((sl) >> 4))
-constexpr size_t KC_SMEM = (size_t)KW_CAP * 8 + (size_t)(KCP(KC_SLOTS) + 1) * 4;
+constexpr size_t KC_SMEM = (size_t)(KW_CAP + 2) * 8 + (size_t)(KCP(KC_SLOTS) + 1) * 4;
 
 __global__ void __launch_bounds__(KW_THREADS, 2)
     k_kw_tile_count(const KwRuns *__restrict__ runs, u32 k, const u64 *__restrict__ pos, u64 *__restrict__ out,
                     u32 *__restrict__ state /* [0] a tile overflowed, [1] tiles on the redo list */,
                     u32 *__restrict__ redo) {
     extern __shared__ __align__(16) u64 s_dyn[];
-    u64 *stage = s_dyn;                      // [KW_CAP] the tile: gathered, then in order
-    u32 *cnt   = (u32 *)(stage + KW_CAP);    // [KCP(KC_SLOTS) + 1] counts, then cursors
+    u64 *stage = s_dyn;                      // [KW_CAP + 2] the tile: gathered, then in order (at the phase of its destination)
+    u32 *cnt   = (u32 *)(s_dyn + KW_CAP + 2);  // [KCP(KC_SLOTS) + 1] counts, then cursors
     __shared__ u64 s_lo[KW_MAXK], s_w64[KW_THREADS / 32], s_mm[2], s_base;
     __shared__ u32 s_len[KW_MAXK], s_off[KW_MAXK + 1], s_coff[KW_MAXK + 1], s_w[KW_THREADS / 32], s_wc[KW_THREADS / 32], s_bad;
     const u64 t = blockIdx.x;
@@ -216,6 +216,10 @@ __global__ void __launch_bounds__(KW_THREADS, 2)
         if (tid == 0) state[0] = 1u;
         return;
     }
+    // the tile is one contiguous range of the output: it is put in order at the 16-byte phase of its
+    // destination and leaves as ONE bulk copy shared -> global (TMA) instead of an LDS + STG per item
+    u64 *dst = out + s_base;
+    stage += ((uintptr_t)dst >> 3) & 1;
     // gather -- three shapes, each the fastest in its range of k (measured, 128 M items: k = 4 1.45 ms,
     // 16 1.73, 32 1.79, 64 1.77, 128 1.85, 256 2.13):
     if (k <= 8) {
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(KW_THREADS, 2)
 #pragma unroll
     for (int j = 0; j < SS_IPT; j++)
         if (tid + j * KW_THREADS < size) stage[atomicAdd(&cnt[KCP((u32)((x[j] - lo) >> shift))], 1u)] = x[j];
+    fence_proxy_async();
     __syncthreads();
     if (any_tie) {
         // cnt[slot] is now the END of the slot's run; it starts where the previous slot's ends
@@ -362,10 +367,13 @@ __global__ void __launch_bounds__(KW_THREADS, 2)
             }
             beg = end;
         }
+        fence_proxy_async();
         __syncthreads();
     }
-    u64 *dst = out + s_base;
-    for (u32 i = tid; i < size; i += KW_THREADS) st_stream(dst + i, stage[i]);
+    if (tid == 0) {
+        bulk_store_items(dst, stage, size);
+        bulk_wait_read();
+    }
 }
 #undef KCP
 }  // namespace

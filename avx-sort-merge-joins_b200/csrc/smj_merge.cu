@@ -152,11 +152,19 @@ __global__ void __launch_bounds__(MP_THREADS, 4) k_mp_merge(const MergeJob *__re
         }
     }
     __syncthreads();  // everyone is done reading the inputs: reuse the buffer for the output
+    // the merged tile is one contiguous range of the output: it is put together at the 16-byte phase of
+    // its destination and leaves as ONE bulk copy shared -> global (instead of an LDS + STG per item)
+    u64      *gout = j.out + d0;
+    const u32 ph   = (u32)(((uintptr_t)gout >> 3) & 1);
 #pragma unroll
     for (int k = 0; k < MP_IPT; k++)
-        if (d + k < cnt) s_in[d + k] = r[k];
+        if (d + k < cnt) s_in[ph + d + k] = r[k];
+    fence_proxy_async();
     __syncthreads();
-    for (u32 i = threadIdx.x; i < cnt; i += MP_THREADS) st_stream(j.out + d0 + i, s_in[i]);
+    if (threadIdx.x == 0) {
+        bulk_store_items(gout, s_in + ph, cnt);
+        bulk_wait_read();
+    }
 }
 
 int run_jobs(SmjCtx *ctx, const std::vector<MergeJob> &jobs_h, int mode) {
@@ -223,9 +231,9 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
         u64  total   = 0;
         for (const Run &r : cur) total += r.n;
         for (const Run &r : cur) inplace |= (r.p < out + total && r.p + r.n > out);
-        // (3 or 4 runs are two merge-path rounds of 0.61 ms per 128 M items: faster than the one pass,
-        // 1.22 against 1.45 ms; from 5 runs on the one pass wins, 8 runs 1.54 against 1.83 ms)
-        const bool want = env ? env[0] == 'k' : cur.size() >= 5;
+        // (up to 16 runs the merge-path rounds of 0.45 ms per 128 M items are faster than the one pass:
+        // 8 runs 1.34 against 1.54 ms, 16 runs 1.80 against 1.76; 32 runs 2.25 against 1.75)
+        const bool want = env ? env[0] == 'k' : cur.size() > 16;
         if (mode == 0 && want && !inplace) {
             std::vector<const u64 *> ps;
             std::vector<u64>         ls;
@@ -238,16 +246,16 @@ int smj_multiway_merge(SmjCtx *ctx, u64 *out, u64 *tmp, const u64 *const *runs, 
             if (used) return 0;
         }
     }
-    // Many runs, whole-word order, large total: the merged sequence is the sorted union of the runs
-    // (ties are bit-identical items), and range-partitioning the union MSD-first (smj_msdsort.cu,
-    // 48 B/item) moves fewer bytes than log2(k) merge-path rounds (16 B/item each) from 8 runs on:
-    // 128 runs of 1 M tuples 6.2 -> 2.4 ms.  The runs are gathered into tmp (they need not be
+    // More than 16 runs in whole-word order that the one-pass merge declined (or SMJ_MERGE_PATH=sort):
+    // the merged sequence is the sorted union of the runs (ties are bit-identical items), and
+    // range-partitioning the union MSD-first (smj_msdsort.cu, 48 B/item) beats log2(k) merge-path
+    // rounds (16 B/item each): 128 runs of 1 M tuples 3.2 -> 2.2 ms.  The runs are gathered into tmp (they need not be
     // adjacent) and sorted into out; the sort declines what it does not suit and the rounds run.
     {
         u64 total = 0;
         for (const Run &r : cur) total += r.n;
         const char *env = getenv("SMJ_MERGE_PATH");  // "rounds" disables this shortcut
-        if (mode == 0 && cur.size() >= 8 && !(env && env[0] == 'r')) {
+        if (mode == 0 && (env ? env[0] == 's' && cur.size() >= 8 : cur.size() > 16)) {
             u64 off = 0;
             bool aliased = false;  // a run inside tmp or out cannot be gathered in place
             for (const Run &r : cur)

@@ -590,20 +590,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Bulk copies shared -> global (TMA, UBLKCP): one instruction of ONE thread writes a whole run of a
-// bin; the copy engine reads shared memory and issues the stores, so the run costs the LSU pipe
-// nothing.  Addresses and size are multiples of 16 bytes.  The writes of the generic proxy (STS)
-// have to be made visible to the asynchronous proxy first (fence_proxy_async + barrier).
-__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u32 bytes) {
-    const u32 s = (u32)__cvta_generic_to_shared(smem_src);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(s), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all bulk copies of this thread have READ their source (the shared-memory buffer may be reused)
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // the tile's items, thread-strided: item[j] = src[j * THREADS + thread]
 template <int THREADS, int IPT, bool FULL>
 __device__ __forceinline__ void unstable_load(u64 (&item)[IPT], const u64 *__restrict__ src, u32 valid) {
