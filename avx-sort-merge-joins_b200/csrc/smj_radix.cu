@@ -497,10 +497,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
     __shared__ u32 s_wsum[32];
 
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < Cfg::WARPS * NB; i += THREADS) s_whist[i] = 0;
+    // (16-byte stores: the two arrays are 2 x 32 KB, a word per thread and store was an eighth of the
+    // kernel's shared-memory instructions)
+    static_assert((Cfg::WARPS * NB) % 4 == 0 && (Cfg::TILE * 8) % 16 == 0, "16-byte zeroing");
+    for (int i = threadIdx.x; i < Cfg::WARPS * NB / 4; i += THREADS) ((uint4 *)s_whist)[i] = make_uint4(0, 0, 0, 0);
     if (RANK == 1) {
         static_assert(Cfg::WARPS * NB * 4 <= Cfg::TILE * 8, "mask array must fit the staging area");
-        for (int i = threadIdx.x; i < Cfg::WARPS * NB; i += THREADS) ((u32 *)s_items)[i] = 0;
+        for (int i = threadIdx.x; i < Cfg::WARPS * NB / 4; i += THREADS) ((uint4 *)s_items)[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const u32 tile   = s_tile;
