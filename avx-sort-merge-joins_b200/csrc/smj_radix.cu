@@ -45,12 +45,28 @@ __global__ void __launch_bounds__(256) k_bits_reduce(const u64 *__restrict__ in,
     // ascend needs no payload passes: a stable sort on the key alone gives the whole-word order.
     u64 vor = 0, vand = ~0ull, flags = 0;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u64 a = ld_stream(in + i);
-        const u64 p = i ? in[i - 1] : 0ull;  // the neighbour's load: same sector, served by L1/L2
-        vor |= a;
-        vand &= a;
-        flags |= (a < p ? 1ull : 0ull) | ((u32)a < (u32)p ? 2ull : 0ull);
+    constexpr int UN = 8;  // independent loads in flight per thread
+    // (the loop condition is the same for all lanes of a warp: the shuffles below need every lane)
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 - lane_id() < n; i0 += UN * stride) {
+        u64 a[UN], p0[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+            const u64 i = i0 + u * stride;
+            a[u]        = i < n ? ld_stream(in + i) : 0ull;
+            // the predecessor is the neighbouring lane's item; only lane 0 loads it (same or previous sector)
+            p0[u] = (i < n && i && lane_id() == 0) ? in[i - 1] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+            const u64 i  = i0 + u * stride;
+            const u64 up = __shfl_up_sync(SMJ_FULL_MASK, a[u], 1);
+            const u64 p  = lane_id() ? up : p0[u];
+            if (i < n) {
+                vor |= a[u];
+                vand &= a[u];
+                flags |= (a[u] < p ? 1ull : 0ull) | ((u32)a[u] < (u32)p ? 2ull : 0ull);
+            }
+        }
     }
     vor   = warp_reduce_or(vor);
     vand  = warp_reduce_and(vand);
