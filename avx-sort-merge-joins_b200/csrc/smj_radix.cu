@@ -989,6 +989,8 @@ int smj_item_bits(SmjCtx *ctx, const u64 *in, u64 n, u64 *h_bits) {
 
 int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
                       u64 **sorted);
+static int lsd_sort_bits_impl(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
+                              u64 **sorted, u64 *exact_bits);
 
 int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, u64 **sorted) {
     *sorted = const_cast<u64 *>(in);
@@ -999,6 +1001,28 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
         return smj_small_sort(ctx, in, a, n, key_only == 1);
     }
     u64 h_bits[3];
+    // Key-only sorts of large inputs do not read the data just to learn which key bits vary (0.25 ms per
+    // 128 M items): the digit plan comes from a SAMPLE of 2^17 items, the histogram pass -- which reads
+    // everything anyway -- accumulates the exact OR / AND on the way, and the host checks before the
+    // scatter passes that no key bit outside the plan varies; if one does (a sampling miss) the plan
+    // is redone from the exact bits the histogram pass has just delivered.  (The order flags of the
+    // full probe only matter to whole-word sorts.)
+    if (key_only && n >= (1ull << 22) && !getenv("SMJ_NO_SAMPLED_BITS")) {
+        SmjScratch sc(ctx);
+        u64 *d_bits = (u64 *)sc.get(16);
+        if (!d_bits) return smj_fail_msg("smj_lsd_sort: scratch allocation failed");
+        const u64 init[2] = {0ull, ~0ull};
+        SMJ_CHECK(cudaMemcpyAsync(d_bits, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+        SMJ_LAUNCH(ctx, k_bits_sample, 128, 256, 0, in, n, std::max<u64>(1, n >> 17), d_bits);
+        SMJ_CHECK(cudaMemcpyAsync(h_bits, d_bits, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+        h_bits[2] = 3;  // nothing is known about the order
+        u64 exact[2] = {0, 0};
+        int rc = lsd_sort_bits_impl(ctx, in, a, b, n, key_only, h_bits, sorted, exact);
+        if (rc <= 0) return rc;  // done (or failed)
+        h_bits[0] = exact[0], h_bits[1] = exact[1];  // rc == 1: the sample missed a varying key bit
+        return lsd_sort_bits_impl(ctx, in, a, b, n, key_only, h_bits, sorted, nullptr);
+    }
     int rc = smj_item_bits(ctx, in, n, h_bits);
     if (rc) return rc;
     return smj_lsd_sort_bits(ctx, in, a, b, n, key_only, h_bits, sorted);
@@ -1009,6 +1033,13 @@ int smj_lsd_sort(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only
 // superset that says "ascending" hold for every contiguous part).  No host synchronisation.
 int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
                       u64 **sorted) {
+    return lsd_sort_bits_impl(ctx, in, a, b, n, key_only, h_bits, sorted, nullptr);
+}
+// exact_bits != null (key-only sorts): h_bits is a guess; the histogram pass delivers the exact OR / AND
+// into exact_bits[0..1], the host synchronises and returns 1 -- before any scatter pass -- when a key bit
+// outside the guess varies.
+static int lsd_sort_bits_impl(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key_only, const u64 *h_bits,
+                              u64 **sorted, u64 *exact_bits) {
     *sorted = const_cast<u64 *>(in);
     const u64 *buf = in;
     if (n <= 1) return 0;
@@ -1047,7 +1078,11 @@ int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key
         }
         v = (end >= 64) ? 0 : (v >> end) << end;
     }
-    if (plan.nd == 0) return 0;  // all items equal (on the compared bits): already sorted
+    if (plan.nd == 0 && !exact_bits) return 0;  // all items equal (on the compared bits): already sorted
+    if (plan.nd == 0) {  // a guess that says "all keys equal" is checked with a plan of one digit
+        plan.d[0].sub = 0, plan.d[0].shift = 32, plan.d[0].mask = 1;
+        plan.nd = 1;
+    }
 
     const size_t sbytes = status_bytes(n);
     u64 *d_hist   = (u64 *)sc.get((size_t)plan.nd * RADIX_NB * 8);
@@ -1060,9 +1095,21 @@ int smj_lsd_sort_bits(SmjCtx *ctx, const u64 *in, u64 *a, u64 *b, u64 n, int key
     SMJ_CHECK(cudaMemsetAsync(d_status, 0, sbytes * plan.nd, ctx->stream));
     SMJ_CHECK(cudaMemsetAsync(d_count, 0, sizeof(u32) * 8, ctx->stream));
     SMJ_ITEMS(ctx, n);
-    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, buf, n, plan, d_hist,
-               (u64 *)nullptr);
+    u64 *d_exact = nullptr;
+    if (exact_bits) {
+        d_exact = (u64 *)sc.get(16);
+        if (!d_exact) return smj_fail_msg("smj_lsd_sort: scratch allocation failed");
+        const u64 init[2] = {0ull, ~0ull};
+        SMJ_CHECK(cudaMemcpyAsync(d_exact, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SMJ_LAUNCH(ctx, k_hist_digits, hist_grid(ctx, n, 512, 16), 512, 0, buf, n, plan, d_hist, d_exact);
     SMJ_LAUNCH(ctx, k_bases_multi, plan.nd, RADIX_NB, 0, d_hist, d_bases);
+    if (exact_bits) {
+        SMJ_CHECK(cudaMemcpyAsync(exact_bits, d_exact, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        SMJ_CHECK(cudaStreamSynchronize(ctx->stream));
+        const u64 key_bits = 0xffffffff00000000ull;
+        if ((exact_bits[0] & ~exact_bits[1] & key_bits) & ~(h_bits[0] & ~h_bits[1])) return 1;  // the plan misses a varying bit
+    }
 
     const u64 *cur = in;
     for (int k = 0; k < plan.nd; k++) {

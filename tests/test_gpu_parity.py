@@ -101,6 +101,37 @@ def test_device_sort(smj, orc, n, algo):
             b.free()
 
 
+def test_key_sort_with_sampled_bit_plan(smj, orc, monkeypatch):
+    """Key-only sorts of >= 2^22 items plan their radix passes from a SAMPLE of the key bits and
+    verify the plan against the exact OR / AND the histogram pass computes on the way.  Same
+    (stable) result as the oracle when the sample is right, when it misses a varying bit (one item
+    with a high key bit at a place the sample does not look: the plan is redone from the exact
+    bits), when all keys are equal, and with the sampling switched off."""
+    rng = np.random.default_rng(4242)
+    n = (1 << 22) + 12345
+    plain = ol.rand_items(rng, n, 1 << 20)
+    missed = plain.copy()
+    missed[1] |= np.uint64(1 << 29) << np.uint64(32)       # index 1 is not a multiple of the sample stride
+    missed[n - 3] |= np.uint64(1 << 27) << np.uint64(32)
+    equal = (plain & np.uint64(0xFFFFFFFF)) | (np.uint64(99) << np.uint64(32))
+    one_off = equal.copy()
+    one_off[7] = (np.uint64(5) << np.uint64(32)) | np.uint64(1)  # "all keys equal" according to the sample only
+    for name, items in (("plain", plain), ("missed", missed), ("equal", equal), ("one_off", one_off)):
+        exp = orc.sort_key_stable(items)
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("SMJ_NO_SAMPLED_BITS", "1")
+            buf, tmp = smj.DeviceBuffer.from_host(items), smj.DeviceBuffer(n)
+            res = C.c_void_p()
+            smj.check(smj.lib.smjdev_sort(buf.ptr, tmp.ptr, n, 1, 0, C.byref(res)), "sort")
+            smj.check(smj.lib.smjdev_sync())
+            got = (buf if res.value == buf.ptr else tmp).to_host()
+            assert np.array_equal(got, exp), (name, off)
+            buf.free()
+            tmp.free()
+            monkeypatch.delenv("SMJ_NO_SAMPLED_BITS", raising=False)
+
+
 @pytest.mark.parametrize("n", [0, 1, 100, 255, 16384, 32684, 81920, 1000003])
 def test_avxsort_tuples_host_api(smj, orc, n):
     """avxsort_tuples with host buffers: sorted contents, pointer-swap contract and the buffer the
