@@ -52,7 +52,7 @@ struct BucketSet {
 };
 int  smj_bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u64 *d_state, u32 *d_list);
 int  smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits, u64 *d_state,
-                     u32 *d_list, u64 *acc);
+                     u32 *d_list, u64 *acc, const u32 *d_range = nullptr /* device: first and one-past-last bucket in use */);
 bool smj_bucket_join_valid(const u64 *h_state, u32 lbits);
 extern const u64 MSD_STATE_INIT[16];
 int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc, int semi = 0);

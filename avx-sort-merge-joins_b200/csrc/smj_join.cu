@@ -442,8 +442,15 @@ __global__ void __launch_bounds__(BJ_WARPS * 32, 4) k_bucket_join(const u64 *__r
                                                                const u64 *__restrict__ se_,
                                                                u32 nbuckets, u32 lo_shift, u32 lbits,
                                                                u64 big, u32 *next_bucket,
-                                                               u64 *__restrict__ acc) {
+                                                               u64 *__restrict__ acc,
+                                                               const u32 *__restrict__ range) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // range != null (join group): only the buckets [range[0], range[1]) can hold anything on this GPU
+    u32 first_bucket = 0;
+    if (range) {
+        first_bucket = range[0];
+        nbuckets     = range[1];
+    }
     const u32 slots = 1u << lbits, mask = slots - 1;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per warp: u64 sumA[slots] followed by u32 cnt[slots]
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(BJ_WARPS * 32, 4) k_bucket_join(const u64 *__r
     constexpr int UN    = 8;  // loads in flight per lane and relation
     while (true) {
         u32 b0 = 0;
-        if (lane == 0) b0 = atomicAdd(next_bucket, CHUNK);
+        if (lane == 0) b0 = first_bucket + atomicAdd(next_bucket, CHUNK);
         b0 = __shfl_sync(SMJ_FULL_MASK, b0, 0);
         if (b0 >= nbuckets) break;
         // lanes 0..15 fetch the 4 x {r0, r1, s0, s1} of the chunk in one go
@@ -1016,7 +1023,7 @@ int smj_bucket_collect(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u64 
 // key domain (lbits > 10), is left to the general sort + scan path.  d_state[1] is the bucket
 // counter (zero on entry).
 int smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_shift, u32 lbits,
-                    u64 *d_state, u32 *d_list, u64 *acc) {
+                    u64 *d_state, u32 *d_list, u64 *acc, const u32 *d_range) {
     const u32 nb2 = 512u * 512u;
     u32 *d_next = (u32 *)(d_state + 1);
     if (lbits > 10) {
@@ -1044,7 +1051,7 @@ int smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo_
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200u * 1024u) / std::max<size_t>(smem, 1)));
     SMJ_ITEMS(ctx, R.n + S.n);
     SMJ_LAUNCH(ctx, k_bucket_join, ctx->sm_count * per_sm, BJ_WARPS * 32, smem, R.items, R.starts, R.ends,
-               S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc);
+               S.items, S.starts, S.ends, nb2, lo_shift, lbits, BJ_BIG, d_next, acc, d_range);
     u32 *d_pref = d_list + nb2 / 2;  // (the list of heavy buckets is short: its upper half holds the chunk prefix)
     SMJ_LAUNCH(ctx, k_big_chunks, 1, 1024, 0, S.starts, S.ends, d_list, (u32 *)(d_state + 6), d_pref, nb2 / 2);
     SMJ_ITEMS(ctx, S.n);

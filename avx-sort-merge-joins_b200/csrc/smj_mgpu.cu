@@ -75,6 +75,7 @@ struct XgLayout {  // what k_xg_layout leaves on the device
     u32 status, abort;
     u64 gbits[4];                 // global sampled OR_R AND_R OR_S AND_S
     u64 n_recv[2];                // items this rank received (k_xg_segs)
+    u32 own_range[2];             // second-level buckets this rank owns: [first, one past the last)
     u64 sent[2];                  // items this rank stored into OTHER ranks' buffers
     u32 owner[XG_NB];
     u64 tab[2][3][XG_NB];         // pass A: cursors, starts, limits (absolute item addresses)
@@ -259,6 +260,8 @@ __global__ void __launch_bounds__(XG_NB) k_xg_layout(const XgPeers *__restrict__
         lay->status = s_status;
         for (int q = 0; q < 4; q++) lay->gbits[q] = gb[q];
         lay->n_recv[0] = lay->n_recv[1] = lay->sent[0] = lay->sent[1] = 0;
+        lay->own_range[0] = s_first[me] * (u32)XG_NB;
+        lay->own_range[1] = ((me + 1 < world) ? s_first[me + 1] : (u32)XG_NB) * (u32)XG_NB;
     }
 }
 
@@ -627,7 +630,7 @@ int smjdev_group_join(void *group, const uint64_t *r_, uint64_t nr, const uint64
     const u32 lo_shift = have_plan ? pl.lo_shift : 32u, lbits = have_plan ? pl.lbits : 1u;
     const BucketSet R = {bR, offR, opt2[0] ? endR : offR + 1, g->cap[0]}, S = {bS, offS, opt2[1] ? endS : offS + 1, g->cap[1]};
     if ((rc = smj_bucket_collect(ctx, R, S, d_state, d_list))) return rc;
-    if ((rc = smj_bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc))) return rc;
+    if ((rc = smj_bucket_join(ctx, R, S, lo_shift, lbits, d_state, d_list, acc, g->d_lay->own_range))) return rc;
     SMJ_LAUNCH(ctx, k_xg_post_result, W, 32, 0, g->d_peers, me, acc, d_state, lbits, g->d_lay, epoch, g->ctl, W,
                &g->d_lay->abort, g->d_lay->out);
     u64 h[12];
