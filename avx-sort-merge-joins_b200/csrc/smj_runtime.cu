@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -424,6 +425,7 @@ int smjdev_ipc_close(void *peer_ptr) {
 // ---------------------------------------------------------------------------------------
 #include <atomic>
 #include <thread>
+extern "C" void smj_stage_copy(void *dst, const void *src, size_t n);  // host/smj_copy.c
 
 namespace {
 constexpr int    STG_SLOTS = 16;
@@ -500,7 +502,13 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
     SMJ_CHECK(cudaStreamWaitEvent(st->stream, st->fence, 0));
     const size_t STG_CHUNK = stg_chunk();
     const size_t nchunks = (bytes + STG_CHUNK - 1) / STG_CHUNK;
-    for (int i = 0; i < STG_SLOTS; i++) st->done[i].store((long long)i - STG_SLOTS);
+    // slots in use: $SMJ_STAGE_SLOTS (2 .. 16)
+    static const int NSLOT = [] {
+        const char *e = getenv("SMJ_STAGE_SLOTS");
+        const int   v = e ? atoi(e) : STG_SLOTS;
+        return v >= 2 && v <= STG_SLOTS ? v : STG_SLOTS;
+    }();
+    for (int i = 0; i < NSLOT; i++) st->done[i].store((long long)i - NSLOT);
     std::atomic<size_t> next{0};
     std::atomic<int>    err{0};
     const int           device = c->device;
@@ -512,12 +520,12 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
         while (!err.load()) {
             const size_t i = next.fetch_add(1);
             if (i >= nchunks) break;
-            const int    slot = (int)(i % STG_SLOTS);
+            const int    slot = (int)(i % NSLOT);
             const size_t off = i * STG_CHUNK, len = std::min(STG_CHUNK, bytes - off);
-            while (st->done[slot].load() != (long long)i - STG_SLOTS) std::this_thread::yield();
+            while (st->done[slot].load() != (long long)i - NSLOT) std::this_thread::yield();
             cudaError_t e = cudaEventSynchronize(st->ev[slot]);  // the slot's previous DMA is over
             if (e == cudaSuccess && dir == 0) {
-                memcpy(st->bounce[slot], host + off, len);
+                smj_stage_copy(st->bounce[slot], host + off, len);
                 e = cudaMemcpyAsync(dev + off, st->bounce[slot], len, cudaMemcpyHostToDevice, st->stream);
                 if (e == cudaSuccess) e = cudaEventRecord(st->ev[slot], st->stream);
             } else if (e == cudaSuccess) {
@@ -531,10 +539,20 @@ int staged_copy(SmjCtx *c, char *dev, char *host, size_t bytes, int dir) {
         }
     };
     const int nthreads = stager_threads(nchunks);
+    const bool dbg = getenv("SMJ_STAGE_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     for (int t = 1; t < nthreads; t++) pool.emplace_back(worker);
     worker();
     for (auto &t : pool) t.join();
+    if (dbg) {
+        const auto t_enq = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(st->stream);
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "[smj_b200] staged copy of %.0f MB: all chunks enqueued after %.2f ms, DMA done after %.2f ms (%d threads)\n",
+                bytes / 1e6, std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_done - t_begin).count(), nthreads);
+    }
     if (err.load()) return smj_fail((cudaError_t)err.load(), "staged_copy", __FILE__, __LINE__);
     // later work on the compute stream must see the uploaded data
     SMJ_CHECK(cudaEventRecord(st->fence, st->stream));
