@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import importlib
 import os
+import sys
 import time
 
 import numpy as np
@@ -128,28 +129,46 @@ def run(args, smj):
 def _bind_to_gpu_numa_node(local: int) -> str:
     """Pinned host slices should live on the NUMA node the GPU hangs off: eight ranks that all pin
     memory on node 0 (torchrun's default affinity) share one memory controller and one socket's PCIe
-    root.  Best effort: moves this process to the cpus of the GPU's node before the buffers are
-    allocated (first touch), if the cpuset allows it."""
+    root.  Best effort, before the buffers are allocated: (1) move this process to the cpus of the
+    GPU's node if the cpuset allows it (first touch then places the pages); (2) in any case ask the
+    kernel to PREFER that node for this process's new pages (set_mempolicy(MPOL_PREFERRED): works
+    without cpus on the node, falls back to any node when it is not allowed).  Returns what happened
+    (reported in the bench line)."""
     try:
-        bus = torch.cuda.get_device_properties(local).pci_bus_id
-        dom = torch.cuda.get_device_properties(local).pci_domain_id
-        dev_id = torch.cuda.get_device_properties(local).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        prop = torch.cuda.get_device_properties(local)
+        path = f"/sys/bus/pci/devices/{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0/numa_node"
         node = int(open(path).read().strip())
-        if node < 0:
-            return "numa node unknown"
+    except Exception as exc:  # noqa: BLE001
+        return f"gpu numa node unknown ({type(exc).__name__})"
+    if node < 0:
+        return "gpu numa node unknown (-1)"
+    what = [f"gpu on node {node}"]
+    try:
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus += list(range(int(lo), int(hi or lo) + 1))
         os.sched_setaffinity(0, cpus)
-        return f"node {node} ({len(cpus)} cpus)"
+        what.append(f"cpus bound ({len(cpus)})")
     except Exception as exc:  # noqa: BLE001
-        return f"not bound ({type(exc).__name__})"
+        what.append(f"cpus not bound ({type(exc).__name__})")
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86-64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 1024)
+        what.append("memory preferred on node" if rc == 0 else f"set_mempolicy failed (errno {ctypes.get_errno()})")
+    except Exception as exc:  # noqa: BLE001
+        what.append(f"set_mempolicy unavailable ({type(exc).__name__})")
+    return ", ".join(what)
 
 
 def _e2e(args, r, s, count, dev, one_step, sync_all, n):
-    _bind_to_gpu_numa_node(dev.index)
+    numa = _bind_to_gpu_numa_node(dev.index)
+    if os.environ.get("SMJ_VERBOSE"):
+        print(f"[bench] rank {dist.get_rank()}: {numa}", file=sys.stderr)
     hr = torch.empty(count, dtype=torch.int64).pin_memory()
     hs = torch.empty(count, dtype=torch.int64).pin_memory()
     hr.copy_(r[:count])
