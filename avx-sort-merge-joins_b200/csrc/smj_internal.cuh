@@ -56,3 +56,6 @@ int  smj_bucket_join(SmjCtx *ctx, const BucketSet &R, const BucketSet &S, u32 lo
 bool smj_bucket_join_valid(const u64 *h_state, u32 lbits);
 extern const u64 MSD_STATE_INIT[16];
 int smj_merge_join_acc(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *s, u64 ns, u64 *acc, int semi = 0);
+// ---- smj_mpsm.cu: all sorted runs of S against the sorted R in one pass over R (*used = 0: not applicable)
+int smj_mpsm_probe(SmjCtx *ctx, const u64 *r, u64 nr, const u64 *const *runs, const u64 *lens, u32 nruns, u64 *acc,
+                   int *used);

@@ -1435,7 +1435,11 @@ extern "C" int smjdev_join(int algo, const uint64_t *r_, uint64_t nr, const uint
             if ((rc = smj_lsd_sort(ctx, r, aR, bR, nr, 2, &sr))) return rc;
             if ((rc = sort_runs(ctx, s, aS, bS, ns, nruns, ps, ls))) return rc;
             t_sort = t_merge = tm.mark();
-            for (size_t i = 0; i < ps.size(); i++)
+            // all runs against R in one pass over R (smj_mpsm.cu); one merge-path scan per run when that
+            // does not apply (long runs of equal keys in R, heavy hitters in S)
+            int probed = 0;
+            if ((rc = smj_mpsm_probe(ctx, sr, nr, ps.data(), ls.data(), (u32)ps.size(), acc, &probed))) return rc;
+            for (size_t i = 0; i < ps.size() && !probed; i++)
                 if ((rc = smj_merge_join_acc(ctx, sr, nr, ps[i], ls[i], acc))) return rc;
             t_join = tm.mark();
         }

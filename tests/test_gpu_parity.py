@@ -497,6 +497,40 @@ def _device_mway_stats(smj, r, s):
     return st
 
 
+def test_mpsm_one_pass_probe_and_its_fallbacks(smj, orc, monkeypatch):
+    """P-MPSM joins all sorted runs of S against the sorted R in ONE pass over R (csrc/smj_mpsm.cu:
+    R tiles that end on key boundaries, the pieces of every run looked up by binary search).  Same
+    count and checksum as the oracle and as one merge-path scan per run (SMJ_MPSM_PER_RUN=1) for:
+    a primary-key R, short runs of duplicates in R (walked inside a tile), an R run longer than a
+    tile (flag -> per-run scans), a hot key of S that would land on one CTA (flag -> per-run scans),
+    S keys below / above R's key range, and more runs than items in a piece."""
+    rng = np.random.default_rng(77)
+    n = 400_000
+    pk = orc.gen_unique(n, 3)
+    cases = {
+        "pk_fk": (pk, orc.gen_fk(3 * n + 11, n, 4)),
+        "dups_r": (ol.rand_items(rng, n, n // 6), ol.rand_items(rng, 2 * n, n // 6)),
+        "long_run_r": (np.concatenate([pk[: n // 2], np.full(6000, (np.uint64(77) << np.uint64(32)) | np.uint64(9))]),
+                       orc.gen_fk(n, n, 5)),
+        "outside": (pk + (np.uint64(1000) << np.uint64(32)), ol.rand_items(rng, n, n + 3000)),
+    }
+    hot = orc.gen_fk(1_300_000, n, 6)
+    hot[: 1_200_000] = (hot[: 1_200_000] & np.uint64(0xFFFFFFFF)) | (np.uint64(4242) << np.uint64(32))
+    cases["hot_s"] = (pk, hot)
+    for name, (r, s) in cases.items():
+        exp = orc.join_bruteforce(r, s)
+        for nruns in (4, 64):
+            for per_run in (False, True):
+                if per_run:
+                    monkeypatch.setenv("SMJ_MPSM_PER_RUN", "1")
+                dr, ds = smj.DeviceBuffer.from_host(r), smj.DeviceBuffer.from_host(s)
+                st = smj.device_join(smj.ALGO_MPSM, dr, ds, nruns)
+                dr.free()
+                ds.free()
+                monkeypatch.delenv("SMJ_MPSM_PER_RUN", raising=False)
+                assert (st.matches, st.checksum) == exp, (name, nruns, per_run)
+
+
 def test_mway_optimistic_partition_and_its_exact_repeats(smj, orc, monkeypatch):
     """The histogram-free partition passes (sampled bin capacities, fixed second-level slots):
     same count and checksum as the exact passes and as the oracle; when a region overflows (forced
