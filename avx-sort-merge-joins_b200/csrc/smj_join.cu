@@ -447,9 +447,9 @@ __global__ void __launch_bounds__(BJ_WARPS * 32, 4) k_bucket_join(const u64 *__r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // range != null (join group): only the buckets [range[0], range[1]) can hold anything on this GPU
     u32 first_bucket = 0;
-    if (range) {
-        first_bucket = range[0];
-        nbuckets     = range[1];
+    if (range) {  // (clamped: a layout that was abandoned half way must not send the walk out of bounds)
+        nbuckets     = min(range[1], nbuckets);
+        first_bucket = min(range[0], nbuckets);
     }
     const u32 slots = 1u << lbits, mask = slots - 1;
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
